@@ -1,0 +1,388 @@
+"""ctypes binding of include/goblin_b200.h (the C ABI of libgoblin_b200.so).
+
+Thin by design: every function here forwards to one extern "C" entry point and
+raises GoblinError on a non-zero status.  There is no Python or CPU fallback;
+if the shared library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoblin_b200.so")
+
+
+class GoblinError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"goblin_b200 error {code}: {msg}")
+        self.code = code
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("offset", C.c_uint32),
+                ("nprims", C.c_uint8), ("axis", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class Model(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("radius", C.c_float), ("material", C.c_int32),
+                ("area_light", C.c_int32), ("node_offset", C.c_uint32), ("node_count", C.c_uint32),
+                ("tri_offset", C.c_uint32), ("tri_count", C.c_uint32), ("vert_offset", C.c_uint32),
+                ("vert_count", C.c_uint32), ("has_normal", C.c_int32), ("has_uv", C.c_int32),
+                ("is_camera_lens", C.c_int32), ("bound", C.c_float * 6)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("to_world", C.c_float * 12), ("to_object", C.c_float * 12), ("aabb", C.c_float * 6),
+                ("model", C.c_int32), ("pad", C.c_int32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
+                ("k", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("color", C.c_float * 3), ("position", C.c_float * 3),
+                ("direction", C.c_float * 3), ("cos_theta_max", C.c_float),
+                ("cos_falloff_start", C.c_float), ("geom_kind", C.c_int32), ("radius", C.c_float),
+                ("area", C.c_float), ("to_world", C.c_float * 12), ("to_object", C.c_float * 12),
+                ("instance", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("orientation", C.c_float * 4), ("proj00", C.c_float),
+                ("proj11", C.c_float), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
+
+
+class FilmDesc(C.Structure):
+    _fields_ = [("xres", C.c_int32), ("yres", C.c_int32), ("xstart", C.c_int32), ("xcount", C.c_int32),
+                ("ystart", C.c_int32), ("ycount", C.c_int32), ("sx0", C.c_int32), ("sx1", C.c_int32),
+                ("sy0", C.c_int32), ("sy1", C.c_int32), ("filter_width", C.c_float * 2),
+                ("filter_table", C.c_float * 256)]
+
+
+class RenderSetting(C.Structure):
+    _fields_ = [("method", C.c_int32), ("spp", C.c_int32), ("max_ray_depth", C.c_int32),
+                ("ao_sample_num", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("top_nodes", C.POINTER(BvhNode)), ("n_top_nodes", C.c_uint32),
+                ("top_order", C.POINTER(C.c_uint32)), ("instances", C.POINTER(Instance)),
+                ("n_instances", C.c_uint32), ("models", C.POINTER(Model)), ("n_models", C.c_uint32),
+                ("model_nodes", C.POINTER(BvhNode)), ("n_model_nodes", C.c_uint64),
+                ("model_order", C.POINTER(C.c_uint32)), ("tri_index", C.POINTER(C.c_uint32)),
+                ("n_tris", C.c_uint64), ("vert_pos", C.POINTER(C.c_float)),
+                ("vert_nrm", C.POINTER(C.c_float)), ("vert_uv", C.POINTER(C.c_float)),
+                ("n_verts", C.c_uint64), ("materials", C.POINTER(Material)), ("n_materials", C.c_uint32),
+                ("lights", C.POINTER(Light)), ("n_lights", C.c_uint32),
+                ("light_power", C.POINTER(C.c_float)), ("light_cdf", C.POINTER(C.c_float)),
+                ("world_bound", C.c_float * 6), ("camera", Camera), ("film", FilmDesc),
+                ("setting", RenderSetting)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("spp_total", C.c_int32), ("spp_begin", C.c_int32),
+                ("spp_end", C.c_int32), ("max_ray_depth", C.c_int32), ("method", C.c_int32),
+                ("ao_sample_num", C.c_int32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("camera_samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_any", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
+                ("instances_entered", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("eps", np.float32), ("inst", np.int32), ("prim", np.int32)])
+NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.uint32),
+                       ("nprims", np.uint8), ("axis", np.uint8), ("pad", np.uint8, 2)])
+
+# every symbol include/goblin_b200.h declares
+EXPORTS = [
+    "gb_scene_load_json", "gb_scene_load_json_string", "gb_scene_destroy", "gb_scene_get_desc",
+    "gb_scene_output_path", "gb_bvh_build", "gb_device_count", "gb_create", "gb_destroy",
+    "gb_upload_scene", "gb_trace_closest", "gb_trace_any", "gb_trace_closest_device",
+    "gb_trace_any_device", "gb_camera_rays", "gb_li", "gb_render", "gb_film_clear",
+    "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image",
+    "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
+    "gb_last_kernel_ms", "gb_last_error", "gb_version",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libgoblin_b200.so (once).  Raises OSError if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C goblin_b200/csrc`")
+        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        l.gb_last_error.restype = C.c_char_p
+        l.gb_version.restype = C.c_char_p
+        l.gb_scene_output_path.restype = C.c_char_p
+        l.gb_scene_output_path.argtypes = [C.c_void_p]
+        l.gb_scene_destroy.restype = None
+        l.gb_scene_destroy.argtypes = [C.c_void_p]
+        l.gb_scene_load_json.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        l.gb_scene_load_json_string.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        l.gb_scene_get_desc.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+        l.gb_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+        l.gb_device_count.argtypes = [C.POINTER(C.c_int)]
+        l.gb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        l.gb_destroy.argtypes = [C.c_void_p]
+        l.gb_upload_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+        l.gb_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gb_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gb_trace_closest_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gb_trace_any_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gb_camera_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.gb_li.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        l.gb_render.argtypes = [C.c_void_p, C.POINTER(RenderParams)]
+        l.gb_film_clear.argtypes = [C.c_void_p]
+        l.gb_film_download.argtypes = [C.c_void_p, C.c_void_p]
+        l.gb_film_upload.argtypes = [C.c_void_p, C.c_void_p]
+        l.gb_film_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        l.gb_film_write.argtypes = [C.c_void_p, C.c_char_p]
+        l.gb_write_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+        l.gb_synchronize.argtypes = [C.c_void_p]
+        l.gb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.gb_enable_counters.argtypes = [C.c_void_p, C.c_int]
+        l.gb_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        l.gb_reset_counters.argtypes = [C.c_void_p]
+        l.gb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GoblinError(rc, lib().gb_last_error().decode(errors="replace"))
+
+
+def _np(ptr, n, dtype):
+    """View n items behind a ctypes pointer as a numpy array (no copy)."""
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    buf = (C.c_uint8 * (int(n) * np.dtype(dtype).itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype)
+
+
+class Scene:
+    """Host-side flattened scene: ContextLoader::load of the reference
+    (src/GoblinContextLoader.cpp:447-503)."""
+
+    def __init__(self, path=None, json_text=None, scene_dir=None):
+        self._h = C.c_void_p()
+        if path is not None:
+            check(lib().gb_scene_load_json(os.fsencode(path), C.byref(self._h)))
+        else:
+            check(lib().gb_scene_load_json_string(json_text.encode(), os.fsencode(scene_dir or "."),
+                                                  C.byref(self._h)))
+        self.desc = SceneDesc()
+        check(lib().gb_scene_get_desc(self._h, C.byref(self.desc)))
+
+    def close(self):
+        if self._h:
+            lib().gb_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def output_path(self):
+        return lib().gb_scene_output_path(self._h).decode()
+
+    # numpy views of the flattened arrays (valid while the Scene is alive)
+    def top_nodes(self):
+        return _np(self.desc.top_nodes, self.desc.n_top_nodes, NODE_DTYPE)
+
+    def top_order(self):
+        return _np(self.desc.top_order, self.desc.n_instances, np.uint32)
+
+    def model_nodes(self):
+        return _np(self.desc.model_nodes, self.desc.n_model_nodes, NODE_DTYPE)
+
+    def model_order(self):
+        return _np(self.desc.model_order, self.desc.n_tris, np.uint32)
+
+    def tri_index(self):
+        return _np(self.desc.tri_index, self.desc.n_tris * 3, np.uint32).reshape(-1, 3)
+
+    def vert_pos(self):
+        return _np(self.desc.vert_pos, self.desc.n_verts * 3, np.float32).reshape(-1, 3)
+
+    def vert_nrm(self):
+        return _np(self.desc.vert_nrm, self.desc.n_verts * 3, np.float32).reshape(-1, 3)
+
+    def vert_uv(self):
+        return _np(self.desc.vert_uv, self.desc.n_verts * 2, np.float32).reshape(-1, 2)
+
+    def instances(self):
+        return [self.desc.instances[i] for i in range(self.desc.n_instances)]
+
+    def models(self):
+        return [self.desc.models[i] for i in range(self.desc.n_models)]
+
+    def lights(self):
+        return [self.desc.lights[i] for i in range(self.desc.n_lights)]
+
+    def light_cdf(self):
+        return _np(self.desc.light_cdf, self.desc.n_lights + 1, np.float32)
+
+    def light_power(self):
+        return _np(self.desc.light_power, self.desc.n_lights, np.float32)
+
+    def sample_range(self):
+        f = self.desc.film
+        return f.sx0, f.sx1, f.sy0, f.sy1
+
+    def spp_squared(self, spp=None):
+        """spp rounded up to a perfect square (src/GoblinSampler.cpp:72)."""
+        spp = self.desc.setting.spp if spp is None else spp
+        root = int(np.ceil(np.sqrt(np.float32(spp))))
+        return root * root
+
+    def camera_samples(self, spp=None):
+        sx0, sx1, sy0, sy1 = self.sample_range()
+        return (sx1 - sx0) * (sy1 - sy0) * self.spp_squared(spp)
+
+
+def bvh_build(aabbs):
+    """BVH::BVH on raw boxes (n x 6 float32) -> (nodes, order)."""
+    aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
+    n = aabbs.shape[0]
+    nodes = np.zeros(max(2 * n, 1), dtype=NODE_DTYPE)
+    order = np.zeros(max(n, 1), dtype=np.uint32)
+    cnt = C.c_uint32()
+    check(lib().gb_bvh_build(aabbs.ctypes.data, n, nodes.ctypes.data, C.byref(cnt), order.ctypes.data))
+    return nodes[:cnt.value].copy(), order[:n].copy()
+
+
+class Context:
+    """One GPU.  Every method is a direct call through the C ABI."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().gb_create(device, C.byref(self._h)))
+        self.scene = None
+
+    def close(self):
+        if self._h:
+            lib().gb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, scene):
+        check(lib().gb_upload_scene(self._h, C.byref(scene.desc)))
+        self.scene = scene
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        check(lib().gb_trace_closest(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data))
+        return hits
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        occ = np.zeros(rays.shape[0], dtype=np.uint8)
+        check(lib().gb_trace_any(self._h, rays.ctypes.data, rays.shape[0], occ.ctypes.data))
+        return occ
+
+    def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr):
+        check(lib().gb_trace_closest_device(self._h, d_rays_ptr, n, d_hits_ptr))
+
+    def trace_any_device(self, d_rays_ptr, n, d_occ_ptr):
+        check(lib().gb_trace_any_device(self._h, d_rays_ptr, n, d_occ_ptr))
+
+    def camera_rays(self, samples):
+        samples = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 4)
+        rays = np.zeros((samples.shape[0], 8), dtype=np.float32)
+        check(lib().gb_camera_rays(self._h, samples.ctypes.data, samples.shape[0], rays.ctypes.data))
+        return rays
+
+    def li(self, samples):
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        n, row = samples.shape
+        out = np.zeros((n, 3), dtype=np.float32)
+        check(lib().gb_li(self._h, samples.ctypes.data, n, row, out.ctypes.data))
+        return out
+
+    def render(self, seed=1, spp_total=None, spp_begin=0, spp_end=None, max_ray_depth=0, method=-1,
+               ao_sample_num=0):
+        if spp_total is None:
+            spp_total = self.scene.spp_squared()
+        if spp_end is None:
+            spp_end = spp_total
+        p = RenderParams(seed, spp_total, spp_begin, spp_end, max_ray_depth, method, ao_sample_num)
+        check(lib().gb_render(self._h, C.byref(p)))
+
+    def film_clear(self):
+        check(lib().gb_film_clear(self._h))
+
+    def film_download(self):
+        f = self.scene.desc.film
+        out = np.zeros((f.yres, f.xres, 4), dtype=np.float32)
+        check(lib().gb_film_download(self._h, out.ctypes.data))
+        return out
+
+    def film_upload(self, rgbw):
+        rgbw = np.ascontiguousarray(rgbw, dtype=np.float32)
+        check(lib().gb_film_upload(self._h, rgbw.ctypes.data))
+
+    def film_device_ptr(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        check(lib().gb_film_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def film_write(self, path):
+        check(lib().gb_film_write(self._h, os.fsencode(path)))
+
+    def synchronize(self):
+        check(lib().gb_synchronize(self._h))
+
+    def stream(self):
+        s = C.c_void_p()
+        check(lib().gb_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def enable_counters(self, on=True):
+        check(lib().gb_enable_counters(self._h, 1 if on else 0))
+
+    def counters(self):
+        c = Counters()
+        check(lib().gb_get_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+    def reset_counters(self):
+        check(lib().gb_reset_counters(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(lib().gb_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+
+def device_count():
+    n = C.c_int()
+    check(lib().gb_device_count(C.byref(n)))
+    return n.value
+
+
+def write_image(path, rgbw):
+    rgbw = np.ascontiguousarray(rgbw, dtype=np.float32)
+    check(lib().gb_write_image(os.fsencode(path), rgbw.ctypes.data, rgbw.shape[1], rgbw.shape[0]))

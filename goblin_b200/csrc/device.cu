@@ -1,0 +1,1305 @@
+// sm_100a kernels, the device context and the GPU half of the C ABI.
+//
+// Execution model (DESIGN.md has the long form):
+//   * gb_trace_*: one persistent kernel; warps pull 32-ray batches from a
+//     global cursor, each thread walks the reference's two-level BVH with a
+//     private stack column in shared memory, nodes arrive as two 128-bit
+//     read-only loads.
+//   * gb_render: a wavefront path tracer over "waves" of a few million camera
+//     samples that live in SoA path-state arrays:
+//       raygen -> [extend -> shade<material> x3 -> shadow] x (depth-1)
+//              -> extend -> emission-only shade -> film accumulate
+//     extend and shadow are the persistent traversal kernels; shade kernels are
+//     binned by material through index queues that the extend kernel fills
+//     with warp-aggregated atomics; the film kernel splats a pixel tile in
+//     shared memory and flushes it with one vector atomic per pixel.
+// No tensor cores, no TMA: traversal is a dependent gather of 32-byte nodes,
+// not a dense contraction (north_star).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "capi_util.h"
+#include "device_scene.h"
+#include "image_io.h"
+#include "rt_core.cuh"
+#include "shade.cuh"
+
+namespace gb {
+
+constexpr int kTraceBlock = 256;   // threads per traversal block
+constexpr int kShadeBlock = 128;
+constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
+constexpr int kCtrStride = 16;     // counters per bounce
+enum { C_EXTEND = 0, C_EXTEND_HEAD = 1, C_MAT0 = 2, C_SHADOW = 5, C_SHADOW_HEAD = 6, C_AO_HEAD = 7 };
+enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_COUNT = 8 };
+
+struct PathState {
+    float4* rayO;    // o.xyz, mint
+    float4* rayD;    // d.xyz, unused
+    float4* hit;     // t, b1, b2, unused
+    int2* hitId;     // instance slot (-1 = miss), triangle slot
+    float4* thr;     // throughput rgb
+    float4* L;       // accumulated radiance rgb, AO: unoccluded count in w
+    float4* pend;    // pending emission weight rgb, __int_as_float(light) in w
+    float4* shO;     // shadow ray o.xyz, mint
+    float4* shD;     // shadow ray d.xyz, maxt
+    float4* shC;     // contribution rgb, __int_as_float(path)
+    unsigned int* qExtend[2];
+    unsigned int* qMat[3];
+    unsigned int* aoCount;
+};
+
+struct WaveParams {
+    unsigned int nPaths;
+    int y0;          // first sample-range row of the wave
+    int width;       // sample-range width
+    int rows;
+    int sppBegin;    // first sample index of this call
+    int nSpp;        // samples per pixel in this wave
+    int sppTotal;    // samples per pixel of the whole job
+    int root;        // sqrt(sppTotal): image-plane strata per axis
+    int maxDepth;
+    int aoSamples;
+    int aoRoot;
+};
+
+__device__ __forceinline__ unsigned long long sampleIdOf(const DeviceScene& sc, const WaveParams& wp, unsigned int i,
+    int* px, int* py, int* s) {
+    unsigned int pix = i / (unsigned int)wp.nSpp;
+    unsigned int k = i - pix * (unsigned int)wp.nSpp;
+    unsigned int row = pix / (unsigned int)wp.width;
+    unsigned int col = pix - row * (unsigned int)wp.width;
+    *px = sc.sx0 + (int)col;
+    *py = wp.y0 + (int)row;
+    *s = wp.sppBegin + (int)k;
+    unsigned long long pixelIndex = (unsigned long long)(*py - sc.sy0) * (unsigned long long)wp.width + col;
+    return pixelIndex * (unsigned long long)wp.sppTotal + (unsigned long long)(*s);
+}
+
+// Sampler::requestSamples' image-plane stratification (GoblinSampler.cpp:
+// 142-143,192-195 with stratifiedUniform2D(buffer, 1)): sample s of a pixel sits
+// in cell (s % root, s / root) of a root x root jittered grid.
+__device__ __forceinline__ void imagePosition(const WaveParams& wp, int px, int py, int s, float4 u, bool tableDriven,
+    float* imageX, float* imageY) {
+    if (tableDriven) { *imageX = u.x; *imageY = u.y; return; }
+    float sub = 1.0f / (float)wp.root;
+    int cx = s % wp.root, cy = s / wp.root;
+    *imageX = (float)px + ((float)cx + u.x) * sub;
+    *imageY = (float)py + ((float)cy + u.y) * sub;
+}
+
+// ------------------------------------------------------------ stand-alone trace
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned int n, gb_hit* __restrict__ hits,
+    unsigned char* __restrict__ occluded, unsigned int* head, unsigned long long* stats) {
+    extern __shared__ unsigned int s_stack[];
+    SmemStack st{s_stack + threadIdx.x, blockDim.x};
+    const unsigned int lane = threadIdx.x & 31;
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(head, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned int i = base + lane;
+        if (i < n) {
+            const float4* r = reinterpret_cast<const float4*>(rays + i);
+            float4 a = __ldg(r), b = __ldg(r + 1);
+            float3 o = make3(a.x, a.y, a.z), d = make3(a.w, b.x, b.y);
+            HitRec h;
+            bool found = traceScene<ANY, STATS>(sc, o, d, b.z, b.w, &h, st, &ts);
+            if (ANY) {
+                occluded[i] = found ? 1 : 0;
+            } else {
+                gb_hit out;
+                if (found) {
+                    int4 sh = __ldg(sc.instShade + h.inst);
+                    int4 info = __ldg(sc.instInfo + h.inst);
+                    out.t = h.t;
+                    out.eps = 1e-3f * h.t;
+                    out.inst = sh.x;
+                    out.prim = 0;
+                    if (info.x == GB_GEOM_MESH) {
+                        out.prim = (int)__float_as_uint(__ldg(sc.triRec + 3 * (size_t)(info.z + h.prim) + 2).y);
+                    }
+                } else {
+                    out.t = 0.0f; out.eps = 0.0f; out.inst = -1; out.prim = -1;
+                }
+                *reinterpret_cast<float4*>(hits + i) = *reinterpret_cast<float4*>(&out);
+            }
+            ++done;
+        }
+    }
+    // one 64-bit atomic per warp for the ray count; traversal statistics only when asked
+    unsigned int total = done;
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+    if (lane == 0 && total) atomicAdd(stats + (ANY ? S_RAYS_ANY : S_RAYS_CLOSEST), (unsigned long long)total);
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
+            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
+            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+        }
+    }
+}
+
+// ------------------------------------------------------------------- raygen
+__global__ void k_raygen(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr,
+    unsigned long long* stats) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ctr[C_EXTEND] = wp.nPaths;
+        atomicAdd(stats + S_SAMPLES, (unsigned long long)wp.nPaths);
+    }
+    if (i >= wp.nPaths) return;
+    int px, py, s;
+    unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
+    float4 u = src.block(id, i, 0);
+    float imageX, imageY;
+    imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
+    float3 o, d;
+    cameraRay(sc, imageX, imageY, u.z, u.w, &o, &d);
+    ps.rayO[i] = make_float4(o.x, o.y, o.z, 1e-3f); // ray->mint = 1e-3f
+    ps.rayD[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    ps.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    ps.pend[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+    if (ps.aoCount) ps.aoCount[i] = 0u;
+}
+
+// ------------------------------------------------------------------- extend
+// Scene::intersect for every queued path, then bin the hits by material.
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
+    unsigned long long* stats) {
+    extern __shared__ unsigned int s_stack[];
+    SmemStack st{s_stack + threadIdx.x, blockDim.x};
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int n = ctr[C_EXTEND];
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(ctr + C_EXTEND_HEAD, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned int j = base + lane;
+        int bin = -1;
+        unsigned int i = 0;
+        if (j < n) {
+            i = queue ? __ldg(queue + j) : j;
+            float4 a = ps.rayO[i], b = ps.rayD[i];
+            HitRec h;
+            bool found = traceScene<false, STATS>(sc, make3(a.x, a.y, a.z), make3(b.x, b.y, b.z), a.w, INFINITY,
+                &h, st, &ts);
+            ps.hit[i] = make_float4(h.t, h.b1, h.b2, 0.0f);
+            ps.hitId[i] = make_int2(h.inst, h.prim);
+            if (found) {
+                if (singleBin) bin = 0;
+                else {
+                    int mat = __ldg(sc.instShade + h.inst).z;
+                    bin = __float_as_int(__ldg(&sc.materials[mat].kdType).w);
+                }
+            }
+            ++done;
+        }
+        // warp-aggregated append to the material queues
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            unsigned int mask = __ballot_sync(0xffffffffu, bin == m);
+            if (mask) {
+                unsigned int leader = __ffs(mask) - 1;
+                unsigned int start = 0;
+                if (lane == leader) start = atomicAdd(ctr + C_MAT0 + m, __popc(mask));
+                start = __shfl_sync(0xffffffffu, start, leader);
+                if (bin == m) ps.qMat[m][start + __popc(mask & ((1u << lane) - 1))] = i;
+            }
+        }
+    }
+    unsigned int total = done;
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+    if (lane == 0 && total) atomicAdd(stats + S_RAYS_CLOSEST, (unsigned long long)total);
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
+            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
+            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+        }
+    }
+}
+
+// ------------------------------------------------------------------- shadow
+// Scene::occluded for every queued shadow segment; unoccluded segments add
+// their (already weighted) contribution to the owning path.
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats) {
+    extern __shared__ unsigned int s_stack[];
+    SmemStack st{s_stack + threadIdx.x, blockDim.x};
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int n = ctr[C_SHADOW];
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(ctr + C_SHADOW_HEAD, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned int j = base + lane;
+        if (j < n) {
+            float4 a = ps.shO[j], b = ps.shD[j];
+            HitRec h;
+            bool occ = traceScene<true, STATS>(sc, make3(a.x, a.y, a.z), make3(b.x, b.y, b.z), a.w, b.w, &h, st, &ts);
+            if (!occ) {
+                float4 c = ps.shC[j];
+                unsigned int i = (unsigned int)__float_as_int(c.w);
+                float4 L = ps.L[i]; // one shadow segment per path per bounce: no race
+                L.x += c.x; L.y += c.y; L.z += c.z;
+                ps.L[i] = L;
+            }
+            ++done;
+        }
+    }
+    unsigned int total = done;
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+    if (lane == 0 && total) atomicAdd(stats + S_RAYS_ANY, (unsigned long long)total);
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
+            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
+            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+        }
+    }
+}
+
+// -------------------------------------------------------------------- shade
+// One bounce of PathTracer::Li (GoblinPathtracer.cpp:76-172) for the paths whose
+// hit carries material MAT.  `bounce` is the reference's loop variable; with
+// emissionOnly the kernel only resolves the pending BSDF-sampled emission
+// (the reference's trace #4 of the last iteration).
+template <int MAT>
+__global__ void __launch_bounds__(kShadeBlock)
+k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounce, int emissionOnly,
+    unsigned int* ctr, unsigned int* ctrNext, unsigned int* qNext) {
+    const unsigned int n = ctr[C_MAT0 + MAT];
+    const unsigned int lane = threadIdx.x & 31;
+    for (unsigned int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; j0 < n; j0 += gridDim.x * blockDim.x) {
+        unsigned int j = j0 + lane;
+        bool alive = false;   // continues to the next extend
+        bool shadow = false;  // emits a shadow segment
+        unsigned int i = 0;
+        float3 shO = make3(0, 0, 0), shD = make3(0, 0, 0), shC = make3(0, 0, 0);
+        float shMint = 0.0f, shMaxt = 0.0f;
+        if (j < n) {
+            i = __ldg(ps.qMat[MAT] + j);
+            float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
+            int2 hid = ps.hitId[i];
+            HitRec h;
+            h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
+            float3 o = make3(ro.x, ro.y, ro.z), d = make3(rd.x, rd.y, rd.z);
+            Frag fr = buildFragment(sc, h, o, d);
+            float3 wo = -d;
+            float4 Lacc = ps.L[i];
+            // emitted radiance seen through this segment
+            if (fr.areaLight >= 0) {
+                float4 lc = __ldg(&sc.lights[fr.areaLight].colorType);
+                bool facing = dot3(fr.n, wo) > 0.0f; // AreaLight::L
+                if (bounce == 0) { // Li += intersection.Le(-ray.d), GoblinPathtracer.cpp:67
+                    if (facing) { Lacc.x += lc.x; Lacc.y += lc.y; Lacc.z += lc.z; }
+                } else {
+                    float4 pd = ps.pend[i]; // BSDF-sampled MIS term, GoblinPathtracer.cpp:148-155
+                    if (__float_as_int(pd.w) == fr.areaLight && facing) {
+                        Lacc.x += pd.x * lc.x; Lacc.y += pd.y * lc.y; Lacc.z += pd.z * lc.z;
+                    }
+                }
+            }
+            if (!emissionOnly) {
+                int px, py, s;
+                unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
+                float4 uA = src.block(id, i, 1u + 2u * (unsigned int)bounce);
+                float4 uB = src.block(id, i, 2u + 2u * (unsigned int)bounce);
+                float pickPdf;
+                int li = pickLight(sc, uB.z, &pickPdf);
+                float4 tv = ps.thr[i];
+                float3 thr = make3(tv.x, tv.y, tv.z);
+                float eps = 1e-3f * h.t;
+                const DeviceMaterial& mat = sc.materials[fr.material];
+                DeviceMaterial m;
+                m.kdType = __ldg(&mat.kdType);
+                m.ktEta = __ldg(&mat.ktEta);
+                if (MAT == GB_MAT_LAMBERT) { // specular BSDFs evaluate to black: no light sample survives
+                    LightSampleResult ls = sampleLight(sc, li, fr.p, eps, uA.y, uA.z);
+                    if (!isBlack(ls.L) && ls.pdf > 0.0f) {
+                        float3 f = lambertEval(m, fr.n, wo, ls.wi);
+                        if (!isBlack(f)) {
+                            float3 c = mul3(f, ls.L) * absdot3(fr.n, ls.wi);
+                            if (!ls.delta) {
+                                float bsdfPdf = lambertPdf(fr.n, wo, ls.wi);
+                                c = c * powerHeuristic(ls.pdf, bsdfPdf);
+                            }
+                            c = div3(c, ls.pdf);
+                            shC = div3(mul3(thr, c), pickPdf);
+                            shO = fr.p; shD = ls.wi; shMint = eps; shMaxt = ls.maxt;
+                            shadow = true;
+                        }
+                    }
+                }
+                BsdfSample bs = sampleBsdf(m, MAT, fr, wo, uA.w, uB.x, uB.y);
+                float4 pendOut = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+                if (!isBlack(bs.f) && bs.pdf > 0.0f) {
+                    float fWeight = 1.0f;
+                    if (!bs.specular) fWeight = powerHeuristic(bs.pdf, lightPdf(sc, li, fr.p, bs.wi));
+                    int ltype = __float_as_int(__ldg(&sc.lights[li].colorType).w);
+                    if (ltype == GB_LIGHT_AREA) {
+                        float3 w = div3(bs.f * absdot3(bs.wi, fr.n) * fWeight, bs.pdf);
+                        float3 pw = div3(mul3(thr, w), pickPdf);
+                        pendOut = make_float4(pw.x, pw.y, pw.z, __int_as_float(li));
+                    }
+                }
+                if (!(isBlack(bs.f) || bs.pdf == 0.0f)) {
+                    float3 w = div3(bs.f * absdot3(bs.wi, fr.n), bs.pdf);
+                    thr = mul3(thr, w);
+                    ps.thr[i] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                    ps.pend[i] = pendOut;
+                    ps.rayO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, eps);
+                    ps.rayD[i] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.0f);
+                    alive = true;
+                }
+            }
+            ps.L[i] = Lacc;
+        }
+        // warp-aggregated appends: next extend queue, shadow queue
+        unsigned int mask = __ballot_sync(0xffffffffu, alive);
+        if (mask) {
+            unsigned int leader = __ffs(mask) - 1, start = 0;
+            if (lane == leader) start = atomicAdd(ctrNext + C_EXTEND, __popc(mask));
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (alive) qNext[start + __popc(mask & ((1u << lane) - 1))] = i;
+        }
+        mask = __ballot_sync(0xffffffffu, shadow);
+        if (mask) {
+            unsigned int leader = __ffs(mask) - 1, start = 0;
+            if (lane == leader) start = atomicAdd(ctr + C_SHADOW, __popc(mask));
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (shadow) {
+                unsigned int k = start + __popc(mask & ((1u << lane) - 1));
+                ps.shO[k] = make_float4(shO.x, shO.y, shO.z, shMint);
+                ps.shD[k] = make_float4(shD.x, shD.y, shD.z, shMaxt);
+                ps.shC[k] = make_float4(shC.x, shC.y, shC.z, __int_as_float((int)i));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------- AO
+// AORenderer::Li (GoblinAO.cpp:12-37): work item = (hit path, occlusion ray).
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr, unsigned long long* stats) {
+    extern __shared__ unsigned int s_stack[];
+    SmemStack st{s_stack + threadIdx.x, blockDim.x};
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned long long n = (unsigned long long)ctr[C_MAT0] * (unsigned long long)wp.aoSamples;
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    unsigned long long* head = reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD + 1); // 8-byte aligned slot
+    while (true) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(head, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        unsigned long long j = base + lane;
+        if (j < n) {
+            unsigned int q = (unsigned int)(j / (unsigned int)wp.aoSamples);
+            unsigned int a = (unsigned int)(j - (unsigned long long)q * (unsigned int)wp.aoSamples);
+            unsigned int i = __ldg(ps.qMat[0] + q);
+            float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
+            int2 hid = ps.hitId[i];
+            HitRec h;
+            h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
+            Frag fr = buildFragment(sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
+            int px, py, s;
+            unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
+            float2 u = src.aoPair(id, i, a);
+            if (!src.table) { // the reference stratifies the AO directions on a root x root grid
+                float sub = 1.0f / (float)wp.aoRoot;
+                u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
+                u.y = ((float)(a / (unsigned int)wp.aoRoot) + u.y) * sub;
+            }
+            float3 dir = shadeToWorld(makeFrame(fr), uniformSampleHemisphere(u.x, u.y));
+            HitRec hh;
+            bool occ = traceScene<true, STATS>(sc, fr.p, dir, 1e-3f * h.t, INFINITY, &hh, st, &ts);
+            if (!occ) atomicAdd(ps.aoCount + i, 1u);
+            ++done;
+        }
+    }
+    unsigned int total = done;
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+    if (lane == 0 && total) atomicAdd(stats + S_RAYS_ANY, (unsigned long long)total);
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
+            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
+            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
+        }
+        if (lane == 0) {
+            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+        }
+    }
+}
+
+__global__ void k_ao_finish(PathState ps, WaveParams wp) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wp.nPaths) return;
+    float v = 0.0f;
+    if (ps.hitId[i].x >= 0) v = (float)ps.aoCount[i] / (float)wp.aoSamples; // (n - occluded) / n
+    ps.L[i] = make_float4(v, v, v, 0.0f);
+}
+
+// --------------------------------------------------------------------- film
+// ImageTile::addSample (GoblinFilm.cpp:61-90) for a tile of sample-range
+// pixels: splat into a shared-memory tile with halo, then flush each touched
+// film pixel with one 128-bit atomic (the analogue of Film::mergeTile).
+constexpr int kFilmTile = 16;
+
+__global__ void __launch_bounds__(256)
+k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int halo) {
+    extern __shared__ float s_tile[]; // (tile + 2 halo)^2 x 4
+    const int side = kFilmTile + 2 * halo;
+    const int tilesX = (wp.width + kFilmTile - 1) / kFilmTile;
+    const int tx = blockIdx.x % tilesX, ty = blockIdx.x / tilesX;
+    const int col0 = tx * kFilmTile, row0 = ty * kFilmTile; // within the wave's rows
+    for (int k = threadIdx.x; k < side * side * 4; k += blockDim.x) s_tile[k] = 0.0f;
+    __syncthreads();
+    const int cols = min(kFilmTile, wp.width - col0), rows = min(kFilmTile, wp.rows - row0);
+    const int baseX = sc.sx0 + col0 - halo, baseY = wp.y0 + row0 - halo; // film pixel of tile cell (0, 0)
+    const int cropX1 = sc.xstart + sc.xcount - 1, cropY1 = sc.ystart + sc.ycount - 1;
+    for (int r = 0; r < rows; ++r) {
+        const unsigned int rowBase = ((unsigned int)(row0 + r) * (unsigned int)wp.width + (unsigned int)col0) *
+            (unsigned int)wp.nSpp;
+        const int nItems = cols * wp.nSpp;
+        for (int k = threadIdx.x; k < nItems; k += blockDim.x) {
+            unsigned int i = rowBase + (unsigned int)k;
+            float4 L = ps.L[i];
+            if (L.x != L.x || L.y != L.y || L.z != L.z) continue; // NaN samples are discarded, weight included
+            int px, py, s;
+            unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
+            float4 u = src.block(id, i, 0);
+            float imageX, imageY;
+            imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
+            float dImageX = imageX - 0.5f, dImageY = imageY - 0.5f;
+            int x0 = (int)ceilf(dImageX - sc.filterWidthX), x1 = (int)floorf(dImageX + sc.filterWidthX);
+            int y0 = (int)ceilf(dImageY - sc.filterWidthY), y1 = (int)floorf(dImageY + sc.filterWidthY);
+            x0 = max(x0, sc.xstart); x1 = min(x1, cropX1);
+            y0 = max(y0, sc.ystart); y1 = min(y1, cropY1);
+            for (int y = y0; y <= y1; ++y) {
+                for (int x = x0; x <= x1; ++x) {
+                    // FilterTable::evaluate: nearest lower entry of the 16 x 16 table
+                    int iy = min((int)floorf(fabsf(16 * ((float)y - dImageY) / sc.filterWidthY)), 15);
+                    int ix = min((int)floorf(fabsf(16 * ((float)x - dImageX) / sc.filterWidthX)), 15);
+                    float w = __ldg(sc.filterTable + iy * 16 + ix);
+                    int cx = x - baseX, cy = y - baseY;
+                    if (cx < 0 || cy < 0 || cx >= side || cy >= side) continue; // cannot happen: halo covers the filter
+                    float* cell = s_tile + 4 * (cy * side + cx);
+                    atomicAdd(cell + 0, w * L.x);
+                    atomicAdd(cell + 1, w * L.y);
+                    atomicAdd(cell + 2, w * L.z);
+                    atomicAdd(cell + 3, w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < side * side; k += blockDim.x) {
+        float4 v = make_float4(s_tile[4 * k], s_tile[4 * k + 1], s_tile[4 * k + 2], s_tile[4 * k + 3]);
+        if (v.w == 0.0f && v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) continue;
+        int x = baseX + k % side, y = baseY + k / side;
+        if (x < 0 || y < 0 || x >= sc.xres || y >= sc.yres) continue;
+        atomicAdd(film + (size_t)y * sc.xres + x, v);
+    }
+}
+
+__global__ void k_copy_L(PathState ps, unsigned int n, float* out) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 L = ps.L[i];
+    out[3 * i] = L.x; out[3 * i + 1] = L.y; out[3 * i + 2] = L.z;
+}
+
+__global__ void k_camera_rays(DeviceScene sc, const float* samples, unsigned int n, gb_ray* rays) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 o, d;
+    cameraRay(sc, samples[4 * i], samples[4 * i + 1], samples[4 * i + 2], samples[4 * i + 3], &o, &d);
+    gb_ray r;
+    r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
+    r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+    r.mint = 1e-3f;
+    r.maxt = INFINITY;
+    rays[i] = r;
+}
+
+} // namespace gb
+
+// =========================================================================
+// host side of the device context
+// =========================================================================
+using namespace gb;
+
+struct gb_context {
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool haveScene = false;
+    DeviceScene sc{};
+    std::vector<void*> sceneAllocs;
+    gb_render_setting setting{};
+    int stackEntries = 0; // per-thread traversal stack entries this scene needs
+    float4* film = nullptr;
+    size_t filmPixels = 0;
+    // wavefront buffers
+    size_t capacity = 0;
+    PathState ps{};
+    std::vector<void*> waveAllocs;
+    unsigned int* ctr = nullptr; // (kMaxDepthCtr) x kCtrStride
+    unsigned int* traceHead = nullptr;
+    unsigned long long* stats = nullptr;
+    bool statsOn = false;
+    uint64_t launches = 0;
+    int traceGrid = 0, aoGrid = 0;
+    size_t maxWavePaths = 4u << 20;
+};
+
+namespace {
+
+constexpr int kMaxDepthCtr = 66;
+
+#define GB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            return gb::failWith(GB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        }                                                                                      \
+    } while (0)
+
+template <typename T>
+int uploadArray(gb_context* ctx, const T* host, size_t n, const T** dev) {
+    *dev = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    void* p = nullptr;
+    GB_CUDA(cudaMalloc(&p, bytes));
+    ctx->sceneAllocs.push_back(p);
+    if (n) GB_CUDA(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = static_cast<const T*>(p);
+    return GB_OK;
+}
+
+void freeScene(gb_context* ctx) {
+    for (void* p : ctx->sceneAllocs) cudaFree(p);
+    ctx->sceneAllocs.clear();
+    if (ctx->film) cudaFree(ctx->film);
+    ctx->film = nullptr;
+    ctx->haveScene = false;
+}
+
+void freeWave(gb_context* ctx) {
+    for (void* p : ctx->waveAllocs) cudaFree(p);
+    ctx->waveAllocs.clear();
+    ctx->capacity = 0;
+}
+
+template <typename T>
+int waveAlloc(gb_context* ctx, T** out, size_t n) {
+    void* p = nullptr;
+    GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    ctx->waveAllocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return GB_OK;
+}
+
+int ensureWave(gb_context* ctx, size_t paths) {
+    if (paths <= ctx->capacity) return GB_OK;
+    freeWave(ctx);
+    PathState& ps = ctx->ps;
+    int rc;
+#define WA(field, type) if ((rc = waveAlloc<type>(ctx, &ps.field, paths)) != GB_OK) return rc
+    WA(rayO, float4); WA(rayD, float4); WA(hit, float4); WA(hitId, int2); WA(thr, float4); WA(L, float4);
+    WA(pend, float4); WA(shO, float4); WA(shD, float4); WA(shC, float4);
+    WA(qExtend[0], unsigned int); WA(qExtend[1], unsigned int);
+    WA(qMat[0], unsigned int); WA(qMat[1], unsigned int); WA(qMat[2], unsigned int);
+    WA(aoCount, unsigned int);
+#undef WA
+    ctx->capacity = paths;
+    return GB_OK;
+}
+
+size_t traceSmem(const gb_context* ctx) { return (size_t)ctx->stackEntries * kTraceBlock * sizeof(unsigned int); }
+
+template <typename K>
+int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
+    size_t smem = traceSmem(ctx);
+    GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSM = 0;
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraceBlock, smem));
+    if (perSM < 1) return gb::failWith(GB_ERR_LIMIT, "traversal kernel does not fit on an SM");
+    *grid = perSM * ctx->numSMs; // persistent: exactly one resident wave of CTAs
+    return GB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gb_device_count(int* count) {
+    if (!count) return gb::failWith(GB_ERR_INVALID, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return gb::failWith(GB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return GB_OK;
+}
+
+int gb_create(int device, gb_context** out) {
+    if (!out) return gb::failWith(GB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        return gb::failWith(GB_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+            cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return gb::failWith(GB_ERR_INVALID, "device index out of range");
+    GB_CUDA(cudaSetDevice(device));
+    gb_context* ctx = new gb_context();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->numSMs = prop.multiProcessorCount;
+    GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaEventCreate(&ctx->evStart));
+    GB_CUDA(cudaEventCreate(&ctx->evStop));
+    GB_CUDA(cudaMalloc((void**)&ctx->ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
+    GB_CUDA(cudaMalloc((void**)&ctx->traceHead, 64));
+    GB_CUDA(cudaMalloc((void**)&ctx->stats, S_COUNT * sizeof(unsigned long long)));
+    GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
+    *out = ctx;
+    return GB_OK;
+}
+
+int gb_destroy(gb_context* ctx) {
+    if (!ctx) return GB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    freeScene(ctx);
+    freeWave(ctx);
+    cudaFree(ctx->ctr);
+    cudaFree(ctx->traceHead);
+    cudaFree(ctx->stats);
+    cudaEventDestroy(ctx->evStart);
+    cudaEventDestroy(ctx->evStop);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GB_OK;
+}
+
+int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
+    if (!ctx || !d) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    freeScene(ctx);
+    DeviceScene sc{};
+    int rc;
+    // ---- validate + measure tree depth (stack need) on the host
+    auto depthOf = [](const gb_bvh_node* nodes, uint32_t count, int* depthOut) -> bool {
+        if (count == 0) { *depthOut = 0; return true; }
+        std::vector<std::pair<uint32_t, int>> todo;
+        todo.push_back({0u, 0});
+        int deepest = 0;
+        size_t visited = 0;
+        while (!todo.empty()) {
+            auto cur = todo.back();
+            todo.pop_back();
+            if (cur.first >= count || ++visited > count) return false;
+            deepest = std::max(deepest, cur.second);
+            const gb_bvh_node& nd = nodes[cur.first];
+            if (nd.nprims == 0) {
+                if (nd.axis > 2) return false;
+                todo.push_back({nd.offset, cur.second + 1});
+                todo.push_back({cur.first + 1, cur.second + 1});
+            }
+        }
+        *depthOut = deepest;
+        return true;
+    };
+    int topDepth = 0, modelDepth = 0;
+    if (!depthOf(d->top_nodes, d->n_top_nodes, &topDepth)) return gb::failWith(GB_ERR_INVALID, "malformed top-level BVH");
+    for (uint32_t m = 0; m < d->n_models; ++m) {
+        const gb_model& md = d->models[m];
+        if (md.kind != GB_GEOM_MESH) continue;
+        if ((uint64_t)md.node_offset + md.node_count > d->n_model_nodes || (uint64_t)md.tri_offset + md.tri_count > d->n_tris ||
+            (uint64_t)md.vert_offset + md.vert_count > d->n_verts) {
+            return gb::failWith(GB_ERR_INVALID, "model ranges exceed the scene arrays");
+        }
+        int dm = 0;
+        if (!depthOf(d->model_nodes + md.node_offset, md.node_count, &dm)) return gb::failWith(GB_ERR_INVALID, "malformed model BVH");
+        modelDepth = std::max(modelDepth, dm);
+    }
+    // push-far/go-near keeps at most one entry per level; both levels share one column
+    ctx->stackEntries = topDepth + modelDepth + 2;
+    if (ctx->stackEntries > 2 * kMaxStack) {
+        return gb::failWith(GB_ERR_LIMIT, "BVH deeper than the traversal stack (reference: todo[64] per level)");
+    }
+    // ---- top level, instances in BVH leaf order
+    const uint32_t nInst = d->n_instances;
+    std::vector<float4> instToObject(3 * (size_t)nInst), instToWorld(3 * (size_t)nInst);
+    std::vector<int4> instInfo(nInst), instShade(nInst);
+    std::vector<uint32_t> instNodeCount(nInst);
+    // triangle records are built once per distinct (node_offset, tri_offset) geometry
+    std::vector<float4> triRec(3 * (size_t)d->n_tris);
+    std::vector<int4> modelShade(d->n_models);
+    for (uint32_t m = 0; m < d->n_models; ++m) {
+        const gb_model& md = d->models[m];
+        modelShade[m] = make_int4((int)md.vert_offset, (int)md.tri_offset, (md.has_normal ? 1 : 0) | (md.has_uv ? 2 : 0), 0);
+        if (md.kind != GB_GEOM_MESH) continue;
+        for (uint32_t k = 0; k < md.tri_count; ++k) {
+            uint32_t face = d->model_order[md.tri_offset + k];
+            if (face >= md.tri_count) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
+            const uint32_t* vi = d->tri_index + 3 * ((size_t)md.tri_offset + face);
+            for (int c = 0; c < 3; ++c) if (vi[c] >= md.vert_count) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
+            const float* p0 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[0]);
+            const float* p1 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[1]);
+            const float* p2 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[2]);
+            // e1 = p1 - p0, e2 = p2 - p0: the reference's per-test subtractions, done once
+            float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+            float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+            float4* r = &triRec[3 * ((size_t)md.tri_offset + k)];
+            float faceBits;
+            std::memcpy(&faceBits, &face, 4);
+            r[0] = make_float4(p0[0], p0[1], p0[2], e1[0]);
+            r[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+            r[2] = make_float4(e2[2], faceBits, 0.0f, 0.0f);
+        }
+    }
+    bool hasArea = false;
+    for (uint32_t s = 0; s < nInst; ++s) {
+        uint32_t id = d->top_order[s];
+        if (id >= nInst) return gb::failWith(GB_ERR_INVALID, "top_order entry out of range");
+        const gb_instance& in = d->instances[id];
+        if (in.model < 0 || (uint32_t)in.model >= d->n_models) return gb::failWith(GB_ERR_INVALID, "instance model out of range");
+        const gb_model& md = d->models[in.model];
+        if (md.material < 0 || (uint32_t)md.material >= d->n_materials) return gb::failWith(GB_ERR_INVALID, "model material out of range");
+        for (int r = 0; r < 3; ++r) {
+            instToObject[3 * (size_t)s + r] = make_float4(in.to_object[4 * r], in.to_object[4 * r + 1], in.to_object[4 * r + 2], in.to_object[4 * r + 3]);
+            instToWorld[3 * (size_t)s + r] = make_float4(in.to_world[4 * r], in.to_world[4 * r + 1], in.to_world[4 * r + 2], in.to_world[4 * r + 3]);
+        }
+        int radiusBits;
+        std::memcpy(&radiusBits, &md.radius, 4);
+        instInfo[s] = make_int4(md.kind, (int)md.node_offset, (int)md.tri_offset, radiusBits);
+        instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
+        instNodeCount[s] = md.kind == GB_GEOM_MESH ? md.node_count : 0u;
+        if (md.area_light >= 0) hasArea = true;
+    }
+    std::vector<DeviceMaterial> mats(d->n_materials);
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const gb_material& mm = d->materials[m];
+        if (mm.type < 0 || mm.type > GB_MAT_TRANSPARENT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
+        int t = mm.type;
+        float tb;
+        std::memcpy(&tb, &t, 4);
+        mats[m].kdType = make_float4(mm.kd[0], mm.kd[1], mm.kd[2], tb);
+        // mirror keeps k in ktEta.x (its Kt is unused)
+        if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
+        else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
+    }
+    // original instance index -> slot, for area lights
+    std::vector<int> slotOf(nInst, -1);
+    for (uint32_t s = 0; s < nInst; ++s) slotOf[d->top_order[s]] = (int)s;
+    std::vector<DeviceLight> lights(d->n_lights);
+    for (uint32_t l = 0; l < d->n_lights; ++l) {
+        const gb_light& gl = d->lights[l];
+        DeviceLight& dl = lights[l];
+        float tb, kb, sb;
+        int t = gl.type, k = gl.geom_kind;
+        int slot = (gl.instance >= 0 && (uint32_t)gl.instance < nInst) ? slotOf[gl.instance] : -1;
+        std::memcpy(&tb, &t, 4);
+        std::memcpy(&kb, &k, 4);
+        std::memcpy(&sb, &slot, 4);
+        dl.colorType = make_float4(gl.color[0], gl.color[1], gl.color[2], tb);
+        dl.posRadius = make_float4(gl.position[0], gl.position[1], gl.position[2], gl.radius);
+        dl.dirCos = make_float4(gl.direction[0], gl.direction[1], gl.direction[2], gl.cos_theta_max);
+        dl.misc = make_float4(gl.cos_falloff_start, gl.area, kb, sb);
+        for (int r = 0; r < 3; ++r) {
+            dl.toWorld[r] = make_float4(gl.to_world[4 * r], gl.to_world[4 * r + 1], gl.to_world[4 * r + 2], gl.to_world[4 * r + 3]);
+            dl.toObject[r] = make_float4(gl.to_object[4 * r], gl.to_object[4 * r + 1], gl.to_object[4 * r + 2], gl.to_object[4 * r + 3]);
+        }
+    }
+    // CDF1D::mIntegral
+    float integral = 0.0f;
+    if (d->n_lights) {
+        float dx = 1.0f / d->n_lights, acc = 0.0f;
+        for (uint32_t l = 0; l < d->n_lights; ++l) acc = acc + d->light_power[l] * dx;
+        integral = acc;
+    }
+#define UP(dst, src, n) if ((rc = uploadArray(ctx, src, n, &dst)) != GB_OK) return rc
+    const float4* tmp4;
+    UP(tmp4, reinterpret_cast<const float4*>(d->top_nodes), 2 * (size_t)d->n_top_nodes); sc.topNodes = tmp4;
+    UP(tmp4, reinterpret_cast<const float4*>(d->model_nodes), 2 * (size_t)d->n_model_nodes); sc.modelNodes = tmp4;
+    UP(sc.instToObject, instToObject.data(), instToObject.size());
+    UP(sc.instToWorld, instToWorld.data(), instToWorld.size());
+    UP(sc.instInfo, instInfo.data(), instInfo.size());
+    UP(sc.instShade, instShade.data(), instShade.size());
+    UP(sc.instNodeCount, instNodeCount.data(), instNodeCount.size());
+    UP(sc.triRec, triRec.data(), triRec.size());
+    UP(sc.modelShade, modelShade.data(), modelShade.size());
+    UP(sc.triIndex, d->tri_index, 3 * (size_t)d->n_tris);
+    UP(sc.vertNrm, d->vert_nrm, 3 * (size_t)d->n_verts);
+    UP(sc.vertUv, d->vert_uv, 2 * (size_t)d->n_verts);
+    UP(sc.materials, mats.data(), mats.size());
+    UP(sc.lights, lights.data(), lights.size());
+    UP(sc.lightPower, d->light_power, (size_t)d->n_lights);
+    UP(sc.lightCdf, d->light_cdf, (size_t)d->n_lights + 1);
+    UP(sc.filterTable, d->film.filter_table, (size_t)256);
+#undef UP
+    sc.nTopNodes = d->n_top_nodes;
+    sc.nInstances = nInst;
+    sc.nLights = d->n_lights;
+    sc.lightIntegral = integral;
+    sc.hasAreaLight = hasArea ? 1u : 0u;
+    sc.camera = d->camera;
+    const gb_film_desc& f = d->film;
+    if (f.xres <= 0 || f.yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad film resolution");
+    sc.xres = f.xres; sc.yres = f.yres;
+    sc.xstart = f.xstart; sc.xcount = f.xcount; sc.ystart = f.ystart; sc.ycount = f.ycount;
+    sc.sx0 = f.sx0; sc.sx1 = f.sx1; sc.sy0 = f.sy0; sc.sy1 = f.sy1;
+    sc.invXRes = 1.0f / (float)f.xres; // Film::mInvXRes
+    sc.invYRes = 1.0f / (float)f.yres;
+    sc.filterWidthX = f.filter_width[0];
+    sc.filterWidthY = f.filter_width[1];
+    ctx->filmPixels = (size_t)f.xres * f.yres;
+    GB_CUDA(cudaMalloc((void**)&ctx->film, ctx->filmPixels * sizeof(float4)));
+    GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream)); // host staging vectors die here
+    ctx->sc = sc;
+    ctx->setting = d->setting;
+    ctx->haveScene = true;
+    // persistent grids for this scene's stack size
+    if (ctx->statsOn) rc = setupTraceKernel(ctx, k_trace<false, true>, &ctx->traceGrid);
+    else rc = setupTraceKernel(ctx, k_trace<false, false>, &ctx->traceGrid);
+    if (rc != GB_OK) return rc;
+    return GB_OK;
+}
+
+static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n, gb_hit* d_hits, unsigned char* d_occ) {
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    if (n > 0xfffffff0ull) return gb::failWith(GB_ERR_LIMIT, "ray batch too large");
+    size_t smem = traceSmem(ctx);
+    int grid = 0, rc;
+    GB_CUDA(cudaMemsetAsync(ctx->traceHead, 0, 4, ctx->stream));
+    GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
+#define LAUNCH(ANYV, STATSV)                                                                       \
+    do {                                                                                           \
+        if ((rc = setupTraceKernel(ctx, k_trace<ANYV, STATSV>, &grid)) != GB_OK) return rc;         \
+        k_trace<ANYV, STATSV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned int)n, d_hits, \
+            d_occ, ctx->traceHead, ctx->stats);                                                     \
+    } while (0)
+    if (any) { if (ctx->statsOn) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (ctx->statsOn) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    ctx->launches++;
+    GB_CUDA(cudaGetLastError());
+    GB_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
+    return GB_OK;
+}
+
+int gb_trace_closest_device(gb_context* ctx, const gb_ray* d_rays, size_t n, gb_hit* d_hits) {
+    if (!ctx || (n && (!d_rays || !d_hits))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    return launchTrace(ctx, false, d_rays, n, d_hits, nullptr);
+}
+
+int gb_trace_any_device(gb_context* ctx, const gb_ray* d_rays, size_t n, uint8_t* d_occ) {
+    if (!ctx || (n && (!d_rays || !d_occ))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    return launchTrace(ctx, true, d_rays, n, nullptr, d_occ);
+}
+
+int gb_trace_closest(gb_context* ctx, const gb_ray* rays, size_t n, gb_hit* hits) {
+    if (!ctx || (n && (!rays || !hits))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    if (n == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(ctx->device));
+    gb_ray* d_rays = nullptr;
+    gb_hit* d_hits = nullptr;
+    GB_CUDA(cudaMalloc((void**)&d_rays, n * sizeof(gb_ray)));
+    cudaError_t e = cudaMalloc((void**)&d_hits, n * sizeof(gb_hit));
+    if (e != cudaSuccess) { cudaFree(d_rays); return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e)); }
+    int rc = GB_OK;
+    e = cudaMemcpyAsync(d_rays, rays, n * sizeof(gb_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = launchTrace(ctx, false, d_rays, n, d_hits, nullptr);
+    if (e == cudaSuccess && rc == GB_OK) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(gb_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == GB_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rays);
+    cudaFree(d_hits);
+    if (rc != GB_OK) return rc;
+    if (e != cudaSuccess) return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e));
+    return GB_OK;
+}
+
+int gb_trace_any(gb_context* ctx, const gb_ray* rays, size_t n, uint8_t* occluded) {
+    if (!ctx || (n && (!rays || !occluded))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    if (n == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(ctx->device));
+    gb_ray* d_rays = nullptr;
+    unsigned char* d_occ = nullptr;
+    GB_CUDA(cudaMalloc((void**)&d_rays, n * sizeof(gb_ray)));
+    cudaError_t e = cudaMalloc((void**)&d_occ, n);
+    if (e != cudaSuccess) { cudaFree(d_rays); return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e)); }
+    int rc = GB_OK;
+    e = cudaMemcpyAsync(d_rays, rays, n * sizeof(gb_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = launchTrace(ctx, true, d_rays, n, nullptr, d_occ);
+    if (e == cudaSuccess && rc == GB_OK) e = cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == GB_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rays);
+    cudaFree(d_occ);
+    if (rc != GB_OK) return rc;
+    if (e != cudaSuccess) return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e));
+    return GB_OK;
+}
+
+int gb_camera_rays(gb_context* ctx, const float* samples, size_t n, gb_ray* rays) {
+    if (!ctx || (n && (!samples || !rays))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    if (n == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(ctx->device));
+    float* d_s = nullptr;
+    gb_ray* d_r = nullptr;
+    GB_CUDA(cudaMalloc((void**)&d_s, n * 4 * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&d_r, n * sizeof(gb_ray));
+    if (e != cudaSuccess) { cudaFree(d_s); return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(d_s, samples, n * 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_camera_rays<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, d_s, (unsigned int)n, d_r);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rays, d_r, n * sizeof(gb_ray), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_s);
+    cudaFree(d_r);
+    if (e != cudaSuccess) return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e));
+    return GB_OK;
+}
+
+// One wave of the wavefront integrator: nPaths camera samples start to finish.
+// table != nullptr: explicit sample values (gb_li); the wave is then a flat
+// list of samples and the film is not touched.
+static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& src, int method, bool toFilm) {
+    PathState& ps = ctx->ps;
+    cudaStream_t st = ctx->stream;
+    const size_t smem = traceSmem(ctx);
+    const unsigned int n = wp.nPaths;
+    int rc, grid = 0;
+    GB_CUDA(cudaMemsetAsync(ctx->ctr, 0, kMaxDepthCtr * kCtrStride * sizeof(unsigned int), st));
+    PathState psRay = ps;
+    if (method != GB_METHOD_AO) psRay.aoCount = nullptr;
+    k_raygen<<<(n + 255) / 256, 256, 0, st>>>(ctx->sc, psRay, wp, src, ctx->ctr, ctx->stats);
+    ctx->launches++;
+    const int shadeGrid = ctx->numSMs * 8;
+    auto extend = [&](int b, int singleBin) -> int {
+        unsigned int* c = ctx->ctr + b * kCtrStride;
+        const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
+        if (ctx->statsOn) {
+            if ((rc = setupTraceKernel(ctx, k_extend<true>, &grid)) != GB_OK) return rc;
+            k_extend<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats);
+        } else {
+            if ((rc = setupTraceKernel(ctx, k_extend<false>, &grid)) != GB_OK) return rc;
+            k_extend<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats);
+        }
+        ctx->launches++;
+        return GB_OK;
+    };
+    if (method == GB_METHOD_AO) {
+        if ((rc = extend(0, 1)) != GB_OK) return rc;
+        if (ctx->statsOn) {
+            if ((rc = setupTraceKernel(ctx, k_ao<true>, &grid)) != GB_OK) return rc;
+            k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+        } else {
+            if ((rc = setupTraceKernel(ctx, k_ao<false>, &grid)) != GB_OK) return rc;
+            k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+        }
+        k_ao_finish<<<(n + 255) / 256, 256, 0, st>>>(ps, wp);
+        ctx->launches += 2;
+    } else if (ctx->sc.nLights > 0) { // no lights: Li returns black before tracing (GoblinPathtracer.cpp:53-56)
+        const int depth = wp.maxDepth;
+        for (int b = 0; b < depth; ++b) {
+            // the last extend only feeds the BSDF-sampled emission term; skip it when no area light exists
+            const bool last = b == depth - 1;
+            if (last && b > 0 && !ctx->sc.hasAreaLight) break;
+            if ((rc = extend(b, 0)) != GB_OK) return rc;
+            unsigned int* c = ctx->ctr + b * kCtrStride;
+            unsigned int* cn = ctx->ctr + (b + 1) * kCtrStride;
+            unsigned int* qn = ps.qExtend[(b + 1) & 1];
+            int eo = last ? 1 : 0;
+            k_shade<GB_MAT_LAMBERT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+            k_shade<GB_MAT_MIRROR><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+            k_shade<GB_MAT_TRANSPARENT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+            ctx->launches += 3;
+            if (!last) {
+                if (ctx->statsOn) {
+                    if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
+                    k_shadow<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats);
+                } else {
+                    if ((rc = setupTraceKernel(ctx, k_shadow<false>, &grid)) != GB_OK) return rc;
+                    k_shadow<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats);
+                }
+                ctx->launches++;
+            }
+        }
+    }
+    if (toFilm) {
+        int halo = (int)ceilf(std::max(ctx->sc.filterWidthX, ctx->sc.filterWidthY) + 0.5f);
+        int side = kFilmTile + 2 * halo;
+        size_t fsmem = (size_t)side * side * 4 * sizeof(float);
+        if (fsmem > 200 * 1024) return gb::failWith(GB_ERR_LIMIT, "filter too wide for the film tile");
+        GB_CUDA(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        int tilesX = (wp.width + kFilmTile - 1) / kFilmTile, tilesY = (wp.rows + kFilmTile - 1) / kFilmTile;
+        k_film<<<tilesX * tilesY, 256, fsmem, st>>>(ctx->sc, ps, wp, src, ctx->film, halo);
+        ctx->launches++;
+    }
+    GB_CUDA(cudaGetLastError());
+    return GB_OK;
+}
+
+int gb_render(gb_context* ctx, const gb_render_params* p) {
+    if (!ctx || !p) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    int method = p->method >= 0 ? p->method : ctx->setting.method;
+    if (method != GB_METHOD_PATH_TRACING && method != GB_METHOD_AO) {
+        return gb::failWith(GB_ERR_INVALID, "render_method is outside the accelerated path (path_tracing and ao only)");
+    }
+    int depth = p->max_ray_depth > 0 ? p->max_ray_depth : ctx->setting.max_ray_depth;
+    if (depth < 1) depth = 1;
+    if (depth > kMaxDepthCtr - 2) return gb::failWith(GB_ERR_LIMIT, "max_ray_depth above 64");
+    int ao = p->ao_sample_num > 0 ? p->ao_sample_num : ctx->setting.ao_sample_num;
+    if (ao < 1) ao = 1;
+    int sppTotal = p->spp_total;
+    int root = (int)ceilf(sqrtf((float)sppTotal)); // roundToSquare, GoblinUtils.h:126-132
+    if (sppTotal < 1 || root * root != sppTotal) {
+        return gb::failWith(GB_ERR_INVALID, "spp_total must be a positive perfect square (sample_per_pixel rounded up)");
+    }
+    if (p->spp_begin < 0 || p->spp_end > sppTotal || p->spp_begin > p->spp_end) {
+        return gb::failWith(GB_ERR_INVALID, "bad sample index range");
+    }
+    const DeviceScene& sc = ctx->sc;
+    const int width = sc.sx1 - sc.sx0, height = sc.sy1 - sc.sy0;
+    if (width <= 0 || height <= 0 || p->spp_begin == p->spp_end) return GB_OK;
+    SampleSource src;
+    src.table = nullptr;
+    src.rowFloats = 0;
+    src.key = make_uint2((unsigned int)p->seed, (unsigned int)(p->seed >> 32));
+    GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
+    // waves: whole rows x a slice of the sample indices, at most maxWavePaths paths
+    int sppChunk = p->spp_end - p->spp_begin;
+    if ((size_t)sppChunk * width > ctx->maxWavePaths) sppChunk = std::max<int>(1, (int)(ctx->maxWavePaths / width));
+    int rowsPerWave = std::max<int>(1, (int)(ctx->maxWavePaths / ((size_t)sppChunk * width)));
+    rowsPerWave = std::min(rowsPerWave, height);
+    int rc = ensureWave(ctx, (size_t)rowsPerWave * width * sppChunk);
+    if (rc != GB_OK) return rc;
+    for (int s0 = p->spp_begin; s0 < p->spp_end; s0 += sppChunk) {
+        int ns = std::min(sppChunk, p->spp_end - s0);
+        for (int y = 0; y < height; y += rowsPerWave) {
+            WaveParams wp;
+            wp.rows = std::min(rowsPerWave, height - y);
+            wp.y0 = sc.sy0 + y;
+            wp.width = width;
+            wp.sppBegin = s0;
+            wp.nSpp = ns;
+            wp.sppTotal = sppTotal;
+            wp.root = root;
+            wp.maxDepth = depth;
+            wp.aoSamples = ao;
+            wp.aoRoot = std::max(1, (int)sqrtf((float)ao));
+            wp.nPaths = (unsigned int)((size_t)wp.rows * width * ns);
+            if ((rc = runWave(ctx, wp, src, method, true)) != GB_OK) return rc;
+        }
+    }
+    GB_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
+    return GB_OK;
+}
+
+int gb_li(gb_context* ctx, const float* samples, size_t n, size_t row_floats, float* out_rgb) {
+    if (!ctx || (n && (!samples || !out_rgb))) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    if (n == 0) return GB_OK;
+    GB_CUDA(cudaSetDevice(ctx->device));
+    int method = ctx->setting.method;
+    if (method != GB_METHOD_PATH_TRACING && method != GB_METHOD_AO) return gb::failWith(GB_ERR_INVALID, "unsupported render_method");
+    int depth = std::max(1, ctx->setting.max_ray_depth);
+    int ao = std::max(1, ctx->setting.ao_sample_num);
+    size_t need = 4 + (method == GB_METHOD_AO ? 2 * (size_t)ao : 7 * (size_t)depth);
+    if (row_floats < need) return gb::failWith(GB_ERR_INVALID, "sample rows too short for this integrator");
+    if (depth > kMaxDepthCtr - 2) return gb::failWith(GB_ERR_LIMIT, "max_ray_depth above 64");
+    float* d_s = nullptr;
+    float* d_out = nullptr;
+    GB_CUDA(cudaMalloc((void**)&d_s, n * row_floats * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&d_out, n * 3 * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_s); return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e)); }
+    int rc = GB_OK;
+    e = cudaMemcpyAsync(d_s, samples, n * row_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    size_t chunk = std::min<size_t>(n, ctx->maxWavePaths);
+    if (e == cudaSuccess) rc = ensureWave(ctx, chunk);
+    for (size_t off = 0; e == cudaSuccess && rc == GB_OK && off < n; off += chunk) {
+        size_t cnt = std::min(chunk, n - off);
+        WaveParams wp{};
+        wp.nPaths = (unsigned int)cnt;
+        wp.y0 = ctx->sc.sy0; wp.width = (int)cnt; wp.rows = 1;
+        wp.sppBegin = 0; wp.nSpp = 1; wp.sppTotal = 1; wp.root = 1;
+        wp.maxDepth = depth; wp.aoSamples = ao; wp.aoRoot = 1;
+        SampleSource src;
+        src.table = d_s + off * row_floats;
+        src.rowFloats = (unsigned int)row_floats;
+        src.key = make_uint2(0, 0);
+        rc = runWave(ctx, wp, src, method, false);
+        if (rc == GB_OK) {
+            k_copy_L<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->ps, (unsigned int)cnt, d_out + 3 * off);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess && rc == GB_OK) e = cudaMemcpyAsync(out_rgb, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == GB_OK) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_s);
+    cudaFree(d_out);
+    if (rc != GB_OK) return rc;
+    if (e != cudaSuccess) return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e));
+    return GB_OK;
+}
+
+int gb_film_clear(gb_context* ctx) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
+    return GB_OK;
+}
+
+int gb_film_download(gb_context* ctx, float* rgbw) {
+    if (!ctx || !rgbw) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaMemcpyAsync(rgbw, ctx->film, ctx->filmPixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+int gb_film_upload(gb_context* ctx, const float* rgbw) {
+    if (!ctx || !rgbw) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaMemcpyAsync(ctx->film, rgbw, ctx->filmPixels * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+int gb_film_device_ptr(gb_context* ctx, void** ptr, size_t* n_floats) {
+    if (!ctx || !ptr || !n_floats) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    *ptr = ctx->film;
+    *n_floats = ctx->filmPixels * 4;
+    return GB_OK;
+}
+
+int gb_film_write(gb_context* ctx, const char* path) {
+    if (!ctx || !path) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    std::vector<float> host(ctx->filmPixels * 4);
+    int rc = gb_film_download(ctx, host.data());
+    if (rc != GB_OK) return rc;
+    std::string err;
+    if (!gb::writeFilm(path, host.data(), ctx->sc.xres, ctx->sc.yres, &err)) return gb::failWith(GB_ERR_IO, err);
+    return GB_OK;
+}
+
+int gb_synchronize(gb_context* ctx) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GB_OK;
+}
+
+int gb_stream(gb_context* ctx, void** cuda_stream) {
+    if (!ctx || !cuda_stream) return gb::failWith(GB_ERR_INVALID, "null argument");
+    *cuda_stream = ctx->stream;
+    return GB_OK;
+}
+
+int gb_enable_counters(gb_context* ctx, int on) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    ctx->statsOn = on != 0;
+    return GB_OK;
+}
+
+int gb_get_counters(gb_context* ctx, gb_counters* out) {
+    if (!ctx || !out) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[S_COUNT];
+    GB_CUDA(cudaMemcpy(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost));
+    out->camera_samples = h[S_SAMPLES];
+    out->rays_closest = h[S_RAYS_CLOSEST];
+    out->rays_any = h[S_RAYS_ANY];
+    out->nodes_visited = h[S_NODES];
+    out->prims_tested = h[S_PRIMS];
+    out->instances_entered = h[S_INSTS];
+    out->kernel_launches = ctx->launches;
+    return GB_OK;
+}
+
+int gb_reset_counters(gb_context* ctx) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
+    ctx->launches = 0;
+    return GB_OK;
+}
+
+int gb_last_kernel_ms(gb_context* ctx, float* ms) {
+    if (!ctx || !ms) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaEventSynchronize(ctx->evStop));
+    GB_CUDA(cudaEventElapsedTime(ms, ctx->evStart, ctx->evStop));
+    return GB_OK;
+}
+
+} // extern "C"

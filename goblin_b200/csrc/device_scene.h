@@ -1,0 +1,72 @@
+// Device-side scene layout (HBM resident, read-only during rendering).
+//
+// Everything a traversal step touches is a 16-byte-aligned float4 / int4 array
+// read with 128-bit __ldg loads:
+//   * BVH nodes stay bit-identical to the reference's 32-byte CompactBVHNode
+//     (src/GoblinBVH.h:8-30) and are fetched as two float4: one node is one
+//     32-byte sector;
+//   * instances and triangles are stored in BVH leaf order, so a leaf's
+//     primitives are contiguous and no order[] indirection is paid per test;
+//   * a triangle test record is p0, e1 = p1 - p0, e2 = p2 - p0 (the values the
+//     reference recomputes per test, src/GoblinTriangle.cpp:51-54) plus the
+//     face index: 10 words in 48 bytes.  Normals / uvs live in separate arrays
+//     touched only by shading.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "goblin_b200.h"
+
+namespace gb {
+
+constexpr int kMaxLights = 1 << 20;
+
+struct DeviceLight { // 128 bytes
+    float4 colorType;   // rgb, __int_as_float(type)
+    float4 posRadius;   // position xyz, radius
+    float4 dirCos;      // direction xyz, cosThetaMax
+    float4 misc;        // cosFalloffStart, area, __int_as_float(geomKind), __int_as_float(instanceSlot)
+    float4 toWorld[3];  // light's own Transform (area lights)
+    float4 toObject[3];
+};
+
+struct DeviceMaterial { // 32 bytes
+    float4 kdType;      // kd / kr rgb, __int_as_float(type)
+    float4 ktEta;       // kt rgb, eta
+};
+
+struct DeviceScene {
+    // ---- traversal data
+    const float4* topNodes;     // 2 per node
+    uint32_t nTopNodes;
+    uint32_t nInstances;
+    const float4* instToObject; // 3 per instance slot (BVH leaf order)
+    const int4* instInfo;       // per slot: kind, node base (in modelNodes), tri base (in triRec), __float_as_int(radius)
+    const uint32_t* instNodeCount; // per slot: node count of the model BVH (0 = empty mesh)
+    const float4* modelNodes;   // 2 per node, all models concatenated
+    const float4* triRec;       // 3 per triangle slot (BVH leaf order, all models concatenated)
+    // ---- shading data
+    const float4* instToWorld;  // 3 per instance slot
+    const int4* instShade;      // per slot: original instance index, model index, material, area light (-1)
+    const int4* modelShade;     // per model: vert base, tri base (face order), has_normal | has_uv << 1, unused
+    const uint32_t* triIndex;   // 3 per face (model-local vertex indices), face order
+    const float* vertNrm;       // 3 per vertex
+    const float* vertUv;        // 2 per vertex
+    const DeviceMaterial* materials;
+    const DeviceLight* lights;
+    const float* lightPower;    // CDF1D::mFunction
+    const float* lightCdf;      // CDF1D::mCDF (nLights + 1)
+    uint32_t nLights;
+    float lightIntegral;        // CDF1D::mIntegral
+    uint32_t hasAreaLight;
+    // ---- camera / film
+    gb_camera camera;
+    int xres, yres;
+    int xstart, xcount, ystart, ycount;
+    int sx0, sx1, sy0, sy1;
+    float invXRes, invYRes;
+    float filterWidthX, filterWidthY;
+    const float* filterTable;   // 256 floats
+};
+
+} // namespace gb

@@ -1,0 +1,15 @@
+// Image output for the film: the reference writes colour / weight as an
+// OpenEXR file with HALF B, G, R channels (src/GoblinImageIO.cpp:35-98) or a
+// gamma-2.2 ASCII PPM (:100-126).  Here: an uncompressed scanline EXR with the
+// same channel layout, the same PPM, and a raw float PFM for parity checks
+// (HALF quantisation would pollute a z-test).
+#pragma once
+#include <string>
+
+namespace gb {
+
+// rgbw: yres x xres x 4 floats (weighted r, g, b, weight); the written colour
+// is rgb / weight (Film::writeImage, src/GoblinFilm.cpp:164-173).
+bool writeFilm(const std::string& path, const float* rgbw, int xres, int yres, std::string* error);
+
+} // namespace gb

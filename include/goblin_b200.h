@@ -1,0 +1,285 @@
+/*
+ * goblin_b200.h -- C ABI of the B200-native Goblin path-tracing hot path.
+ *
+ * The reference (bachi95/Goblin) has no FFI; its only seam is the virtual
+ * Renderer chosen by JSON (src/GoblinRenderer.h:50-61, selected in
+ * src/GoblinContextLoader.cpp:67-92) and driven from
+ * RenderContext::render() (src/GoblinRenderContext.h:19-22).  This header is
+ * the thin extern "C" layer that a Goblin maintainer would bind behind that
+ * seam: plain structs and pointers, every call returns an
+ * int status (0 = ok) and never throws, the caller owns all input arrays and
+ * may free them when the call returns, outputs go to caller-allocated buffers,
+ * one context per GPU driven by one host thread.  There is no CPU fallback:
+ * every compute entry point fails with GB_ERR_CUDA when no device is usable.
+ */
+#ifndef GOBLIN_B200_H
+#define GOBLIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_OK 0
+#define GB_ERR_INVALID 1  /* bad argument / malformed scene description      */
+#define GB_ERR_IO 2       /* unreadable scene / mesh / output file           */
+#define GB_ERR_CUDA 3     /* no device, launch failure, out of device memory */
+#define GB_ERR_STATE 4    /* call made before its prerequisite (no scene ..) */
+#define GB_ERR_LIMIT 5    /* scene exceeds a compiled-in limit (stack depth) */
+
+/* ------------------------------------------------------------------ records */
+
+/* Bit-for-bit the reference's CompactBVHNode (src/GoblinBVH.h:8-30): 24-byte
+ * box, first-primitive index (leaf) or second-child index (interior; the first
+ * child is node + 1), primitive count (0 = interior), split axis, 2 pad bytes
+ * that are zero.  One node is one 32-byte sector. */
+typedef struct gb_bvh_node {
+    float bmin[3];
+    float bmax[3];
+    uint32_t offset;
+    uint8_t nprims;
+    uint8_t axis;
+    uint8_t pad[2];
+} gb_bvh_node;
+
+/* Ray as the reference carries it (src/GoblinRay.h:9-19). */
+typedef struct gb_ray {
+    float o[3];
+    float d[3];
+    float mint;
+    float maxt;
+} gb_ray;
+
+/* Closest hit.  inst = index of the hit instance in scene order
+ * ([camera lens] + JSON "instance" primitives + area-light instances,
+ * src/GoblinContextLoader.cpp:161-163,381-383,437-439), prim = triangle index
+ * in the mesh's face order (0 for sphere / disk); inst = -1 on a miss.
+ * t is the shrunk ray.maxt, eps the reference's 1e-3 * t
+ * (src/GoblinTriangle.cpp:80-81). */
+typedef struct gb_hit {
+    float t;
+    float eps;
+    int32_t inst;
+    int32_t prim;
+} gb_hit;
+
+enum { GB_GEOM_MESH = 0, GB_GEOM_SPHERE = 1, GB_GEOM_DISK = 2 };
+enum { GB_MAT_LAMBERT = 0, GB_MAT_MIRROR = 1, GB_MAT_TRANSPARENT = 2 };
+enum { GB_LIGHT_POINT = 0, GB_LIGHT_DIRECTIONAL = 1, GB_LIGHT_SPOT = 2, GB_LIGHT_AREA = 3 };
+enum { GB_METHOD_PATH_TRACING = 0, GB_METHOD_AO = 1 };
+
+/* Model = geometry + material (+ area light) (src/GoblinModel.cpp:10-26).
+ * Mesh models own a private BVH over their triangles; the node / order /
+ * triangle / vertex ranges index the concatenated arrays of gb_scene_desc. */
+typedef struct gb_model {
+    int32_t kind;          /* GB_GEOM_*                                        */
+    float radius;          /* sphere / disk                                    */
+    int32_t material;      /* index into materials                             */
+    int32_t area_light;    /* index into lights, -1 if none                    */
+    uint32_t node_offset;  /* first BVH node of this model in model_nodes      */
+    uint32_t node_count;
+    uint32_t tri_offset;   /* first triangle in tri_index / model_order        */
+    uint32_t tri_count;
+    uint32_t vert_offset;  /* first vertex in vert_pos / vert_nrm / vert_uv    */
+    uint32_t vert_count;
+    int32_t has_normal;    /* mesh carries vn (src/GoblinPolygonMesh.cpp:130-147) */
+    int32_t has_uv;
+    int32_t is_camera_lens;
+    float bound[6];        /* object-space AABB (Model::getAABB)               */
+} gb_model;
+
+/* Instance = transform + model (src/GoblinPrimitive.cpp:99-122).  Row-major
+ * 3x4 matrices: the 4x4 of Transform::update (src/GoblinTransform.cpp:182-193)
+ * without its constant last row. */
+typedef struct gb_instance {
+    float to_world[12];
+    float to_object[12];
+    float aabb[6];         /* world AABB, Transform::onBBox                    */
+    int32_t model;
+    int32_t pad;
+} gb_instance;
+
+typedef struct gb_material {
+    int32_t type;          /* GB_MAT_*                                         */
+    float kd[3];           /* lambert Kd | mirror / transparent Kr             */
+    float kt[3];           /* transparent Kt                                   */
+    float eta;             /* transparent index | mirror index                 */
+    float k;               /* mirror absorption                                */
+} gb_material;
+
+typedef struct gb_light {
+    int32_t type;          /* GB_LIGHT_*                                       */
+    float color[3];        /* intensity (point, spot) | radiance (dir, area)   */
+    float position[3];
+    float direction[3];    /* directional: getDirection(); spot: cone axis     */
+    float cos_theta_max;   /* spot                                             */
+    float cos_falloff_start;
+    int32_t geom_kind;     /* area: GB_GEOM_SPHERE / GB_GEOM_DISK              */
+    float radius;          /* area                                             */
+    float area;            /* area: GeometrySet::mSumArea                      */
+    float to_world[12];    /* area: light's own Transform                      */
+    float to_object[12];
+    int32_t instance;      /* area: scene instance that carries the geometry   */
+} gb_light;
+
+typedef struct gb_camera {
+    float position[3];
+    float orientation[4];  /* w, x, y, z (src/GoblinUtils.cpp:78-79)           */
+    float proj00;          /* mProj[0][0], mProj[1][1] of matrixPerspectiveLHD3D */
+    float proj11;
+    float lens_radius;
+    float focal_distance;
+} gb_camera;
+
+typedef struct gb_film_desc {
+    int32_t xres, yres;
+    int32_t xstart, xcount, ystart, ycount;   /* crop window (Film ctor)      */
+    int32_t sx0, sx1, sy0, sy1;               /* Film::getSampleRange          */
+    float filter_width[2];
+    float filter_table[256];                  /* FilterTable, 16 x 16          */
+} gb_film_desc;
+
+typedef struct gb_render_setting {
+    int32_t method;        /* GB_METHOD_*                                      */
+    int32_t spp;           /* sample_per_pixel as written in the scene         */
+    int32_t max_ray_depth;
+    int32_t ao_sample_num;
+} gb_render_setting;
+
+/* Flattened scene.  All pointers are host pointers owned by whoever filled the
+ * struct (gb_scene owns them when it came from gb_scene_get_desc). */
+typedef struct gb_scene_desc {
+    /* top level: BVH over instances (Scene::mBVH, src/GoblinScene.cpp:15) */
+    const gb_bvh_node* top_nodes;
+    uint32_t n_top_nodes;
+    const uint32_t* top_order;      /* BVH leaf slot -> instance index       */
+    const gb_instance* instances;
+    uint32_t n_instances;
+    /* models */
+    const gb_model* models;
+    uint32_t n_models;
+    const gb_bvh_node* model_nodes; /* per-model BVHs, concatenated           */
+    uint64_t n_model_nodes;
+    const uint32_t* model_order;    /* BVH leaf slot -> face index (per model) */
+    const uint32_t* tri_index;      /* 3 vertex indices per face (model local) */
+    uint64_t n_tris;
+    const float* vert_pos;          /* 3 per vertex                           */
+    const float* vert_nrm;          /* 3 per vertex                           */
+    const float* vert_uv;           /* 2 per vertex                           */
+    uint64_t n_verts;
+    /* shading */
+    const gb_material* materials;
+    uint32_t n_materials;
+    const gb_light* lights;
+    uint32_t n_lights;
+    const float* light_power;       /* CDF1D::mFunction, n_lights             */
+    const float* light_cdf;         /* CDF1D::mCDF, n_lights + 1              */
+    float world_bound[6];           /* Scene BVH AABB (getBoundingSphere)     */
+    gb_camera camera;
+    gb_film_desc film;
+    gb_render_setting setting;
+} gb_scene_desc;
+
+typedef struct gb_render_params {
+    uint64_t seed;          /* Philox key                                      */
+    int32_t spp_total;      /* samples per pixel of the whole job (squared up) */
+    int32_t spp_begin;      /* this call renders sample indices [begin, end)   */
+    int32_t spp_end;
+    int32_t max_ray_depth;  /* <= 0: take the scene's                          */
+    int32_t method;         /* < 0: take the scene's                           */
+    int32_t ao_sample_num;  /* <= 0: take the scene's                          */
+} gb_render_params;
+
+typedef struct gb_counters {
+    uint64_t camera_samples;
+    uint64_t rays_closest;      /* closest-hit traversals executed           */
+    uint64_t rays_any;          /* any-hit (shadow / AO) traversals executed */
+    uint64_t nodes_visited;     /* BVH nodes whose box test was evaluated    */
+    uint64_t prims_tested;      /* triangle / sphere / disk tests            */
+    uint64_t instances_entered; /* world->object ray transforms              */
+    uint64_t kernel_launches;   /* launches of this library's kernels        */
+} gb_counters;
+
+typedef struct gb_scene gb_scene;     /* host-side flattened scene            */
+typedef struct gb_context gb_context; /* one GPU                              */
+
+/* ------------------------------------------------------------- host scene */
+
+/* ContextLoader::load (src/GoblinContextLoader.cpp:447-503): parse the JSON
+ * scene, load OBJ meshes, build the reference's equal_count BVHs bit-exactly,
+ * flatten.  Pure host code; needs no GPU. */
+int gb_scene_load_json(const char* path, gb_scene** out);
+/* The same from a JSON string; mesh paths resolve against scene_dir. */
+int gb_scene_load_json_string(const char* json, const char* scene_dir, gb_scene** out);
+void gb_scene_destroy(gb_scene* scene);
+int gb_scene_get_desc(const gb_scene* scene, gb_scene_desc* out);
+/* film output path chosen by the loader (film "file" or <scene>.exr) */
+const char* gb_scene_output_path(const gb_scene* scene);
+
+/* BVH::BVH (src/GoblinBVH.cpp:34-151) on raw boxes: nodes must hold
+ * 2 * n entries, order n entries.  Returns the node count in *n_nodes. */
+int gb_bvh_build(const float* aabbs /* n x 6 */, uint32_t n, gb_bvh_node* nodes,
+                 uint32_t* n_nodes, uint32_t* order);
+
+/* --------------------------------------------------------------- device */
+
+int gb_device_count(int* count);
+int gb_create(int device, gb_context** out);
+int gb_destroy(gb_context* ctx);
+int gb_upload_scene(gb_context* ctx, const gb_scene_desc* desc);
+
+/* Scene::intersect / Scene::occluded (src/GoblinScene.cpp:75-87) over a ray
+ * batch.  Host buffers; copies are part of the call. */
+int gb_trace_closest(gb_context* ctx, const gb_ray* rays, size_t n, gb_hit* hits);
+int gb_trace_any(gb_context* ctx, const gb_ray* rays, size_t n, uint8_t* occluded);
+/* The same on device-resident buffers (no copies), asynchronous on the
+ * context's stream; gb_synchronize() to wait. */
+int gb_trace_closest_device(gb_context* ctx, const gb_ray* d_rays, size_t n, gb_hit* d_hits);
+int gb_trace_any_device(gb_context* ctx, const gb_ray* d_rays, size_t n, uint8_t* d_occluded);
+
+/* PerspectiveCamera::generateRay (src/GoblinCamera.cpp:97-148) on explicit
+ * samples: n x 4 floats (imageX, imageY, lensU1, lensU2) -> n rays. */
+int gb_camera_rays(gb_context* ctx, const float* samples, size_t n, gb_ray* rays);
+
+/* Renderer::Li (src/GoblinPathtracer.cpp:50-179, src/GoblinAO.cpp:12-37) on
+ * explicit sample values; row layout as oracle/ref/ref_tool.cpp "li":
+ * imageX, imageY, lensU1, lensU2, then 7 floats per bounce (path tracing) or
+ * 2 per AO ray.  out: n x 3 radiance. */
+int gb_li(gb_context* ctx, const float* samples, size_t n, size_t row_floats, float* out_rgb);
+
+/* Renderer::render (src/GoblinRenderer.cpp:99-126): accumulate the sample
+ * indices [spp_begin, spp_end) of every pixel of the sample range into the
+ * device film.  Asynchronous on the context's stream. */
+int gb_render(gb_context* ctx, const gb_render_params* params);
+int gb_film_clear(gb_context* ctx);
+/* Film::mPixels as 4 planes-interleaved floats per pixel (r, g, b, weight),
+ * yres x xres x 4. Synchronises. */
+int gb_film_download(gb_context* ctx, float* rgbw);
+int gb_film_upload(gb_context* ctx, const float* rgbw);
+/* Device address + float count of the film, for an external all-reduce
+ * (torch.distributed / NCCL): the analogue of Film::mergeTile
+ * (src/GoblinFilm.cpp:140-153). */
+int gb_film_device_ptr(gb_context* ctx, void** ptr, size_t* n_floats);
+/* Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, written as
+ * .exr (half, like src/GoblinImageIO.cpp:35-98), .pfm or .ppm by extension. */
+int gb_film_write(gb_context* ctx, const char* path);
+int gb_write_image(const char* path, const float* rgbw, int xres, int yres);
+
+int gb_synchronize(gb_context* ctx);
+int gb_stream(gb_context* ctx, void** cuda_stream);
+int gb_enable_counters(gb_context* ctx, int on); /* traversal statistics (slower) */
+int gb_get_counters(gb_context* ctx, gb_counters* out);
+int gb_reset_counters(gb_context* ctx);
+/* milliseconds spent in the last gb_render / gb_trace_*_device call's kernels,
+ * from CUDA events on the context's stream. Synchronises. */
+int gb_last_kernel_ms(gb_context* ctx, float* ms);
+
+const char* gb_last_error(void);
+const char* gb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOBLIN_B200_H */
