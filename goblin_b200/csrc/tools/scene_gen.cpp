@@ -290,10 +290,16 @@ static void genTiny(const std::string& dir) {
     writeObj(dir + "/models/ico_flat.obj", ico, 0);
     Mesh blob = bunnyStandin(2, 99);
     writeObj(dir + "/models/blob.obj", blob, 1);
-    // a quad-faced box (tests the quad split) with v/vt only
+    // a quad-faced box (tests the quad split) with v/vt only.  uv = (x - z, y - z) / 2 + 1/2: the
+    // map's null direction (1, 1, 1) lies in no face plane, so no triangle has a zero uv
+    // determinant (the reference reads a stale Fragment for those, GoblinTriangle.cpp:113-117).
     Mesh box;
     const double c[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
-    for (auto& p : c) { box.pos.push_back(V3{p[0] * 0.5, p[1] * 0.5, p[2] * 0.5}); box.uv.push_back(p[0] * 0.5 + 0.5); box.uv.push_back(p[1] * 0.5 + 0.5); }
+    for (auto& p : c) {
+        box.pos.push_back(V3{p[0] * 0.5, p[1] * 0.5, p[2] * 0.5});
+        box.uv.push_back((p[0] - p[2]) * 0.25 + 0.5);
+        box.uv.push_back((p[1] - p[2]) * 0.25 + 0.5);
+    }
     const uint32_t q[24] = {0, 3, 2, 1, 4, 5, 6, 7, 0, 1, 5, 4, 2, 3, 7, 6, 1, 2, 6, 5, 0, 4, 7, 3};
     box.idx.assign(q, q + 24);
     writeObj(dir + "/models/box.obj", box, 3, true);

@@ -1,0 +1,180 @@
+"""Host scene layer (JSON + OBJ loader, transforms, equal_count BVH builder, flattening) against
+the reference's own structures, dumped by oracle/_ref/ref_tool into tests/golden/tiny_dump.gbar.
+Bit-exact: whole 32-byte nodes are compared as bytes (north_star criterion 1)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from goblin_b200 import api, gbar
+from tests import util
+
+
+@pytest.fixture(scope="module")
+def scene(built):
+    return api.Scene(util.TINY_PT)
+
+
+@pytest.fixture(scope="module")
+def dump():
+    return gbar.load(os.path.join(util.GOLDEN, "tiny_dump.gbar"))
+
+
+def _node_bytes(nodes):
+    return np.frombuffer(np.ascontiguousarray(nodes).tobytes(), dtype=np.uint8).reshape(-1, 32)
+
+
+def test_top_level_bvh_bit_exact(scene, dump):
+    assert np.array_equal(_node_bytes(scene.top_nodes()), dump["top.nodes"])
+    assert np.array_equal(scene.top_order(), dump["top.order"])
+
+
+def test_instances_bit_exact(scene, dump):
+    insts = scene.instances()
+    assert len(insts) == dump["inst.fwd"].shape[0]
+    for i, inst in enumerate(insts):
+        fwd = np.array(inst.to_world[:], np.float32).reshape(3, 4)
+        inv = np.array(inst.to_object[:], np.float32).reshape(3, 4)
+        assert np.array_equal(fwd.view(np.uint32), dump["inst.fwd"][i].reshape(4, 4)[:3].view(np.uint32)), i
+        assert np.array_equal(inv.view(np.uint32), dump["inst.inv"][i].reshape(4, 4)[:3].view(np.uint32)), i
+        assert np.array_equal(np.array(inst.aabb[:], np.float32).view(np.uint32), dump["inst.aabb"][i].view(np.uint32)), i
+        # last rows of the reference's 4x4 are the constant (0, 0, 0, 1) the 3x4 layout drops
+        assert np.array_equal(dump["inst.fwd"][i].reshape(4, 4)[3], [0, 0, 0, 1])
+
+
+def test_models_bit_exact(scene, dump):
+    """Per-model BVH nodes, leaf order, vertex and index arrays, matched through the instances
+    (model numbering is an implementation detail; the instance -> model content map is not)."""
+    models = scene.models()
+    nodes, order = scene.model_nodes(), scene.model_order()
+    tri, pos, nrm, uv = scene.tri_index(), scene.vert_pos(), scene.vert_nrm(), scene.vert_uv()
+    seen_mesh = 0
+    for i, inst in enumerate(scene.instances()):
+        m = models[inst.model]
+        rm = int(dump["inst.model"][i])
+        assert m.kind == int(dump["model.kind"][rm])
+        assert m.area_light == int(dump["model.light"][rm])
+        if m.kind == 0:
+            pre = f"model{rm}."
+            mine = nodes[m.node_offset:m.node_offset + m.node_count]
+            assert np.array_equal(_node_bytes(mine), dump[pre + "nodes"]), f"instance {i}"
+            assert np.array_equal(order[m.tri_offset:m.tri_offset + m.tri_count], dump[pre + "order"])
+            assert np.array_equal(tri[m.tri_offset:m.tri_offset + m.tri_count], dump[pre + "idx"])
+            sl = slice(m.vert_offset, m.vert_offset + m.vert_count)
+            assert np.array_equal(pos[sl].view(np.uint32), dump[pre + "pos"].view(np.uint32))
+            assert np.array_equal(nrm[sl].view(np.uint32), dump[pre + "nrm"].view(np.uint32))
+            assert np.array_equal(uv[sl].view(np.uint32), dump[pre + "uv"].view(np.uint32))
+            assert [m.has_normal, m.has_uv] == list(dump[pre + "flags"])
+            assert np.array_equal(np.array(m.bound[:], np.float32), dump[pre + "bound"])
+            seen_mesh += 1
+        else:
+            assert np.float32(m.radius) == dump["model.radius"][rm]
+    assert seen_mesh >= 4
+
+
+def test_lights_camera_film_bit_exact(scene, dump):
+    assert np.array_equal(scene.light_power().view(np.uint32), dump["light.power"].view(np.uint32))
+    assert np.array_equal(scene.light_cdf().view(np.uint32), dump["light.cdf"].view(np.uint32))
+    cam = scene.desc.camera
+    mine = np.array(list(cam.position) + list(cam.orientation) + [cam.proj00, cam.proj11, cam.lens_radius,
+                                                                  cam.focal_distance], np.float32)
+    assert np.array_equal(mine.view(np.uint32), dump["camera"].view(np.uint32))
+    f = scene.desc.film
+    assert [f.xres, f.yres, f.xstart, f.xcount, f.ystart, f.ycount, f.sx0, f.sx1, f.sy0, f.sy1] == list(dump["film"])
+    assert np.array_equal(np.array(f.filter_table[:], np.float32).view(np.uint32), dump["filter.table"].view(np.uint32))
+    assert np.array_equal(np.array(f.filter_width[:], np.float32), dump["filter.width"])
+
+
+def test_bvh_build_properties():
+    """gb_bvh_build on random boxes: 2n-1 nodes, one primitive per leaf, a permutation as order,
+    every leaf box equal to its primitive's box, parents enclosing children (BVH::BVH,
+    src/GoblinBVH.cpp:34-151)."""
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 17, 1000):
+        lo = rng.uniform(-10, 10, (n, 3)).astype(np.float32)
+        boxes = np.concatenate([lo, lo + rng.uniform(0.01, 1, (n, 3)).astype(np.float32)], 1)
+        nodes, order = api.bvh_build(boxes)
+        assert len(nodes) == 2 * n - 1
+        assert sorted(order.tolist()) == list(range(n))
+        leaves = nodes[nodes["nprims"] > 0]
+        assert len(leaves) == n and (leaves["nprims"] == 1).all()
+        for nd in leaves:
+            b = boxes[order[nd["offset"]]]
+            assert np.array_equal(nd["bmin"], b[:3]) and np.array_equal(nd["bmax"], b[3:])
+        for i, nd in enumerate(nodes):
+            if nd["nprims"] == 0:
+                for c in (i + 1, int(nd["offset"])):
+                    assert (nodes[c]["bmin"] >= nd["bmin"]).all() and (nodes[c]["bmax"] <= nd["bmax"]).all()
+
+
+def test_bvh_build_coincident_centroids():
+    """Primitives whose centroids coincide on the split axis end in one multi-primitive leaf
+    (src/GoblinBVH.cpp:110-120)."""
+    boxes = np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (5, 1))
+    nodes, order = api.bvh_build(boxes)
+    assert len(nodes) == 1 and nodes[0]["nprims"] == 5
+    assert sorted(order.tolist()) == list(range(5))
+
+
+def test_bvh_build_empty():
+    nodes, order = api.bvh_build(np.zeros((0, 6), np.float32))
+    assert len(nodes) == 0 and len(order) == 0
+
+
+def test_loader_errors(built, tmp_path):
+    with pytest.raises(api.GoblinError) as e:
+        api.Scene(str(tmp_path / "missing.json"))
+    assert e.value.code == 2  # GB_ERR_IO, ContextLoader::load returns nullptr (src/GoblinContextLoader.cpp:449-459)
+    bad = tmp_path / "bad.json"
+    bad.write_text("{ not json")
+    with pytest.raises(api.GoblinError):
+        api.Scene(str(bad))
+
+
+def test_paramset_int_float_quirk(built, tmp_path):
+    """Ints and floats do not cross-convert (src/GoblinParamSet.cpp:104-120): "radius": 2 is an
+    int, so getFloat("radius", 1.0) yields the default."""
+    src = open(util.TINY_PT).read().replace('"type": "sphere", "radius": 0.6', '"type": "sphere", "radius": 2')
+    assert src != open(util.TINY_PT).read()
+    sc = api.Scene(json_text=src, scene_dir=os.path.dirname(util.TINY_PT))
+    radii = sorted({round(m.radius, 3) for m in sc.models() if m.kind == 1})
+    assert 2.0 not in radii and 1.0 in radii
+
+
+def test_spp_rounds_up_to_square(scene):
+    assert scene.spp_squared(50) == 64 and scene.spp_squared(100) == 100 and scene.spp_squared(1) == 1
+
+
+def test_c_abi_exports_every_declared_symbol(built):
+    """Every function include/goblin_b200.h declares is exported by libgoblin_b200.so."""
+    import re
+    header = open(os.path.join(util.ROOT, "include", "goblin_b200.h")).read()
+    declared = set(re.findall(r"\b(gb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    lib = api.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gb_version().decode()
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device every compute entry point fails loudly with GB_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.GoblinError) as e:
+        api.Context(0)
+    assert e.value.code == 3
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product tree never links, loads or names oracle/."""
+    import subprocess
+    out = subprocess.run(["grep", "-rIl", "-e", "goblin_oracle", "-e", "oracle/", os.path.join(util.ROOT, "goblin_b200")],
+                         capture_output=True, text=True).stdout.split()
+    out = [p for p in out if "/build/" not in p]
+    assert out == [], out
+    so = os.path.join(util.ROOT, "goblin_b200", "libgoblin_b200.so")
+    ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "goblin_oracle" not in ldd
