@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark: path-traced Msamples/s (and Mrays/s) on bunny.json.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+One "step" is one complete render of the workload scene (S1 of SURVEY 8(d):
+examples/bunny.json with the path_tracing integrator, 512 x 384, 100 spp, depth
+8; the missing bunny.obj is replaced by the deterministic stand-in mesh of
+goblin_b200/bin/scene_gen, 81,920 triangles) through the C ABI, scene resident
+in HBM.  With N > 1 every rank renders the same scene with its own sample set
+(weak scaling) and the film buffers are summed with one NCCL all-reduce per
+step, inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENES = {
+    # name: (scene_gen kind, args, json file)
+    "bunny": ("bunny", [], "bunny_pt.json"),
+    "bunny_ao": ("bunny", [], "bunny_ao.json"),
+    "spheres": ("spheres", [], "spheres_pt.json"),
+    "grid": ("grid", [], "grid_pt.json"),
+    "grid_small": ("grid", [512], "grid_pt.json"),
+    "field": ("field", [], "field_pt.json"),
+}
+WORKLOAD_NOTE = ("S1: examples/bunny.json layout, render_method path_tracing, 512x384, 100 spp, max_ray_depth 8, "
+                 "gaussian filter r=2; stand-in bunny mesh (icosphere 6x + hashed noise, 81,920 tris): "
+                 "examples/models/bunny.obj is absent from the reference mount")
+SCENE_GEN = os.path.join(ROOT, "goblin_b200", "bin", "scene_gen")
+REF_TOOL = os.path.join(ROOT, "oracle", "_ref", "ref_tool")
+
+
+def scene_path(name):
+    kind, args, fname = SCENES[name]
+    d = os.path.join(ROOT, "scenes", "_gen", kind + ("_" + "_".join(map(str, args)) if args else ""))
+    marker = os.path.join(d, ".done")
+    if not os.path.exists(marker):
+        os.makedirs(d, exist_ok=True)
+        subprocess.run([SCENE_GEN, kind, d, *map(str, args)], check=True)
+        open(marker, "w").close()
+    return os.path.join(d, fname)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ref_tool(scene, spp, threads=0):
+    """Timed RenderContext::render() of the unmodified reference (oracle/_ref/ref_tool render)."""
+    cmd = [REF_TOOL, "render", scene, "-", "--spp", str(spp)]
+    if threads:
+        cmd += ["--threads", str(threads)]
+    with tempfile.TemporaryDirectory() as td:  # the reference writes its image next to the CWD
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=td).stdout
+    return json.loads(out.split("REF_RESULT", 1)[1])
+
+
+def cpu_reference_sample(scene_json, budget_s=12.0):
+    """A bounded sample of the workload on the host cores: the reference itself when its binary
+    travelled here (kind "reference"), else the oracle port (kind "port")."""
+    if os.path.exists(REF_TOOL):
+        probe = run_ref_tool(scene_json, 1)
+        rate = probe["camera_samples"] / max(probe["seconds"], 1e-3)
+        root = max(1, min(10, int((budget_s * rate / probe["camera_samples"]) ** 0.5)))
+        res = run_ref_tool(scene_json, root * root) if root > 1 else probe
+        return {"value": res["msamples_per_s"], "unit": "Msamples/s", "cores": res["cores"], "kind": "reference",
+                "sample": f"same scene, {res['spp']} spp ({res['camera_samples']} camera samples) in "
+                          f"{res['seconds']:.2f} s, g_ray thread pool on all host cores",
+                "mrays_per_s": res["mrays_per_s"], "seconds": res["seconds"]}
+    from goblin_b200 import api
+    from tests import oracle_port as op
+    scene = api.Scene(scene_json)
+    t0 = time.perf_counter()
+    _, c, calls = op.render(scene, seed=1, spp_total=1)
+    dt = time.perf_counter() - t0
+    return {"value": c["camera_samples"] / dt * 1e-6, "unit": "Msamples/s", "cores": op.hardware_threads(),
+            "kind": "port", "sample": f"same scene, 1 spp ({c['camera_samples']} camera samples) in {dt:.2f} s",
+            "mrays_per_s": (calls[0] + calls[1]) / dt * 1e-6, "seconds": dt}
+
+
+def bench_reference(args, rank):
+    if rank != 0:
+        return
+    scene_json = scene_path(args.scene)
+    vals = []
+    last = None
+    for step in range(args.warmup + args.steps):
+        last = cpu_reference_sample(scene_json, budget_s=args.ref_budget)
+        if step >= args.warmup:
+            vals.append(last)
+    value = sum(v["value"] for v in vals) / len(vals)
+    secs = sum(v["seconds"] for v in vals) / len(vals)
+    line = {"impl": "reference", "metric": "path-traced Msamples/s (bunny.json)", "value": value,
+            "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NOTE, "scene": args.scene, "step": last["sample"]},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"],
+                             "sample": last["sample"]},
+            "mrays_per_s": sum(v["mrays_per_s"] for v in vals) / len(vals),
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+class DevBuf:
+    """A device allocation exposed through __cuda_array_interface__ (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def scene_bytes(desc):
+    d = desc
+    return (32 * (d.n_top_nodes + d.n_model_nodes) + 4 * d.n_instances + 128 * d.n_instances + 12 * d.n_tris * 2 +
+            4 * d.n_tris + 32 * d.n_verts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default="bunny", choices=sorted(SCENES))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
+    ap.add_argument("--wave-paths", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        bench_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from goblin_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # scene (rank 0 generates, everybody loads: full replica per GPU)
+    if rank == 0:
+        scene_json = scene_path(args.scene)
+    barrier()
+    scene_json = scene_path(args.scene)
+    t0 = time.perf_counter()
+    scene = api.Scene(scene_json)
+    load_s = time.perf_counter() - t0
+    ctx = api.Context(local_rank)
+    ctx.upload_scene(scene)
+    if args.wave_paths:
+        ctx.set_wave_paths(args.wave_paths)
+    spp = scene.spp_squared(args.spp or None)
+    if args.scaling == "strong":
+        per = (spp + world - 1) // world
+        spp_begin, spp_end = min(spp, rank * per), min(spp, (rank + 1) * per)
+        seed_of = lambda step: 1000 + step  # noqa: E731  one sample set, split by index range
+    else:
+        spp_begin, spp_end = 0, spp
+        seed_of = lambda step: 1000 + step + 7919 * rank  # noqa: E731  independent sample sets
+    my_samples = (scene.sample_range()[1] - scene.sample_range()[0]) * \
+        (scene.sample_range()[3] - scene.sample_range()[2]) * (spp_end - spp_begin)
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    film_ptr, film_floats = ctx.film_device_ptr()
+    film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(i, flush_l2=True):
+        with torch.cuda.stream(stream):
+            if flush_l2:
+                flush.fill_(i & 0xFF)
+            ctx.film_clear()
+            ctx.render(seed=seed_of(i), spp_total=spp, spp_begin=spp_begin, spp_end=spp_end)
+            if world > 1:
+                dist.all_reduce(film_t)  # Film::mergeTile across GPUs
+
+    # traversal statistics of one step (untimed, counters on): the algorithmic bytes
+    ctx.enable_counters(True)
+    ctx.reset_counters()
+    step(0, flush_l2=False)
+    ctx.synchronize()
+    st = ctx.counters()
+    ctx.enable_counters(False)
+
+    for i in range(args.warmup):
+        step(i)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    ctx.reset_counters()
+    ctx.reset_kernel_times()
+    ctx.enable_kernel_timing(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the L2 flush is part of the loop; its fill (~40 us) is timed separately and subtracted
+    fl0, fl1 = [], []
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            flush.fill_(i & 0xFF)
+            b.record()
+            fl0.append(a)
+            fl1.append(b)
+        step(args.warmup + i, flush_l2=False)
+    with torch.cuda.stream(stream):
+        ev1.record()
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    clocks.stop_flag.set()
+    total_ms = ev0.elapsed_time(ev1) - sum(a.elapsed_time(b) for a, b in zip(fl0, fl1))
+    ctx.enable_kernel_timing(False)
+    ktimes = ctx.kernel_times()
+    timed = ctx.counters()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(my_samples), float(timed["rays_closest"] + timed["rays_any"])], dtype=torch.float64,
+                       device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    total_ms = float(t.item())
+    samples_per_step_all = float(tot[0].item())
+    rays_all = float(tot[1].item())
+    ms_per_step = total_ms / args.steps
+    value = samples_per_step_all / (ms_per_step * 1e-3) * 1e-6
+    mrays = rays_all / (total_ms * 1e-3) * 1e-6
+
+    # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + film download (D2H)
+    e2e_steps = max(1, min(args.steps, 5))
+    for i in range(2):
+        ctx.upload_scene(scene)
+    film_ptr, film_floats = ctx.film_device_ptr()
+    film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
+    barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx.upload_scene(scene)  # frees and reallocates the film: re-wrap it
+        film_ptr, film_floats = ctx.film_device_ptr()
+        film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
+        step(10000 + i, flush_l2=False)
+        host_film = ctx.film_download()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    e2e_value = samples_per_step_all / (e2e_ms / e2e_steps * 1e-3) * 1e-6
+    assert np.isfinite(host_film).all()
+
+    if rank == 0:
+        # ---- roofline of the dominant traversal kernel (closest-hit extend vs any-hit shadow / ao)
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak, peak_src = (peaks["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+            else (6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)")
+        any_cls = "ao" if ktimes["ao"][0] > ktimes["shadow"][0] else "shadow"
+        bytes_closest = (32 * (st["nodes_visited"] - st["nodes_visited_any"]) + 48 * (st["prims_tested"] - st["prims_tested_any"]) +
+                         64 * (st["instances_entered"] - st["instances_entered_any"]) + 48 * st["rays_closest"])
+        bytes_any = (32 * st["nodes_visited_any"] + 48 * st["prims_tested_any"] + 64 * st["instances_entered_any"] +
+                     48 * st["rays_any"])
+        if ktimes["extend"][0] >= ktimes[any_cls][0]:
+            kname, kms, kbytes, krays = "k_extend (closest-hit two-level BVH traversal)", ktimes["extend"], bytes_closest, st["rays_closest"]
+        else:
+            kname, kms, kbytes, krays = f"k_{any_cls} (any-hit traversal)", ktimes[any_cls], bytes_any, st["rays_any"]
+        launches_per_step = kms[1] / args.steps
+        avg_launch_ms = kms[0] / max(kms[1], 1)
+        achieved = (kbytes / max(launches_per_step, 1)) / (avg_launch_ms * 1e-3) * 1e-9 if avg_launch_ms > 0 else 0.0
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tr_path):
+            traffic = json.load(open(tr_path)).get(args.scene)
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                    "algorithmic_bytes_per_ray": kbytes / max(krays, 1),
+                    "algorithmic_bytes_per_launch": kbytes / max(launches_per_step, 1),
+                    "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
+                    "nodes_per_ray": (st["nodes_visited"]) / max(st["rays_closest"] + st["rays_any"], 1),
+                    "kernel_share_of_step": kms[0] / total_ms,
+                    "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]}}
+        line = {"metric": "path-traced Msamples/s (bunny.json)", "value": value, "unit": "Msamples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD_NOTE, "scene": args.scene, "spp": spp, "spp_range_rank0": [spp_begin, spp_end],
+                           "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
+                           "parallelism": f"spp x{world} (scene replica per GPU, NCCL film all-reduce)" if world > 1 else "1 GPU",
+                           "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~0.8 GB per wave) exceeds L2",
+                           "scene_load_s": load_s},
+                "mrays_per_s": mrays, "rays_per_sample": rays_all / (samples_per_step_all * args.steps),
+                "gpu_launches": int(timed["kernel_launches"]),
+                "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(scene_bytes(scene.desc)),
+                        "d2h_bytes_per_step": int(film_floats * 4), "steps": e2e_steps,
+                        "what": "gb_upload_scene (host arrays) + gb_film_clear + gb_render + gb_film_download per step"},
+                "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb = cpu_reference_sample(scene_json, budget_s=args.ref_budget)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"]["mrays_per_s_reference_equivalent"] = cb["mrays_per_s"]
+            except Exception as e:  # the baseline is reported, never fatal
+                line["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

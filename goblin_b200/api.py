@@ -91,7 +91,9 @@ class RenderParams(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("camera_samples", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_any", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64),
-                ("instances_entered", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("instances_entered", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("nodes_visited_any", C.c_uint64), ("prims_tested_any", C.c_uint64),
+                ("instances_entered_any", C.c_uint64)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("mint", np.float32), ("maxt", np.float32)])
@@ -107,8 +109,15 @@ EXPORTS = [
     "gb_trace_any_device", "gb_camera_rays", "gb_li", "gb_render", "gb_film_clear",
     "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image",
     "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
-    "gb_last_kernel_ms", "gb_last_error", "gb_version",
+    "gb_last_kernel_ms", "gb_last_error", "gb_version", "gb_enable_kernel_timing", "gb_get_kernel_times",
+    "gb_reset_kernel_times", "gb_set_wave_paths",
 ]
+
+KERNEL_CLASSES = ["raygen", "extend", "shade", "shadow", "ao", "film", "trace", "other"]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
 
 _lib = None
 
@@ -154,6 +163,10 @@ def lib():
         l.gb_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
         l.gb_reset_counters.argtypes = [C.c_void_p]
         l.gb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        l.gb_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        l.gb_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTimes)]
+        l.gb_reset_kernel_times.argtypes = [C.c_void_p]
+        l.gb_set_wave_paths.argtypes = [C.c_void_p, C.c_size_t]
         _lib = l
     return _lib
 
@@ -370,6 +383,21 @@ class Context:
 
     def reset_counters(self):
         check(lib().gb_reset_counters(self._h))
+
+    def enable_kernel_timing(self, on=True):
+        check(lib().gb_enable_kernel_timing(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{class: (ms, launches)} since the last reset_kernel_times()."""
+        t = KernelTimes()
+        check(lib().gb_get_kernel_times(self._h, C.byref(t)))
+        return {name: (t.ms[k], t.launches[k]) for k, name in enumerate(KERNEL_CLASSES)}
+
+    def reset_kernel_times(self):
+        check(lib().gb_reset_kernel_times(self._h))
+
+    def set_wave_paths(self, max_paths):
+        check(lib().gb_set_wave_paths(self._h, max_paths))
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -35,7 +35,8 @@ constexpr int kShadeBlock = 128;
 constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
 constexpr int kCtrStride = 16;     // counters per bounce
 enum { C_EXTEND = 0, C_EXTEND_HEAD = 1, C_MAT0 = 2, C_SHADOW = 5, C_SHADOW_HEAD = 6, C_AO_HEAD = 7 };
-enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_COUNT = 8 };
+// traversal statistics are kept apart for closest-hit and any-hit walks (S_ANY_BASE + ...)
+enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_ANY_BASE = 8, S_COUNT = 16 };
 
 struct PathState {
     float4* rayO;    // o.xyz, mint
@@ -147,9 +148,9 @@ k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned int n, gb_hit*
             ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
         }
         if (lane == 0) {
-            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+            atomicAdd(stats + (ANY ? S_ANY_BASE : 0) + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + (ANY ? S_ANY_BASE : 0) + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + (ANY ? S_ANY_BASE : 0) + S_INSTS, (unsigned long long)ts.insts);
         }
     }
 }
@@ -287,9 +288,9 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
             ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
         }
         if (lane == 0) {
-            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+            atomicAdd(stats + S_ANY_BASE + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_ANY_BASE + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_ANY_BASE + S_INSTS, (unsigned long long)ts.insts);
         }
     }
 }
@@ -465,9 +466,9 @@ k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int
             ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
         }
         if (lane == 0) {
-            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
+            atomicAdd(stats + S_ANY_BASE + S_NODES, (unsigned long long)ts.nodes);
+            atomicAdd(stats + S_ANY_BASE + S_PRIMS, (unsigned long long)ts.prims);
+            atomicAdd(stats + S_ANY_BASE + S_INSTS, (unsigned long long)ts.insts);
         }
     }
 }
@@ -593,6 +594,13 @@ struct gb_context {
     uint64_t launches = 0;
     int traceGrid = 0, aoGrid = 0;
     size_t maxWavePaths = 4u << 20;
+    // optional per-kernel-class timing (CUDA event pairs on the context's stream)
+    bool timingOn = false;
+    std::vector<cudaEvent_t> evPool;
+    size_t evUsed = 0;
+    std::vector<int> evClass; // class of event pair k (events 2k, 2k + 1)
+    double classMs[GB_K_COUNT] = {};
+    uint64_t classLaunches[GB_K_COUNT] = {};
 };
 
 namespace {
@@ -631,6 +639,42 @@ void freeWave(gb_context* ctx) {
     for (void* p : ctx->waveAllocs) cudaFree(p);
     ctx->waveAllocs.clear();
     ctx->capacity = 0;
+}
+
+// Kernel-class timing: an event pair around each launch, resolved at collect time.
+struct KernelTick {
+    gb_context* ctx;
+    bool live = false;
+    KernelTick(gb_context* c, int cls) : ctx(c) {
+        if (!ctx->timingOn) return;
+        if (ctx->evUsed + 2 > ctx->evPool.size()) {
+            for (int k = 0; k < 2; ++k) {
+                cudaEvent_t e = nullptr;
+                if (cudaEventCreate(&e) != cudaSuccess) return;
+                ctx->evPool.push_back(e);
+            }
+        }
+        cudaEventRecord(ctx->evPool[ctx->evUsed], ctx->stream);
+        ctx->evClass.push_back(cls);
+        live = true;
+    }
+    ~KernelTick() {
+        if (!live) return;
+        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], ctx->stream);
+        ctx->evUsed += 2;
+    }
+};
+
+void collectTimes(gb_context* ctx) { // the stream must be idle
+    for (size_t k = 0; 2 * k + 1 < ctx->evUsed; ++k) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->evPool[2 * k], ctx->evPool[2 * k + 1]) == cudaSuccess) {
+            ctx->classMs[ctx->evClass[k]] += ms;
+            ctx->classLaunches[ctx->evClass[k]]++;
+        }
+    }
+    ctx->evUsed = 0;
+    ctx->evClass.clear();
 }
 
 template <typename T>
@@ -725,6 +769,7 @@ int gb_destroy(gb_context* ctx) {
     cudaFree(ctx->stats);
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
+    for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GB_OK;
@@ -927,6 +972,7 @@ static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n
 #define LAUNCH(ANYV, STATSV)                                                                       \
     do {                                                                                           \
         if ((rc = setupTraceKernel(ctx, k_trace<ANYV, STATSV>, &grid)) != GB_OK) return rc;         \
+        KernelTick tick(ctx, GB_K_TRACE);                                                           \
         k_trace<ANYV, STATSV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned int)n, d_hits, \
             d_occ, ctx->traceHead, ctx->stats);                                                     \
     } while (0)
@@ -1031,12 +1077,16 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     GB_CUDA(cudaMemsetAsync(ctx->ctr, 0, kMaxDepthCtr * kCtrStride * sizeof(unsigned int), st));
     PathState psRay = ps;
     if (method != GB_METHOD_AO) psRay.aoCount = nullptr;
-    k_raygen<<<(n + 255) / 256, 256, 0, st>>>(ctx->sc, psRay, wp, src, ctx->ctr, ctx->stats);
+    {
+        KernelTick tick(ctx, GB_K_RAYGEN);
+        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(ctx->sc, psRay, wp, src, ctx->ctr, ctx->stats);
+    }
     ctx->launches++;
     const int shadeGrid = ctx->numSMs * 8;
     auto extend = [&](int b, int singleBin) -> int {
         unsigned int* c = ctx->ctr + b * kCtrStride;
         const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
+        KernelTick tick(ctx, GB_K_EXTEND);
         if (ctx->statsOn) {
             if ((rc = setupTraceKernel(ctx, k_extend<true>, &grid)) != GB_OK) return rc;
             k_extend<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats);
@@ -1049,14 +1099,20 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     };
     if (method == GB_METHOD_AO) {
         if ((rc = extend(0, 1)) != GB_OK) return rc;
-        if (ctx->statsOn) {
-            if ((rc = setupTraceKernel(ctx, k_ao<true>, &grid)) != GB_OK) return rc;
-            k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
-        } else {
-            if ((rc = setupTraceKernel(ctx, k_ao<false>, &grid)) != GB_OK) return rc;
-            k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+        {
+            KernelTick tick(ctx, GB_K_AO);
+            if (ctx->statsOn) {
+                if ((rc = setupTraceKernel(ctx, k_ao<true>, &grid)) != GB_OK) return rc;
+                k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+            } else {
+                if ((rc = setupTraceKernel(ctx, k_ao<false>, &grid)) != GB_OK) return rc;
+                k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+            }
         }
-        k_ao_finish<<<(n + 255) / 256, 256, 0, st>>>(ps, wp);
+        {
+            KernelTick tick(ctx, GB_K_OTHER);
+            k_ao_finish<<<(n + 255) / 256, 256, 0, st>>>(ps, wp);
+        }
         ctx->launches += 2;
     } else if (ctx->sc.nLights > 0) { // no lights: Li returns black before tracing (GoblinPathtracer.cpp:53-56)
         const int depth = wp.maxDepth;
@@ -1069,11 +1125,15 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             unsigned int* cn = ctx->ctr + (b + 1) * kCtrStride;
             unsigned int* qn = ps.qExtend[(b + 1) & 1];
             int eo = last ? 1 : 0;
-            k_shade<GB_MAT_LAMBERT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
-            k_shade<GB_MAT_MIRROR><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
-            k_shade<GB_MAT_TRANSPARENT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+            {
+                KernelTick tick(ctx, GB_K_SHADE);
+                k_shade<GB_MAT_LAMBERT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+                k_shade<GB_MAT_MIRROR><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+                k_shade<GB_MAT_TRANSPARENT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+            }
             ctx->launches += 3;
             if (!last) {
+                KernelTick tick(ctx, GB_K_SHADOW);
                 if (ctx->statsOn) {
                     if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
                     k_shadow<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats);
@@ -1092,7 +1152,10 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         if (fsmem > 200 * 1024) return gb::failWith(GB_ERR_LIMIT, "filter too wide for the film tile");
         GB_CUDA(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
         int tilesX = (wp.width + kFilmTile - 1) / kFilmTile, tilesY = (wp.rows + kFilmTile - 1) / kFilmTile;
-        k_film<<<tilesX * tilesY, 256, fsmem, st>>>(ctx->sc, ps, wp, src, ctx->film, halo);
+        {
+            KernelTick tick(ctx, GB_K_FILM);
+            k_film<<<tilesX * tilesY, 256, fsmem, st>>>(ctx->sc, ps, wp, src, ctx->film, halo);
+        }
         ctx->launches++;
     }
     GB_CUDA(cudaGetLastError());
@@ -1278,9 +1341,12 @@ int gb_get_counters(gb_context* ctx, gb_counters* out) {
     out->camera_samples = h[S_SAMPLES];
     out->rays_closest = h[S_RAYS_CLOSEST];
     out->rays_any = h[S_RAYS_ANY];
-    out->nodes_visited = h[S_NODES];
-    out->prims_tested = h[S_PRIMS];
-    out->instances_entered = h[S_INSTS];
+    out->nodes_visited = h[S_NODES] + h[S_ANY_BASE + S_NODES];
+    out->prims_tested = h[S_PRIMS] + h[S_ANY_BASE + S_PRIMS];
+    out->instances_entered = h[S_INSTS] + h[S_ANY_BASE + S_INSTS];
+    out->nodes_visited_any = h[S_ANY_BASE + S_NODES];
+    out->prims_tested_any = h[S_ANY_BASE + S_PRIMS];
+    out->instances_entered_any = h[S_ANY_BASE + S_INSTS];
     out->kernel_launches = ctx->launches;
     return GB_OK;
 }
@@ -1291,6 +1357,43 @@ int gb_reset_counters(gb_context* ctx) {
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
     GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
     ctx->launches = 0;
+    return GB_OK;
+}
+
+int gb_enable_kernel_timing(gb_context* ctx, int on) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    collectTimes(ctx);
+    ctx->timingOn = on != 0;
+    return GB_OK;
+}
+
+int gb_get_kernel_times(gb_context* ctx, gb_kernel_times* out) {
+    if (!ctx || !out) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    collectTimes(ctx);
+    for (int k = 0; k < GB_K_COUNT; ++k) {
+        out->ms[k] = ctx->classMs[k];
+        out->launches[k] = ctx->classLaunches[k];
+    }
+    return GB_OK;
+}
+
+int gb_reset_kernel_times(gb_context* ctx) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    collectTimes(ctx);
+    for (int k = 0; k < GB_K_COUNT; ++k) { ctx->classMs[k] = 0.0; ctx->classLaunches[k] = 0; }
+    return GB_OK;
+}
+
+int gb_set_wave_paths(gb_context* ctx, size_t max_paths) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (max_paths < 1024 || max_paths > (size_t)1 << 28) return gb::failWith(GB_ERR_INVALID, "wave size out of range");
+    ctx->maxWavePaths = max_paths;
     return GB_OK;
 }
 

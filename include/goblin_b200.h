@@ -200,7 +200,18 @@ typedef struct gb_counters {
     uint64_t prims_tested;      /* triangle / sphere / disk tests            */
     uint64_t instances_entered; /* world->object ray transforms              */
     uint64_t kernel_launches;   /* launches of this library's kernels        */
+    uint64_t nodes_visited_any;     /* the any-hit traversals' share of the  */
+    uint64_t prims_tested_any;      /* three totals above                    */
+    uint64_t instances_entered_any;
 } gb_counters;
+
+/* Kernel classes of the wavefront integrator, for gb_get_kernel_times. */
+enum { GB_K_RAYGEN = 0, GB_K_EXTEND = 1, GB_K_SHADE = 2, GB_K_SHADOW = 3, GB_K_AO = 4, GB_K_FILM = 5,
+       GB_K_TRACE = 6, GB_K_OTHER = 7, GB_K_COUNT = 8 };
+typedef struct gb_kernel_times {
+    double ms[GB_K_COUNT];          /* device time per class, CUDA events       */
+    uint64_t launches[GB_K_COUNT];  /* timed launch groups per class            */
+} gb_kernel_times;
 
 typedef struct gb_scene gb_scene;     /* host-side flattened scene            */
 typedef struct gb_context gb_context; /* one GPU                              */
@@ -275,6 +286,16 @@ int gb_reset_counters(gb_context* ctx);
 /* milliseconds spent in the last gb_render / gb_trace_*_device call's kernels,
  * from CUDA events on the context's stream. Synchronises. */
 int gb_last_kernel_ms(gb_context* ctx, float* ms);
+
+/* Per-kernel-class device time: when enabled, every launch of this library is
+ * bracketed by a CUDA event pair on the context's stream; gb_get_kernel_times
+ * synchronises and returns the sums since the last reset. */
+int gb_enable_kernel_timing(gb_context* ctx, int on);
+int gb_get_kernel_times(gb_context* ctx, gb_kernel_times* out);
+int gb_reset_kernel_times(gb_context* ctx);
+/* Upper bound on the camera samples in flight per wave of the wavefront
+ * integrator (path-state memory ~ 200 B per path). */
+int gb_set_wave_paths(gb_context* ctx, size_t max_paths);
 
 const char* gb_last_error(void);
 const char* gb_version(void);

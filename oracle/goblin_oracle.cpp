@@ -101,6 +101,7 @@ struct Isect {
 
 struct Stats {
     uint64_t nodes = 0, prims = 0, insts = 0, closest = 0, any = 0;
+    uint64_t nodesAny = 0, primsAny = 0, instsAny = 0; // the any-hit walks' share
     uint64_t refIntersect = 0, refOccluded = 0; // calls the reference would have made
 };
 
@@ -424,6 +425,14 @@ struct Oracle {
     // Scene::occluded (src/GoblinScene.cpp:85-87)
     bool occluded(const Ray& ray, Stats& st) const {
         st.any++;
+        const uint64_t n0 = st.nodes, p0 = st.prims, i0 = st.insts;
+        bool occ = occludedWalk(ray, st);
+        st.nodesAny += st.nodes - n0;
+        st.primsAny += st.prims - p0;
+        st.instsAny += st.insts - i0;
+        return occ;
+    }
+    bool occludedWalk(const Ray& ray, Stats& st) const {
         return walk<true>(d->top_nodes, d->n_top_nodes, ray, st, [&](uint32_t slot) {
             const gb_instance& in = d->instances[d->top_order[slot]];
             const gb_model& m = d->models[in.model];
@@ -865,6 +874,7 @@ void addStats(gb_counters* out, const std::vector<Stats>& per, uint64_t samples,
     for (const Stats& p : per) {
         s.nodes += p.nodes; s.prims += p.prims; s.insts += p.insts; s.closest += p.closest; s.any += p.any;
         s.refIntersect += p.refIntersect; s.refOccluded += p.refOccluded;
+        s.nodesAny += p.nodesAny; s.primsAny += p.primsAny; s.instsAny += p.instsAny;
     }
     if (out) {
         out->camera_samples += samples;
@@ -873,6 +883,9 @@ void addStats(gb_counters* out, const std::vector<Stats>& per, uint64_t samples,
         out->nodes_visited += s.nodes;
         out->prims_tested += s.prims;
         out->instances_entered += s.insts;
+        out->nodes_visited_any += s.nodesAny;
+        out->prims_tested_any += s.primsAny;
+        out->instances_entered_any += s.instsAny;
     }
     if (refCalls) { refCalls[0] += s.refIntersect; refCalls[1] += s.refOccluded; }
 }

@@ -148,11 +148,17 @@ def main():
     ref("dump", pt, os.path.join(OUT, "tiny_dump.gbar"))
     dump = gbar.load(os.path.join(OUT, "tiny_dump.gbar"))
     rng = np.random.default_rng(20261018)
+    if "--films-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "tiny_film_pt.npz"), **make_film(pt, 24, 256))
+        np.savez_compressed(os.path.join(OUT, "tiny_film_ao.npz"), **make_film(ao, 16, 64))
+        return
     np.savez_compressed(os.path.join(OUT, "tiny_rays.npz"), **make_rays(pt, rng, dump))
     np.savez_compressed(os.path.join(OUT, "tiny_li_pt.npz"), **make_li(pt, rng, 4096))
     np.savez_compressed(os.path.join(OUT, "tiny_li_ao.npz"), **make_li(ao, rng, 2048, ao=True))
-    np.savez_compressed(os.path.join(OUT, "tiny_film_pt.npz"), **make_film(pt, 8, 1024))
-    np.savez_compressed(os.path.join(OUT, "tiny_film_ao.npz"), **make_film(ao, 8, 256))
+    # many short batches rather than few long ones: the per-pixel variance of the mean is itself
+    # estimated from the batches, and the two-sample t-test in tests/ needs it to be stable
+    np.savez_compressed(os.path.join(OUT, "tiny_film_pt.npz"), **make_film(pt, 24, 256))
+    np.savez_compressed(os.path.join(OUT, "tiny_film_ao.npz"), **make_film(ao, 16, 64))
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         if os.path.isfile(p):

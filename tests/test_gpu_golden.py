@@ -108,29 +108,31 @@ def test_li_ao_golden(ao):
     assert np.abs(got - g["L"]).max() <= 0.0801
 
 
-def _ztest(img, g):
-    mean = g["mean"].astype(np.float64)
-    var = g["var_of_mean"].astype(np.float64)
-    return (img - mean) / np.sqrt(var + 1e-12), mean
+def _batches(ctx, n, spp, seed0):
+    imgs = []
+    total = None
+    for b in range(n):
+        ctx.film_clear()
+        ctx.render(seed=seed0 + b, spp_total=spp)
+        film = ctx.film_download()
+        total = film.astype(np.float64) if total is None else total + film
+        imgs.append(util.film_image(film))
+    return np.stack(imgs), util.film_image(total)
 
 
 def test_film_path_tracer_converged(pt):
-    """Renderer::render + Film (src/GoblinRenderer.cpp:99-126, src/GoblinFilm.cpp:61-173):
-    a 4096-spp Philox render against the reference's 8 x 1024-spp mean.  relMSE < 1e-3 and a
-    per-pixel variance-normalised z-test (the GPU image carries its own variance, about twice
-    the reference mean's, hence sigma_total^2 ~ 3 var_of_mean)."""
+    """Renderer::render + Film (src/GoblinRenderer.cpp:99-126, src/GoblinFilm.cpp:61-173) with the
+    Philox sampler against the reference's own renders (24 x 256 spp, mt19937 stratified sampler):
+    4096 spp in 16 independently seeded batches; relMSE of the total < 1e-3 and a per-pixel
+    variance-normalised two-sample test whose statistic must look standard normal."""
     ctx, scene = pt
     g = util.golden("tiny_film_pt.npz")
-    ctx.film_clear()
-    ctx.render(seed=11, spp_total=4096)
-    film = ctx.film_download()
-    assert film[..., 3].min() > 0
-    img = film[..., :3].astype(np.float64) / film[..., 3:4]
-    assert util.rel_mse(img, g["mean"]) < 1e-3
-    z, _ = _ztest(img, g)
-    z = z / np.sqrt(3.0)
-    assert abs(z.mean()) < 0.1, f"biased: mean z = {z.mean():.3f}"
-    assert (np.abs(z) > 4).mean() < 0.01
+    imgs, total = _batches(ctx, 16, 256, 100)
+    assert util.rel_mse(total, g["mean"]) < 1e-3
+    t = util.film_ttest(imgs, g)
+    assert abs(t.mean()) < 0.1, f"biased: mean t = {t.mean():.3f}"
+    assert 0.85 < t.std() < 1.15, f"t spread {t.std():.3f}"
+    assert (np.abs(t) > 4.5).mean() < 1e-3
     c = ctx.counters()
     assert c["camera_samples"] >= scene.camera_samples(4096)
 
@@ -138,14 +140,11 @@ def test_film_path_tracer_converged(pt):
 def test_film_ao_converged(ao):
     ctx, scene = ao
     g = util.golden("tiny_film_ao.npz")
-    ctx.film_clear()
-    ctx.render(seed=5, spp_total=1024)
-    film = ctx.film_download()
-    img = film[..., :3].astype(np.float64) / film[..., 3:4]
-    assert util.rel_mse(img, g["mean"]) < 1e-3
-    z, _ = _ztest(img, g)
-    z = z / np.sqrt(3.0)
-    assert abs(z.mean()) < 0.1, f"biased: mean z = {z.mean():.3f}"
+    imgs, total = _batches(ctx, 16, 64, 200)
+    assert util.rel_mse(total, g["mean"]) < 1e-3
+    t = util.film_ttest(imgs, g)
+    assert abs(t.mean()) < 0.1, f"biased: mean t = {t.mean():.3f}"
+    assert 0.85 < t.std() < 1.15, f"t spread {t.std():.3f}"
 
 
 def test_spp_sharding_is_a_partition(pt):

@@ -37,3 +37,28 @@ def rel_mse(img, ref, eps=1e-2):
     img = np.asarray(img, np.float64)
     ref = np.asarray(ref, np.float64)
     return float(np.mean((img - ref) ** 2 / (ref ** 2 + eps)))
+
+
+def film_image(film):
+    """Film::writeImage's normalisation: colour / weight (src/GoblinFilm.cpp:164-173)."""
+    film = np.asarray(film, np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        img = film[..., :3] / film[..., 3:4]
+    return np.nan_to_num(img)
+
+
+def film_ttest(images, gold, rel_floor=2e-3):
+    """Per-pixel variance-normalised two-sample test of a stack of independently seeded images
+    against the reference's batch statistics in a tiny_film_*.npz.  Returns the t values of the
+    pixels the reference lit.  The relative floor keeps pixels with (numerically) zero variance --
+    an emitter seen directly has the same radiance in every sample -- from dividing a 1e-6
+    rounding difference by ~0."""
+    images = np.asarray(images, np.float64)
+    b = images.shape[0]
+    mean = images.mean(0)
+    var_of_mean = images.var(0, ddof=1) / b
+    ref = gold["mean"].astype(np.float64)
+    ref_var = gold["var_of_mean"].astype(np.float64)
+    floor = (rel_floor * np.maximum(ref, mean)) ** 2 + 1e-12
+    t = (mean - ref) / np.sqrt(var_of_mean + ref_var + floor)
+    return t[ref.sum(axis=2) > 0]
