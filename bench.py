@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
     ap.add_argument("--wave-paths", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -293,8 +294,9 @@ def main():
     mrays = rays_all / (total_ms * 1e-3) * 1e-6
 
     # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + film download (D2H)
-    e2e_steps = max(1, min(args.steps, 5))
-    for i in range(2):
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
+    host_film = np.zeros(1, np.float32)
+    for i in range(2 if e2e_steps else 0):
         ctx.upload_scene(scene)
     film_ptr, film_floats = ctx.film_device_ptr()
     film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
@@ -313,7 +315,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
-    e2e_value = samples_per_step_all / (e2e_ms / e2e_steps * 1e-3) * 1e-6
+    e2e_value = samples_per_step_all / (e2e_ms / e2e_steps * 1e-3) * 1e-6 if e2e_steps else None
     assert np.isfinite(host_film).all()
 
     if rank == 0:

@@ -15,6 +15,7 @@
 //     shared memory and flushes it with one vector atomic per pixel.
 // No tensor cores, no TMA: traversal is a dependent gather of 32-byte nodes,
 // not a dense contraction (north_star).
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -482,65 +483,83 @@ __global__ void k_ao_finish(PathState ps, WaveParams wp) {
 }
 
 // --------------------------------------------------------------------- film
-// ImageTile::addSample (GoblinFilm.cpp:61-90) for a tile of sample-range
-// pixels: splat into a shared-memory tile with halo, then flush each touched
-// film pixel with one 128-bit atomic (the analogue of Film::mergeTile).
-constexpr int kFilmTile = 16;
+// ImageTile::addSample (GoblinFilm.cpp:61-90) + Film::mergeTile (:140-153) as a
+// warp-per-sample-pixel gather: the samples of one sample-range pixel can only
+// touch the (2 ceil(wx) + 1) x (2 ceil(wy) + 1) film pixels around it, so lane c
+// owns candidate pixel c, the warp streams the pixel's samples 32 at a time
+// (each lane loads one L and regenerates its image position from Philox, then
+// the values are broadcast with shuffles) and every lane accumulates w * L and
+// w for its own pixel in registers.  One 128-bit atomic per touched film pixel
+// per sample pixel replaces 64 scalar atomics per sample.
+// The inclusion test is the reference's: x0 = ceil(dx - w) <= x <= floor(dx + w)
+// clamped to the crop window; for integer x that is dx - w <= x <= dx + w.
+constexpr int kFilmBlock = 256;
 
-__global__ void __launch_bounds__(256)
-k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int halo) {
-    extern __shared__ float s_tile[]; // (tile + 2 halo)^2 x 4
-    const int side = kFilmTile + 2 * halo;
-    const int tilesX = (wp.width + kFilmTile - 1) / kFilmTile;
-    const int tx = blockIdx.x % tilesX, ty = blockIdx.x / tilesX;
-    const int col0 = tx * kFilmTile, row0 = ty * kFilmTile; // within the wave's rows
-    for (int k = threadIdx.x; k < side * side * 4; k += blockDim.x) s_tile[k] = 0.0f;
+__global__ void __launch_bounds__(kFilmBlock)
+k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int radX, int radY,
+    int invExact) {
+    __shared__ float s_table[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_table[k] = __ldg(sc.filterTable + k);
     __syncthreads();
-    const int cols = min(kFilmTile, wp.width - col0), rows = min(kFilmTile, wp.rows - row0);
-    const int baseX = sc.sx0 + col0 - halo, baseY = wp.y0 + row0 - halo; // film pixel of tile cell (0, 0)
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warpsPerBlock = blockDim.x >> 5;
+    const unsigned int nPix = (unsigned int)wp.width * (unsigned int)wp.rows;
+    const int dX = 2 * radX + 1, dY = 2 * radY + 1;
+    const int nCand = dX * dY;
     const int cropX1 = sc.xstart + sc.xcount - 1, cropY1 = sc.ystart + sc.ycount - 1;
-    for (int r = 0; r < rows; ++r) {
-        const unsigned int rowBase = ((unsigned int)(row0 + r) * (unsigned int)wp.width + (unsigned int)col0) *
-            (unsigned int)wp.nSpp;
-        const int nItems = cols * wp.nSpp;
-        for (int k = threadIdx.x; k < nItems; k += blockDim.x) {
-            unsigned int i = rowBase + (unsigned int)k;
-            float4 L = ps.L[i];
-            if (L.x != L.x || L.y != L.y || L.z != L.z) continue; // NaN samples are discarded, weight included
-            int px, py, s;
-            unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
-            float4 u = src.block(id, i, 0);
-            float imageX, imageY;
-            imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
-            float dImageX = imageX - 0.5f, dImageY = imageY - 0.5f;
-            int x0 = (int)ceilf(dImageX - sc.filterWidthX), x1 = (int)floorf(dImageX + sc.filterWidthX);
-            int y0 = (int)ceilf(dImageY - sc.filterWidthY), y1 = (int)floorf(dImageY + sc.filterWidthY);
-            x0 = max(x0, sc.xstart); x1 = min(x1, cropX1);
-            y0 = max(y0, sc.ystart); y1 = min(y1, cropY1);
-            for (int y = y0; y <= y1; ++y) {
-                for (int x = x0; x <= x1; ++x) {
-                    // FilterTable::evaluate: nearest lower entry of the 16 x 16 table
-                    int iy = min((int)floorf(fabsf(16 * ((float)y - dImageY) / sc.filterWidthY)), 15);
-                    int ix = min((int)floorf(fabsf(16 * ((float)x - dImageX) / sc.filterWidthX)), 15);
-                    float w = __ldg(sc.filterTable + iy * 16 + ix);
-                    int cx = x - baseX, cy = y - baseY;
-                    if (cx < 0 || cy < 0 || cx >= side || cy >= side) continue; // cannot happen: halo covers the filter
-                    float* cell = s_tile + 4 * (cy * side + cx);
-                    atomicAdd(cell + 0, w * L.x);
-                    atomicAdd(cell + 1, w * L.y);
-                    atomicAdd(cell + 2, w * L.z);
-                    atomicAdd(cell + 3, w);
+    const float wX = sc.filterWidthX, wY = sc.filterWidthY;
+    const float sX = 16.0f / wX, sY = 16.0f / wY; // exact when the width is a power of two
+    for (unsigned int pix = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); pix < nPix;
+         pix += gridDim.x * warpsPerBlock) {
+        const unsigned int row = pix / (unsigned int)wp.width, col = pix - row * (unsigned int)wp.width;
+        const int px = sc.sx0 + (int)col, py = wp.y0 + (int)row;
+        const unsigned int base = pix * (unsigned int)wp.nSpp;
+        for (int c0 = 0; c0 < nCand; c0 += 32) { // one pass per 32 candidate pixels (one pass for widths <= 2)
+            const int c = c0 + (int)lane;
+            const int cx = px - radX + c % dX, cy = py - radY + c / dX;
+            const bool mine = c < nCand && cx >= sc.xstart && cx <= cropX1 && cy >= sc.ystart && cy <= cropY1;
+            const float fx = (float)cx, fy = (float)cy;
+            float aR = 0.0f, aG = 0.0f, aB = 0.0f, aW = 0.0f;
+            for (int k0 = 0; k0 < wp.nSpp; k0 += 32) {
+                const int k = k0 + (int)lane;
+                float dImageX = 0.0f, dImageY = 0.0f;
+                float4 L = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                bool ok = false;
+                if (k < wp.nSpp) {
+                    const unsigned int i = base + (unsigned int)k;
+                    L = ps.L[i];
+                    ok = !(L.x != L.x || L.y != L.y || L.z != L.z); // NaN samples are discarded, weight included
+                    int qx, qy, s;
+                    unsigned long long id = sampleIdOf(sc, wp, i, &qx, &qy, &s);
+                    float4 u = src.block(id, i, 0);
+                    float imageX, imageY;
+                    imagePosition(wp, qx, qy, s, u, src.table != nullptr, &imageX, &imageY);
+                    dImageX = imageX - 0.5f;
+                    dImageY = imageY - 0.5f;
+                }
+                const unsigned int okMask = __ballot_sync(0xffffffffu, ok);
+                const int cnt = min(32, wp.nSpp - k0);
+                for (int j = 0; j < cnt; ++j) {
+                    const float sx = __shfl_sync(0xffffffffu, dImageX, j);
+                    const float sy = __shfl_sync(0xffffffffu, dImageY, j);
+                    const float lr = __shfl_sync(0xffffffffu, L.x, j);
+                    const float lg = __shfl_sync(0xffffffffu, L.y, j);
+                    const float lb = __shfl_sync(0xffffffffu, L.z, j);
+                    if (!((okMask >> j) & 1u)) continue;
+                    if (mine && fx >= sx - wX && fx <= sx + wX && fy >= sy - wY && fy <= sy + wY) {
+                        // FilterTable::evaluate: nearest lower entry of the 16 x 16 table
+                        const float tx = invExact ? fabsf((fx - sx) * sX) : fabsf(16 * (fx - sx) / wX);
+                        const float ty = invExact ? fabsf((fy - sy) * sY) : fabsf(16 * (fy - sy) / wY);
+                        const int ix = min((int)floorf(tx), 15), iy = min((int)floorf(ty), 15);
+                        const float w = s_table[iy * 16 + ix];
+                        aR += w * lr; aG += w * lg; aB += w * lb; aW += w;
+                    }
                 }
             }
+            if (mine && (aW != 0.0f || aR != 0.0f || aG != 0.0f || aB != 0.0f)) {
+                atomicAdd(film + (size_t)cy * sc.xres + cx, make_float4(aR, aG, aB, aW));
+            }
         }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < side * side; k += blockDim.x) {
-        float4 v = make_float4(s_tile[4 * k], s_tile[4 * k + 1], s_tile[4 * k + 2], s_tile[4 * k + 3]);
-        if (v.w == 0.0f && v.x == 0.0f && v.y == 0.0f && v.z == 0.0f) continue;
-        int x = baseX + k % side, y = baseY + k / side;
-        if (x < 0 || y < 0 || x >= sc.xres || y >= sc.yres) continue;
-        atomicAdd(film + (size_t)y * sc.xres + x, v);
     }
 }
 
@@ -1146,15 +1165,16 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         }
     }
     if (toFilm) {
-        int halo = (int)ceilf(std::max(ctx->sc.filterWidthX, ctx->sc.filterWidthY) + 0.5f);
-        int side = kFilmTile + 2 * halo;
-        size_t fsmem = (size_t)side * side * 4 * sizeof(float);
-        if (fsmem > 200 * 1024) return gb::failWith(GB_ERR_LIMIT, "filter too wide for the film tile");
-        GB_CUDA(cudaFuncSetAttribute(k_film, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        int tilesX = (wp.width + kFilmTile - 1) / kFilmTile, tilesY = (wp.rows + kFilmTile - 1) / kFilmTile;
+        const float wx = ctx->sc.filterWidthX, wy = ctx->sc.filterWidthY;
+        const int radX = (int)ceilf(wx), radY = (int)ceilf(wy);
+        auto pow2 = [](float v) { int e; return std::frexp(v, &e) == 0.5f; };
+        const int invExact = pow2(wx) && pow2(wy) ? 1 : 0; // 16 * x / w == x * (16 / w) bit for bit
+        const unsigned int nPix = (unsigned int)wp.width * (unsigned int)wp.rows;
+        const unsigned int warpsPerBlock = kFilmBlock / 32;
+        unsigned int blocks = std::min<unsigned int>((nPix + warpsPerBlock - 1) / warpsPerBlock, (unsigned int)ctx->numSMs * 16u);
         {
             KernelTick tick(ctx, GB_K_FILM);
-            k_film<<<tilesX * tilesY, 256, fsmem, st>>>(ctx->sc, ps, wp, src, ctx->film, halo);
+            k_film<<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY, invExact);
         }
         ctx->launches++;
     }
