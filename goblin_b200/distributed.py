@@ -1,0 +1,66 @@
+"""Multi-GPU rendering: samples-per-pixel sharded over one process per GPU.
+
+The reference has one collective-like step, Film::mergeTile (src/GoblinFilm.cpp:
+140-153): every worker thread's full-frame (colour, weight) tile is summed into
+the film under a mutex.  Across GPUs that is an all-reduce(sum) of the 4 W H
+float film buffer, done here with torch.distributed (NCCL over NVLink on the
+GPU box; any backend for host tensors in the CPU tests).  Geometry is never
+partitioned: every rank holds a full scene replica and camera samples are
+independent, so the film sum is the only data-path exchange.
+"""
+import numpy as np
+
+
+def spp_shard(spp_total, rank, world):
+    """Sample-index range [begin, end) of `rank`: contiguous, disjoint, covering [0, spp_total).
+    Philox is keyed on (seed, pixel, sample index), so the union over ranks is exactly the
+    1-GPU sample set."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank / world size")
+    return spp_total * rank // world, spp_total * (rank + 1) // world
+
+
+class DeviceFilm:
+    """The context's device film exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ctx):
+        ptr, n_floats = ctx.film_device_ptr()
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    def tensor(self, device):
+        import torch
+        return torch.as_tensor(self, device=device)
+
+
+def allreduce_film(film, group=None):
+    """Sum the (r, g, b, weight) film over all ranks, in place.  `film` is a torch tensor (the
+    device film on the GPU path, a host tensor in the gloo tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(film, op=dist.ReduceOp.SUM, group=group)
+    return film
+
+
+def render_sharded(ctx, scene, seed, rank, world, spp=None, stream=None, **render_kw):
+    """Render this rank's share of the samples into the context's device film and all-reduce it.
+    Asynchronous on the context's stream (pass the torch ExternalStream wrapping it so that the
+    NCCL all-reduce is ordered after the render kernels)."""
+    import torch
+    spp_total = scene.spp_squared(spp)
+    begin, end = spp_shard(spp_total, rank, world)
+    device = torch.device("cuda", torch.cuda.current_device())
+    if stream is None:
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    with torch.cuda.stream(stream):
+        ctx.film_clear()
+        ctx.render(seed=seed, spp_total=spp_total, spp_begin=begin, spp_end=end, **render_kw)
+        film = DeviceFilm(ctx).tensor(device)
+        allreduce_film(film)
+    return film
+
+
+def normalize(film_rgbw):
+    """Film::writeImage: colour / weight (src/GoblinFilm.cpp:164-173)."""
+    film_rgbw = np.asarray(film_rgbw, np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.nan_to_num(film_rgbw[..., :3] / film_rgbw[..., 3:4])
