@@ -27,6 +27,7 @@
 #include "device_scene.h"
 #include "image_io.h"
 #include "rt_core.cuh"
+#include "traverse.cuh"
 #include "shade.cuh"
 
 namespace gb {
@@ -34,8 +35,10 @@ namespace gb {
 constexpr int kTraceBlock = 256;   // threads per traversal block
 constexpr int kShadeBlock = 128;
 constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
+constexpr size_t kMaxTraceSmem = 200 * 1024;
 constexpr int kCtrStride = 16;     // counters per bounce
-enum { C_EXTEND = 0, C_EXTEND_HEAD = 1, C_MAT0 = 2, C_SHADOW = 5, C_SHADOW_HEAD = 6, C_AO_HEAD = 7 };
+// per-bounce counters; the *_HEAD cursors are 64-bit (two slots, 8-byte aligned)
+enum { C_EXTEND = 0, C_SHADOW = 1, C_MAT0 = 2, C_EXTEND_HEAD = 6, C_SHADOW_HEAD = 8, C_AO_HEAD = 10 };
 // traversal statistics are kept apart for closest-hit and any-hit walks (S_ANY_BASE + ...)
 enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_ANY_BASE = 8, S_COUNT = 16 };
 
@@ -94,51 +97,12 @@ __device__ __forceinline__ void imagePosition(const WaveParams& wp, int px, int 
     *imageY = (float)py + ((float)cy + u.y) * sub;
 }
 
-// ------------------------------------------------------------ stand-alone trace
+// Shared tail of the traversal kernels: ray count and (optional) traversal statistics, one
+// 64-bit atomic per warp.
 template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
-k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned int n, gb_hit* __restrict__ hits,
-    unsigned char* __restrict__ occluded, unsigned int* head, unsigned long long* stats) {
-    extern __shared__ unsigned int s_stack[];
-    SmemStack st{s_stack + threadIdx.x, blockDim.x};
+__device__ __forceinline__ void flushStats(unsigned long long* stats, unsigned int done, const TraceStats& tsIn) {
     const unsigned int lane = threadIdx.x & 31;
-    TraceStats ts{0, 0, 0};
-    unsigned int done = 0;
-    while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(head, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned int i = base + lane;
-        if (i < n) {
-            const float4* r = reinterpret_cast<const float4*>(rays + i);
-            float4 a = __ldg(r), b = __ldg(r + 1);
-            float3 o = make3(a.x, a.y, a.z), d = make3(a.w, b.x, b.y);
-            HitRec h;
-            bool found = traceScene<ANY, STATS>(sc, o, d, b.z, b.w, &h, st, &ts);
-            if (ANY) {
-                occluded[i] = found ? 1 : 0;
-            } else {
-                gb_hit out;
-                if (found) {
-                    int4 sh = __ldg(sc.instShade + h.inst);
-                    int4 info = __ldg(sc.instInfo + h.inst);
-                    out.t = h.t;
-                    out.eps = 1e-3f * h.t;
-                    out.inst = sh.x;
-                    out.prim = 0;
-                    if (info.x == GB_GEOM_MESH) {
-                        out.prim = (int)__float_as_uint(__ldg(sc.triRec + 3 * (size_t)(info.z + h.prim) + 2).y);
-                    }
-                } else {
-                    out.t = 0.0f; out.eps = 0.0f; out.inst = -1; out.prim = -1;
-                }
-                *reinterpret_cast<float4*>(hits + i) = *reinterpret_cast<float4*>(&out);
-            }
-            ++done;
-        }
-    }
-    // one 64-bit atomic per warp for the ray count; traversal statistics only when asked
+    TraceStats ts = tsIn;
     unsigned int total = done;
     for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
     if (lane == 0 && total) atomicAdd(stats + (ANY ? S_RAYS_ANY : S_RAYS_CLOSEST), (unsigned long long)total);
@@ -154,6 +118,63 @@ k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned int n, gb_hit*
             atomicAdd(stats + (ANY ? S_ANY_BASE : 0) + S_INSTS, (unsigned long long)ts.insts);
         }
     }
+}
+
+#define GB_TRACE_SMEM(stackEntries)                                                    \
+    extern __shared__ uint2 s_dyn[];                                                   \
+    uint2* s_stack = s_dyn;                                                            \
+    float* s_ray = reinterpret_cast<float*>(s_dyn + (size_t)(stackEntries) * blockDim.x)
+
+// ------------------------------------------------------------ stand-alone trace
+template <bool ANY>
+struct TracePolicy {
+    const gb_ray* rays;
+    gb_hit* hits;
+    unsigned char* occluded;
+    const DeviceScene* sc;
+    __device__ __forceinline__ bool fetch(unsigned long long i, float3* o, float3* d, float* mint, float* maxt) {
+        const float4* r = reinterpret_cast<const float4*>(rays + i);
+        float4 a = __ldg(r), b = __ldg(r + 1);
+        *o = make3(a.x, a.y, a.z);
+        *d = make3(a.w, b.x, b.y);
+        *mint = b.z;
+        *maxt = b.w;
+        return true;
+    }
+    __device__ __forceinline__ void finish(bool done, unsigned long long i, bool found, const HitRec& h) {
+        if (!done) return;
+        if (ANY) {
+            occluded[i] = found ? 1 : 0;
+            return;
+        }
+        gb_hit out;
+        if (found) {
+            int4 sh = __ldg(sc->instShade + h.inst);
+            int4 info = __ldg(sc->instInfo + h.inst);
+            out.t = h.t;
+            out.eps = 1e-3f * h.t;
+            out.inst = sh.x;
+            out.prim = 0;
+            if (info.x == GB_GEOM_MESH) {
+                out.prim = (int)__float_as_uint(__ldg(sc->triRec + 3 * (size_t)(info.z + h.prim) + 2).y);
+            }
+        } else {
+            out.t = 0.0f; out.eps = 0.0f; out.inst = -1; out.prim = -1;
+        }
+        *reinterpret_cast<float4*>(hits + i) = *reinterpret_cast<float4*>(&out);
+    }
+};
+
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned long long n, gb_hit* __restrict__ hits,
+    unsigned char* __restrict__ occluded, unsigned long long* head, unsigned long long* stats, int stackEntries) {
+    GB_TRACE_SMEM(stackEntries);
+    TracePolicy<ANY> pol{rays, hits, occluded, &sc};
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    persistentTrace<ANY, STATS>(sc, pol, n, head, s_stack, s_ray, ts, &done);
+    flushStats<ANY, STATS>(stats, done, ts);
 }
 
 // ------------------------------------------------------------------- raygen
@@ -182,40 +203,35 @@ __global__ void k_raygen(DeviceScene sc, PathState ps, WaveParams wp, SampleSour
 
 // ------------------------------------------------------------------- extend
 // Scene::intersect for every queued path, then bin the hits by material.
-template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
-k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
-    unsigned long long* stats) {
-    extern __shared__ unsigned int s_stack[];
-    SmemStack st{s_stack + threadIdx.x, blockDim.x};
-    const unsigned int lane = threadIdx.x & 31;
-    const unsigned int n = ctr[C_EXTEND];
-    TraceStats ts{0, 0, 0};
-    unsigned int done = 0;
-    while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(ctr + C_EXTEND_HEAD, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned int j = base + lane;
+struct ExtendPolicy {
+    const DeviceScene* sc;
+    PathState ps;
+    const unsigned int* queue;
+    unsigned int* ctr;
+    int singleBin;
+    unsigned int path; // per lane: the path the lane's ray belongs to
+    __device__ __forceinline__ bool fetch(unsigned long long j, float3* o, float3* d, float* mint, float* maxt) {
+        path = queue ? __ldg(queue + j) : (unsigned int)j;
+        float4 a = ps.rayO[path], b = ps.rayD[path];
+        *o = make3(a.x, a.y, a.z);
+        *d = make3(b.x, b.y, b.z);
+        *mint = a.w;
+        *maxt = INFINITY;
+        return true;
+    }
+    __device__ __forceinline__ void finish(bool done, unsigned long long, bool found, const HitRec& h) {
+        const unsigned int lane = threadIdx.x & 31;
         int bin = -1;
-        unsigned int i = 0;
-        if (j < n) {
-            i = queue ? __ldg(queue + j) : j;
-            float4 a = ps.rayO[i], b = ps.rayD[i];
-            HitRec h;
-            bool found = traceScene<false, STATS>(sc, make3(a.x, a.y, a.z), make3(b.x, b.y, b.z), a.w, INFINITY,
-                &h, st, &ts);
-            ps.hit[i] = make_float4(h.t, h.b1, h.b2, 0.0f);
-            ps.hitId[i] = make_int2(h.inst, h.prim);
+        if (done) {
+            ps.hit[path] = make_float4(h.t, h.b1, h.b2, 0.0f);
+            ps.hitId[path] = make_int2(h.inst, h.prim);
             if (found) {
                 if (singleBin) bin = 0;
                 else {
-                    int mat = __ldg(sc.instShade + h.inst).z;
-                    bin = __float_as_int(__ldg(&sc.materials[mat].kdType).w);
+                    int mat = __ldg(sc->instShade + h.inst).z;
+                    bin = __float_as_int(__ldg(&sc->materials[mat].kdType).w);
                 }
             }
-            ++done;
         }
         // warp-aggregated append to the material queues
 #pragma unroll
@@ -226,74 +242,58 @@ k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, u
                 unsigned int start = 0;
                 if (lane == leader) start = atomicAdd(ctr + C_MAT0 + m, __popc(mask));
                 start = __shfl_sync(0xffffffffu, start, leader);
-                if (bin == m) ps.qMat[m][start + __popc(mask & ((1u << lane) - 1))] = i;
+                if (bin == m) ps.qMat[m][start + __popc(mask & ((1u << lane) - 1))] = path;
             }
         }
     }
-    unsigned int total = done;
-    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-    if (lane == 0 && total) atomicAdd(stats + S_RAYS_CLOSEST, (unsigned long long)total);
-    if (STATS) {
-        for (int off = 16; off > 0; off >>= 1) {
-            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
-            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
-            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
-        }
-        if (lane == 0) {
-            atomicAdd(stats + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_INSTS, (unsigned long long)ts.insts);
-        }
-    }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(kTraceBlock)
+k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
+    unsigned long long* stats, int stackEntries) {
+    GB_TRACE_SMEM(stackEntries);
+    ExtendPolicy pol{&sc, ps, queue, ctr, singleBin, 0u};
+    TraceStats ts{0, 0, 0};
+    unsigned int done = 0;
+    persistentTrace<false, STATS>(sc, pol, (unsigned long long)ctr[C_EXTEND],
+        reinterpret_cast<unsigned long long*>(ctr + C_EXTEND_HEAD), s_stack, s_ray, ts, &done);
+    flushStats<false, STATS>(stats, done, ts);
 }
 
 // ------------------------------------------------------------------- shadow
 // Scene::occluded for every queued shadow segment; unoccluded segments add
 // their (already weighted) contribution to the owning path.
+struct ShadowPolicy {
+    PathState ps;
+    __device__ __forceinline__ bool fetch(unsigned long long j, float3* o, float3* d, float* mint, float* maxt) {
+        float4 a = ps.shO[j], b = ps.shD[j];
+        *o = make3(a.x, a.y, a.z);
+        *d = make3(b.x, b.y, b.z);
+        *mint = a.w;
+        *maxt = b.w;
+        return true;
+    }
+    __device__ __forceinline__ void finish(bool done, unsigned long long j, bool found, const HitRec&) {
+        if (!done || found) return;
+        float4 c = ps.shC[j];
+        unsigned int i = (unsigned int)__float_as_int(c.w);
+        float4 L = ps.L[i]; // one shadow segment per path per bounce: no race
+        L.x += c.x; L.y += c.y; L.z += c.z;
+        ps.L[i] = L;
+    }
+};
+
 template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock)
-k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats) {
-    extern __shared__ unsigned int s_stack[];
-    SmemStack st{s_stack + threadIdx.x, blockDim.x};
-    const unsigned int lane = threadIdx.x & 31;
-    const unsigned int n = ctr[C_SHADOW];
+k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats, int stackEntries) {
+    GB_TRACE_SMEM(stackEntries);
+    ShadowPolicy pol{ps};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(ctr + C_SHADOW_HEAD, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned int j = base + lane;
-        if (j < n) {
-            float4 a = ps.shO[j], b = ps.shD[j];
-            HitRec h;
-            bool occ = traceScene<true, STATS>(sc, make3(a.x, a.y, a.z), make3(b.x, b.y, b.z), a.w, b.w, &h, st, &ts);
-            if (!occ) {
-                float4 c = ps.shC[j];
-                unsigned int i = (unsigned int)__float_as_int(c.w);
-                float4 L = ps.L[i]; // one shadow segment per path per bounce: no race
-                L.x += c.x; L.y += c.y; L.z += c.z;
-                ps.L[i] = L;
-            }
-            ++done;
-        }
-    }
-    unsigned int total = done;
-    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-    if (lane == 0 && total) atomicAdd(stats + S_RAYS_ANY, (unsigned long long)total);
-    if (STATS) {
-        for (int off = 16; off > 0; off >>= 1) {
-            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
-            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
-            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
-        }
-        if (lane == 0) {
-            atomicAdd(stats + S_ANY_BASE + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_ANY_BASE + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_ANY_BASE + S_INSTS, (unsigned long long)ts.insts);
-        }
-    }
+    persistentTrace<true, STATS>(sc, pol, (unsigned long long)ctr[C_SHADOW],
+        reinterpret_cast<unsigned long long*>(ctr + C_SHADOW_HEAD), s_stack, s_ray, ts, &done);
+    flushStats<true, STATS>(stats, done, ts);
 }
 
 // -------------------------------------------------------------------- shade
@@ -417,61 +417,53 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
 
 // ----------------------------------------------------------------------- AO
 // AORenderer::Li (GoblinAO.cpp:12-37): work item = (hit path, occlusion ray).
+struct AOPolicy {
+    const DeviceScene* sc;
+    PathState ps;
+    WaveParams wp;
+    SampleSource src;
+    unsigned int path;
+    __device__ __forceinline__ bool fetch(unsigned long long j, float3* o, float3* d, float* mint, float* maxt) {
+        unsigned int q = (unsigned int)(j / (unsigned int)wp.aoSamples);
+        unsigned int a = (unsigned int)(j - (unsigned long long)q * (unsigned int)wp.aoSamples);
+        unsigned int i = __ldg(ps.qMat[0] + q);
+        path = i;
+        float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
+        int2 hid = ps.hitId[i];
+        HitRec h;
+        h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
+        Frag fr = buildFragment(*sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
+        int px, py, s;
+        unsigned long long id = sampleIdOf(*sc, wp, i, &px, &py, &s);
+        float2 u = src.aoPair(id, i, a);
+        if (!src.table) { // the reference stratifies the AO directions on a root x root grid
+            float sub = 1.0f / (float)wp.aoRoot;
+            u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
+            u.y = ((float)(a / (unsigned int)wp.aoRoot) + u.y) * sub;
+        }
+        *o = fr.p;
+        *d = shadeToWorld(makeFrame(fr), uniformSampleHemisphere(u.x, u.y));
+        *mint = 1e-3f * h.t;
+        *maxt = INFINITY;
+        return true;
+    }
+    __device__ __forceinline__ void finish(bool done, unsigned long long, bool found, const HitRec&) {
+        if (done && !found) atomicAdd(ps.aoCount + path, 1u);
+    }
+};
+
 template <bool STATS>
 __global__ void __launch_bounds__(kTraceBlock)
-k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr, unsigned long long* stats) {
-    extern __shared__ unsigned int s_stack[];
-    SmemStack st{s_stack + threadIdx.x, blockDim.x};
-    const unsigned int lane = threadIdx.x & 31;
-    const unsigned long long n = (unsigned long long)ctr[C_MAT0] * (unsigned long long)wp.aoSamples;
+k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr, unsigned long long* stats,
+    int stackEntries) {
+    GB_TRACE_SMEM(stackEntries);
+    AOPolicy pol{&sc, ps, wp, src, 0u};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    unsigned long long* head = reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD + 1); // 8-byte aligned slot
-    while (true) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(head, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        unsigned long long j = base + lane;
-        if (j < n) {
-            unsigned int q = (unsigned int)(j / (unsigned int)wp.aoSamples);
-            unsigned int a = (unsigned int)(j - (unsigned long long)q * (unsigned int)wp.aoSamples);
-            unsigned int i = __ldg(ps.qMat[0] + q);
-            float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
-            int2 hid = ps.hitId[i];
-            HitRec h;
-            h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
-            Frag fr = buildFragment(sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
-            int px, py, s;
-            unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
-            float2 u = src.aoPair(id, i, a);
-            if (!src.table) { // the reference stratifies the AO directions on a root x root grid
-                float sub = 1.0f / (float)wp.aoRoot;
-                u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
-                u.y = ((float)(a / (unsigned int)wp.aoRoot) + u.y) * sub;
-            }
-            float3 dir = shadeToWorld(makeFrame(fr), uniformSampleHemisphere(u.x, u.y));
-            HitRec hh;
-            bool occ = traceScene<true, STATS>(sc, fr.p, dir, 1e-3f * h.t, INFINITY, &hh, st, &ts);
-            if (!occ) atomicAdd(ps.aoCount + i, 1u);
-            ++done;
-        }
-    }
-    unsigned int total = done;
-    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
-    if (lane == 0 && total) atomicAdd(stats + S_RAYS_ANY, (unsigned long long)total);
-    if (STATS) {
-        for (int off = 16; off > 0; off >>= 1) {
-            ts.nodes += __shfl_xor_sync(0xffffffffu, ts.nodes, off);
-            ts.prims += __shfl_xor_sync(0xffffffffu, ts.prims, off);
-            ts.insts += __shfl_xor_sync(0xffffffffu, ts.insts, off);
-        }
-        if (lane == 0) {
-            atomicAdd(stats + S_ANY_BASE + S_NODES, (unsigned long long)ts.nodes);
-            atomicAdd(stats + S_ANY_BASE + S_PRIMS, (unsigned long long)ts.prims);
-            atomicAdd(stats + S_ANY_BASE + S_INSTS, (unsigned long long)ts.insts);
-        }
-    }
+    const unsigned long long n = (unsigned long long)ctr[C_MAT0] * (unsigned long long)wp.aoSamples;
+    persistentTrace<true, STATS>(sc, pol, n, reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD), s_stack, s_ray,
+        ts, &done);
+    flushStats<true, STATS>(stats, done, ts);
 }
 
 __global__ void k_ao_finish(PathState ps, WaveParams wp) {
@@ -607,7 +599,7 @@ struct gb_context {
     PathState ps{};
     std::vector<void*> waveAllocs;
     unsigned int* ctr = nullptr; // (kMaxDepthCtr) x kCtrStride
-    unsigned int* traceHead = nullptr;
+    unsigned long long* traceHead = nullptr;
     unsigned long long* stats = nullptr;
     bool statsOn = false;
     uint64_t launches = 0;
@@ -721,7 +713,8 @@ int ensureWave(gb_context* ctx, size_t paths) {
     return GB_OK;
 }
 
-size_t traceSmem(const gb_context* ctx) { return (size_t)ctx->stackEntries * kTraceBlock * sizeof(unsigned int); }
+// per thread: stackEntries 8-byte stack entries + the 6-float world-space ray
+size_t traceSmem(const gb_context* ctx) { return ((size_t)ctx->stackEntries * sizeof(uint2) + 6 * sizeof(float)) * kTraceBlock; }
 
 template <typename K>
 int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
@@ -838,6 +831,53 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     }
     // push-far/go-near keeps at most one entry per level; both levels share one column
     ctx->stackEntries = topDepth + modelDepth + 2;
+    // pair nodes (traverse.cuh): per interior node, both child boxes + child references
+    auto refOf = [](const gb_bvh_node* nodes, const std::vector<uint32_t>& pairIndex, uint32_t node) -> uint32_t {
+        const gb_bvh_node& nd = nodes[node];
+        if (nd.nprims == 0) return pairIndex[node];
+        if (nd.nprims == 1) return REF_LEAF | nd.offset;
+        return REF_LEAF | REF_MULTI | node;
+    };
+    auto buildPairs = [&](const gb_bvh_node* nodes, uint32_t count, std::vector<float4>& out, uint32_t* rootRef) -> bool {
+        std::vector<uint32_t> pairIndex(count, 0u);
+        uint32_t nPairs = 0;
+        for (uint32_t i = 0; i < count; ++i) {
+            if (nodes[i].nprims == 0) pairIndex[i] = nPairs++;
+            else if (nodes[i].nprims == 1 ? nodes[i].offset > REF_INDEX : i > REF_INDEX) return false;
+        }
+        if (nPairs > REF_INDEX) return false;
+        size_t base = out.size();
+        out.resize(base + 4 * (size_t)nPairs);
+        for (uint32_t i = 0; i < count; ++i) {
+            const gb_bvh_node& nd = nodes[i];
+            if (nd.nprims != 0) continue;
+            const gb_bvh_node& l = nodes[i + 1];
+            const gb_bvh_node& r = nodes[nd.offset];
+            float4* q = &out[base + 4 * (size_t)pairIndex[i]];
+            q[0] = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], l.bmax[0]);
+            q[1] = make_float4(l.bmax[1], l.bmax[2], r.bmin[0], r.bmin[1]);
+            q[2] = make_float4(r.bmin[2], r.bmax[0], r.bmax[1], r.bmax[2]);
+            uint32_t w[4] = {refOf(nodes, pairIndex, i + 1), refOf(nodes, pairIndex, nd.offset), nd.axis, 0u};
+            std::memcpy(&q[3], w, 16);
+        }
+        *rootRef = count ? refOf(nodes, pairIndex, 0) : REF_NONE;
+        return true;
+    };
+    std::vector<float4> topPairs, modelPairs;
+    uint32_t topRootRef = REF_NONE;
+    if (!buildPairs(d->top_nodes, d->n_top_nodes, topPairs, &topRootRef)) {
+        return gb::failWith(GB_ERR_LIMIT, "top-level BVH exceeds the 30-bit node reference");
+    }
+    std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE), modelPairBase(d->n_models, 0u);
+    for (uint32_t m = 0; m < d->n_models; ++m) {
+        const gb_model& md = d->models[m];
+        if (md.kind != GB_GEOM_MESH) continue;
+        modelPairBase[m] = (uint32_t)(modelPairs.size() / 4);
+        if (modelPairs.size() / 4 > 0xffffffffull ||
+            !buildPairs(d->model_nodes + md.node_offset, md.node_count, modelPairs, &modelRootRef[m])) {
+            return gb::failWith(GB_ERR_LIMIT, "model BVH exceeds the 30-bit node reference");
+        }
+    }
     if (ctx->stackEntries > 2 * kMaxStack) {
         return gb::failWith(GB_ERR_LIMIT, "BVH deeper than the traversal stack (reference: todo[64] per level)");
     }
@@ -845,7 +885,7 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const uint32_t nInst = d->n_instances;
     std::vector<float4> instToObject(3 * (size_t)nInst), instToWorld(3 * (size_t)nInst);
     std::vector<int4> instInfo(nInst), instShade(nInst);
-    std::vector<uint32_t> instNodeCount(nInst);
+    std::vector<int4> instInfo2(nInst);
     // triangle records are built once per distinct (node_offset, tri_offset) geometry
     std::vector<float4> triRec(3 * (size_t)d->n_tris);
     std::vector<int4> modelShade(d->n_models);
@@ -888,7 +928,8 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         std::memcpy(&radiusBits, &md.radius, 4);
         instInfo[s] = make_int4(md.kind, (int)md.node_offset, (int)md.tri_offset, radiusBits);
         instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
-        instNodeCount[s] = md.kind == GB_GEOM_MESH ? md.node_count : 0u;
+        instInfo2[s] = make_int4((int)modelRootRef[in.model], (int)modelPairBase[in.model],
+            md.kind == GB_GEOM_MESH ? (int)md.node_count : 0, 0);
         if (md.area_light >= 0) hasArea = true;
     }
     std::vector<DeviceMaterial> mats(d->n_materials);
@@ -940,7 +981,9 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     UP(sc.instToWorld, instToWorld.data(), instToWorld.size());
     UP(sc.instInfo, instInfo.data(), instInfo.size());
     UP(sc.instShade, instShade.data(), instShade.size());
-    UP(sc.instNodeCount, instNodeCount.data(), instNodeCount.size());
+    UP(sc.instInfo2, instInfo2.data(), instInfo2.size());
+    UP(sc.topPairs, topPairs.data(), topPairs.size());
+    UP(sc.modelPairs, modelPairs.data(), modelPairs.size());
     UP(sc.triRec, triRec.data(), triRec.size());
     UP(sc.modelShade, modelShade.data(), modelShade.size());
     UP(sc.triIndex, d->tri_index, 3 * (size_t)d->n_tris);
@@ -953,6 +996,7 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     UP(sc.filterTable, d->film.filter_table, (size_t)256);
 #undef UP
     sc.nTopNodes = d->n_top_nodes;
+    sc.topRootRef = topRootRef;
     sc.nInstances = nInst;
     sc.nLights = d->n_lights;
     sc.lightIntegral = integral;
@@ -983,17 +1027,16 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
 
 static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n, gb_hit* d_hits, unsigned char* d_occ) {
     if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
-    if (n > 0xfffffff0ull) return gb::failWith(GB_ERR_LIMIT, "ray batch too large");
     size_t smem = traceSmem(ctx);
     int grid = 0, rc;
-    GB_CUDA(cudaMemsetAsync(ctx->traceHead, 0, 4, ctx->stream));
+    GB_CUDA(cudaMemsetAsync(ctx->traceHead, 0, 8, ctx->stream));
     GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
 #define LAUNCH(ANYV, STATSV)                                                                       \
     do {                                                                                           \
         if ((rc = setupTraceKernel(ctx, k_trace<ANYV, STATSV>, &grid)) != GB_OK) return rc;         \
         KernelTick tick(ctx, GB_K_TRACE);                                                           \
-        k_trace<ANYV, STATSV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned int)n, d_hits, \
-            d_occ, ctx->traceHead, ctx->stats);                                                     \
+        k_trace<ANYV, STATSV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned long long)n, d_hits, \
+            d_occ, ctx->traceHead, ctx->stats, ctx->stackEntries);                                  \
     } while (0)
     if (any) { if (ctx->statsOn) LAUNCH(true, true); else LAUNCH(true, false); }
     else { if (ctx->statsOn) LAUNCH(false, true); else LAUNCH(false, false); }
@@ -1108,10 +1151,10 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         KernelTick tick(ctx, GB_K_EXTEND);
         if (ctx->statsOn) {
             if ((rc = setupTraceKernel(ctx, k_extend<true>, &grid)) != GB_OK) return rc;
-            k_extend<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats);
+            k_extend<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries);
         } else {
             if ((rc = setupTraceKernel(ctx, k_extend<false>, &grid)) != GB_OK) return rc;
-            k_extend<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats);
+            k_extend<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries);
         }
         ctx->launches++;
         return GB_OK;
@@ -1122,10 +1165,10 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             KernelTick tick(ctx, GB_K_AO);
             if (ctx->statsOn) {
                 if ((rc = setupTraceKernel(ctx, k_ao<true>, &grid)) != GB_OK) return rc;
-                k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+                k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);
             } else {
                 if ((rc = setupTraceKernel(ctx, k_ao<false>, &grid)) != GB_OK) return rc;
-                k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats);
+                k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);
             }
         }
         {
@@ -1155,10 +1198,10 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                 KernelTick tick(ctx, GB_K_SHADOW);
                 if (ctx->statsOn) {
                     if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
-                    k_shadow<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats);
+                    k_shadow<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
                 } else {
                     if ((rc = setupTraceKernel(ctx, k_shadow<false>, &grid)) != GB_OK) return rc;
-                    k_shadow<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats);
+                    k_shadow<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
                 }
                 ctx->launches++;
             }

@@ -3,8 +3,10 @@
 // Everything a traversal step touches is a 16-byte-aligned float4 / int4 array
 // read with 128-bit __ldg loads:
 //   * BVH nodes stay bit-identical to the reference's 32-byte CompactBVHNode
-//     (src/GoblinBVH.h:8-30) and are fetched as two float4: one node is one
-//     32-byte sector;
+//     (src/GoblinBVH.h:8-30); the traversal reads a derived "pair node" per
+//     interior node -- both children's boxes and references in 64 bytes, so one
+//     step tests two boxes (still 32 bytes per box test) -- and the original
+//     nodes only for each level's root and for the rare multi-primitive leaf;
 //   * instances and triangles are stored in BVH leaf order, so a leaf's
 //     primitives are contiguous and no order[] indirection is paid per test;
 //   * a triangle test record is p0, e1 = p1 - p0, e2 = p2 - p0 (the values the
@@ -40,10 +42,13 @@ struct DeviceScene {
     const float4* topNodes;     // 2 per node
     uint32_t nTopNodes;
     uint32_t nInstances;
+    const float4* topPairs;     // 4 per interior node of the top-level BVH (pair nodes, traverse.cuh)
+    uint32_t topRootRef;        // pair index 0, or a leaf reference when the root is a leaf
     const float4* instToObject; // 3 per instance slot (BVH leaf order)
     const int4* instInfo;       // per slot: kind, node base (in modelNodes), tri base (in triRec), __float_as_int(radius)
-    const uint32_t* instNodeCount; // per slot: node count of the model BVH (0 = empty mesh)
+    const int4* instInfo2;      // per slot: root reference, pair base (in modelPairs), node count (0 = empty mesh), 0
     const float4* modelNodes;   // 2 per node, all models concatenated
+    const float4* modelPairs;   // 4 per interior node, all models concatenated
     const float4* triRec;       // 3 per triangle slot (BVH leaf order, all models concatenated)
     // ---- shading data
     const float4* instToWorld;  // 3 per instance slot

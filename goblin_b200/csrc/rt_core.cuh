@@ -1,4 +1,4 @@
-// Ray / box, ray / primitive tests and the two-level traversal.
+// Ray / box and ray / primitive tests (the two-level traversal is traverse.cuh).
 //
 // The arithmetic follows the reference expression by expression so that hit
 // ids and distances agree with the CPU build (x86-64 SSE2, no FMA): this file
@@ -129,143 +129,6 @@ __device__ __forceinline__ bool diskTest(float radius, float3 o, float3 d, float
     if (squareR > radius * radius) return false;
     *tOut = t;
     return true;
-}
-
-// Per-thread traversal stack in shared memory, one column per thread so that a
-// warp's pushes / pops never bank-conflict: entry k of thread t lives at
-// stack[k * blockDim.x + t].
-struct SmemStack {
-    unsigned int* base; // &stack[threadIdx.x]
-    unsigned int stride;
-    __device__ __forceinline__ void put(int k, unsigned int v) { base[k * stride] = v; }
-    __device__ __forceinline__ unsigned int get(int k) const { return base[k * stride]; }
-};
-
-// BVH::intersect / BVH::occluded over one model's triangles, in object space.
-// Returns true as soon as something is hit when ANY; otherwise shrinks *maxt
-// and records the last accepted triangle (t <= maxt accepts ties, so the later
-// primitive in traversal order wins, as in the reference).
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool walkModel(const DeviceScene& sc, unsigned int nodeBase, unsigned int triBase,
-    float3 o, float3 d, float mint, float* maxt, HitRec* hit, int instSlot, SmemStack st, int sp0,
-    TraceStats* stats) {
-    float3 invDir = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int negX = d.x < 0.0f, negY = d.y < 0.0f, negZ = d.z < 0.0f;
-    unsigned int node = 0;
-    int sp = sp0;
-    bool found = false;
-    const float4* nodes = sc.modelNodes + 2 * (size_t)nodeBase;
-    while (true) {
-        float4 n0 = __ldg(nodes + 2 * node);
-        float4 n1 = __ldg(nodes + 2 * node + 1);
-        if (STATS) stats->nodes++;
-        bool descend = false;
-        if (slabTest(n0, n1, o, invDir, negX, negY, negZ, mint, *maxt)) {
-            unsigned int meta = __float_as_uint(n1.w);
-            unsigned int nprims = meta & 0xffu;
-            unsigned int offset = __float_as_uint(n1.z);
-            if (nprims > 0) {
-                for (unsigned int i = 0; i < nprims; ++i) {
-                    const float4* tr = sc.triRec + 3 * (size_t)(triBase + offset + i);
-                    float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-                    if (STATS) stats->prims++;
-                    float t, b1, b2;
-                    if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), o, d,
-                            mint, *maxt, &t, &b1, &b2)) {
-                        if (ANY) return true;
-                        *maxt = t;
-                        hit->t = t; hit->b1 = b1; hit->b2 = b2;
-                        hit->inst = instSlot;
-                        hit->prim = (int)(offset + i);
-                        found = true;
-                    }
-                }
-            } else {
-                unsigned int axis = (meta >> 8) & 0xffu;
-                int neg = axis == 0 ? negX : (axis == 1 ? negY : negZ);
-                if (neg) { st.put(sp++, node + 1); node = offset; }
-                else { st.put(sp++, offset); node = node + 1; }
-                descend = true;
-            }
-        }
-        if (!descend) {
-            if (sp == sp0) break;
-            node = st.get(--sp);
-        }
-    }
-    return found;
-}
-
-// Scene::intersect (ANY = false) / Scene::occluded (ANY = true).
-template <bool ANY, bool STATS>
-__device__ __forceinline__ bool traceScene(const DeviceScene& sc, float3 o, float3 d, float mint, float maxt,
-    HitRec* hit, SmemStack st, TraceStats* stats) {
-    hit->inst = -1;
-    hit->prim = 0;
-    hit->t = maxt;
-    hit->b1 = hit->b2 = 0.0f;
-    if (sc.nTopNodes == 0) return false;
-    float3 invDir = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    int negX = d.x < 0.0f, negY = d.y < 0.0f, negZ = d.z < 0.0f;
-    unsigned int node = 0;
-    int sp = 0;
-    bool found = false;
-    while (true) {
-        float4 n0 = __ldg(sc.topNodes + 2 * node);
-        float4 n1 = __ldg(sc.topNodes + 2 * node + 1);
-        if (STATS) stats->nodes++;
-        bool descend = false;
-        if (slabTest(n0, n1, o, invDir, negX, negY, negZ, mint, maxt)) {
-            unsigned int meta = __float_as_uint(n1.w);
-            unsigned int nprims = meta & 0xffu;
-            unsigned int offset = __float_as_uint(n1.z);
-            if (nprims > 0) {
-                for (unsigned int i = 0; i < nprims; ++i) {
-                    unsigned int slot = offset + i;
-                    const float4* m = sc.instToObject + 3 * (size_t)slot;
-                    float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
-                    int4 info = __ldg(sc.instInfo + slot);
-                    if (STATS) stats->insts++;
-                    // Transform::invertRay: direction is not renormalised, t is shared
-                    float3 oo = xfPoint(r0, r1, r2, o);
-                    float3 od = xfVector(r0, r1, r2, d);
-                    if (info.x == GB_GEOM_MESH) {
-                        if (__ldg(sc.instNodeCount + slot) == 0) continue;
-                        if (walkModel<ANY, STATS>(sc, (unsigned int)info.y, (unsigned int)info.z, oo, od, mint,
-                                &maxt, hit, (int)slot, st, sp, stats)) {
-                            if (ANY) return true;
-                            found = true;
-                        }
-                    } else {
-                        float t;
-                        float radius = __int_as_float(info.w);
-                        if (STATS) stats->prims++;
-                        bool h = info.x == GB_GEOM_SPHERE ? sphereTest(radius, oo, od, mint, maxt, &t)
-                                                          : diskTest(radius, oo, od, mint, maxt, &t);
-                        if (h) {
-                            if (ANY) return true;
-                            maxt = t;
-                            hit->t = t; hit->b1 = 0.0f; hit->b2 = 0.0f;
-                            hit->inst = (int)slot;
-                            hit->prim = 0;
-                            found = true;
-                        }
-                    }
-                }
-            } else {
-                unsigned int axis = (meta >> 8) & 0xffu;
-                int neg = axis == 0 ? negX : (axis == 1 ? negY : negZ);
-                if (neg) { st.put(sp++, node + 1); node = offset; }
-                else { st.put(sp++, offset); node = node + 1; }
-                descend = true;
-            }
-        }
-        if (!descend) {
-            if (sp == 0) break;
-            node = st.get(--sp);
-        }
-    }
-    return found;
 }
 
 } // namespace gb

@@ -1,0 +1,302 @@
+// Persistent two-level BVH traversal with per-lane ray refill.
+//
+// What is walked is the reference's tree in the reference's order
+// (src/GoblinBVH.cpp:189-280: near child first by dirIsNeg[axis], far child
+// pushed, leaves tested as they are reached, t <= maxt accepted), so hit ids,
+// distances and the visited-node counts equal the CPU build's.  How it is
+// walked is B200-shaped:
+//   * "pair nodes": one 64-byte record per interior node holds BOTH child boxes
+//     and child references, fetched as 4 x 128-bit read-only loads; a step
+//     tests two boxes, which halves the dependent-load chain of the 32-byte
+//     one-box-per-visit layout (same 32 algorithmic bytes per box test);
+//   * the far child's entry distance rides on the stack (8-byte entries in a
+//     shared-memory column per thread) and is re-checked against the shrunk
+//     maxt when popped -- exactly the box test the reference evaluates at pop
+//     time, since nothing else in that test depends on maxt;
+//   * branch-free slab tests that keep the reference's comparison structure
+//     (and therefore its NaN behaviour for zero direction components);
+//   * one step per loop iteration (an interior step, then a leaf step for the
+//     lanes that hold one), so a lane never waits longer than one step;
+//   * lanes that finish a ray pull the next one from a global cursor with a
+//     warp-aggregated atomic instead of idling until the whole warp is done.
+#pragma once
+#include "rt_core.cuh"
+
+namespace gb {
+
+constexpr unsigned int REF_LEAF = 0x80000000u;  // child is a leaf
+constexpr unsigned int REF_MULTI = 0x40000000u; // leaf with nprims != 1: index = original node
+constexpr unsigned int REF_INDEX = 0x3FFFFFFFu;
+constexpr unsigned int REF_NONE = 0xFFFFFFFFu;  // nothing left at this level
+constexpr int kRefillBelow = 20;                // pull new rays when fewer lanes than this are busy
+
+// Per-thread columns in shared memory: entry k of thread t lives at [k * blockDim.x + t],
+// so a warp's pushes / pops are contiguous.
+struct TravStack {
+    uint2* base;
+    unsigned int stride;
+    __device__ __forceinline__ void put(int k, unsigned int ref, float tmin) {
+        base[k * stride] = make_uint2(ref, __float_as_uint(tmin));
+    }
+    __device__ __forceinline__ uint2 get(int k) const { return base[k * stride]; }
+};
+
+// The reference's ordered slab test on sign-selected bounds, without early returns.
+__device__ __forceinline__ bool slabNoBranch(float nearX, float nearY, float nearZ, float farX, float farY, float farZ,
+    float3 o, float3 inv, float mint, float maxt, float* tEntry) {
+    float tMin = (nearX - o.x) * inv.x;
+    float tMax = (farX - o.x) * inv.x;
+    float tYMin = (nearY - o.y) * inv.y;
+    float tYMax = (farY - o.y) * inv.y;
+    bool miss = (tYMax < tMin) | (tYMin > tMax);
+    tMin = tYMin > tMin ? tYMin : tMin;
+    tMax = tYMax < tMax ? tYMax : tMax;
+    float tZMin = (nearZ - o.z) * inv.z;
+    float tZMax = (farZ - o.z) * inv.z;
+    miss |= (tZMax < tMin) | (tZMin > tMax);
+    tMin = tZMin > tMin ? tZMin : tMin;
+    tMax = tZMax < tMax ? tZMax : tMax;
+    *tEntry = tMin;
+    return !miss & (tMin < maxt) & (tMax > mint);
+}
+
+// One original 32-byte node (two float4) against a ray: used for the root of each level.
+__device__ __forceinline__ bool rootTest(float4 n0, float4 n1, float3 o, float3 inv, unsigned int neg, float mint,
+    float maxt) {
+    bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+    float t;
+    return slabNoBranch(nx ? n0.w : n0.x, ny ? n1.x : n0.y, nz ? n1.y : n0.z, nx ? n0.x : n0.w, ny ? n0.y : n1.x,
+        nz ? n0.z : n1.y, o, inv, mint, maxt, &t);
+}
+
+__device__ __forceinline__ unsigned int signBits(float3 d) {
+    return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+}
+
+// Policy interface (all members __device__):
+//   bool fetch(unsigned long long item, float3* o, float3* d, float* mint, float* maxt)
+//        -- loads / generates ray `item`; false = nothing to trace for this item
+//   void finish(bool done, unsigned long long item, bool found, const HitRec& hit)
+//        -- warp-collective: every lane calls it, `done` marks lanes whose ray just ended
+//
+// s_stack: stackEntries x blockDim.x uint2, s_ray: 6 x blockDim.x floats (the world-space ray
+// while a lane is inside an instance).
+template <bool ANY, bool STATS, typename Policy>
+__device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& pol, unsigned long long n,
+    unsigned long long* head, uint2* s_stack, float* s_ray, TraceStats& ts, unsigned int* raysDone) {
+    const unsigned int FULL = 0xffffffffu;
+    const unsigned int lane = threadIdx.x & 31;
+    TravStack st{s_stack + threadIdx.x, blockDim.x};
+    float* wr = s_ray + threadIdx.x;
+    const unsigned int ws = blockDim.x;
+
+    bool have = false, exhausted = false;
+    unsigned long long item = 0;
+    float3 o = make3(0, 0, 0), d = make3(0, 0, 0), inv = make3(0, 0, 0);
+    unsigned int neg = 0, cur = REF_NONE;
+    float mint = 0.0f, maxt = 0.0f;
+    int sp = 0, spFloor = 0, level = 0, curSlot = 0;
+    const float4* pairs = sc.topPairs;
+    unsigned int triBase = 0, nodeBase = 0, instNext = 0, instEnd = 0;
+    HitRec hit;
+    hit.inst = -1; hit.prim = 0; hit.t = 0.0f; hit.b1 = hit.b2 = 0.0f;
+    bool found = false;
+
+    for (;;) {
+        // ------------------------------------------------ refill idle lanes
+        unsigned int idle = __ballot_sync(FULL, !have);
+        if (idle && !exhausted) {
+            const unsigned int leader = __ffs(idle) - 1;
+            const unsigned int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(head, (unsigned long long)want);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + want >= n) exhausted = true;
+            if (!have) {
+                unsigned long long my = base + __popc(idle & ((1u << lane) - 1u));
+                if (my < n) {
+                    item = my;
+                    have = true;
+                    found = false;
+                    hit.inst = -1; hit.prim = 0; hit.b1 = hit.b2 = 0.0f;
+                    level = 0; sp = 0; spFloor = 0; instNext = instEnd = 0;
+                    pairs = sc.topPairs;
+                    cur = REF_NONE;
+                    if (pol.fetch(item, &o, &d, &mint, &maxt)) {
+                        ++*raysDone;
+                        wr[0] = o.x; wr[ws] = o.y; wr[2 * ws] = o.z;
+                        wr[3 * ws] = d.x; wr[4 * ws] = d.y; wr[5 * ws] = d.z;
+                        inv = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        neg = signBits(d);
+                        if (sc.nTopNodes) {
+                            float4 n0 = __ldg(sc.topNodes), n1 = __ldg(sc.topNodes + 1);
+                            if (STATS) ts.nodes++;
+                            if (rootTest(n0, n1, o, inv, neg, mint, maxt)) cur = sc.topRootRef;
+                        }
+                    }
+                    hit.t = maxt;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, have) == 0) break;
+
+        // ------------------------------------------------ traversal burst
+        // One iteration = at most one interior step and one leaf step per lane; the warp leaves
+        // the burst as soon as enough lanes are idle to be worth a refill.
+        bool fin = false;
+        for (;;) {
+            if (have && !fin) {
+                if (!(cur & REF_LEAF)) { // ---- interior step: two box tests
+                    const float4* p = pairs + 4 * (size_t)cur;
+                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
+                    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+                    float tL, tR;
+                    const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
+                        nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
+                    const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
+                        nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
+                    const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
+                    const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
+                    const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
+                    const float tF = rightFirst ? tL : tR;
+                    bool needPop = false;
+                    if (STATS) {
+                        // the reference tests the near child now and the far child when it is popped
+                        ts.nodes++;
+                        st.put(sp++, farRef, hitF ? tF : INFINITY);
+                        cur = nearRef;
+                        needPop = !hitN;
+                    } else if (hitN) {
+                        cur = nearRef;
+                        if (hitF) st.put(sp++, farRef, tF);
+                    } else if (hitF) {
+                        cur = farRef;
+                    } else {
+                        needPop = true;
+                    }
+                    if (needPop) {
+                        cur = REF_NONE;
+                        while (sp > spFloor) {
+                            uint2 e = st.get(--sp);
+                            if (STATS) ts.nodes++;
+                            if (__uint_as_float(e.y) < maxt) { cur = e.x; break; }
+                        }
+                    }
+                }
+                // ---- leaf step / level change
+                bool doInst = false, needPop = false;
+                if (cur == REF_NONE) {
+                    if (level == 1) { // this instance is exhausted: back to world space
+                        level = 0;
+                        spFloor = 0;
+                        pairs = sc.topPairs;
+                        o = make3(wr[0], wr[ws], wr[2 * ws]);
+                        d = make3(wr[3 * ws], wr[4 * ws], wr[5 * ws]);
+                        inv = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                        neg = signBits(d);
+                        doInst = true;
+                    } else {
+                        fin = true;
+                    }
+                } else if (cur & REF_LEAF) {
+                    if (level == 1) { // triangle leaf
+                        unsigned int first = cur & REF_INDEX, count = 1;
+                        if (cur & REF_MULTI) {
+                            const float4 n1 = __ldg(sc.modelNodes + 2 * ((size_t)nodeBase + first) + 1);
+                            count = __float_as_uint(n1.w) & 0xffu;
+                            first = __float_as_uint(n1.z);
+                        }
+                        for (unsigned int k = 0; k < count; ++k) {
+                            const float4* tr = sc.triRec + 3 * ((size_t)triBase + first + k);
+                            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+                            if (STATS) ts.prims++;
+                            float t, b1, b2;
+                            if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), o, d,
+                                    mint, maxt, &t, &b1, &b2)) {
+                                found = true;
+                                if (ANY) { fin = true; break; }
+                                maxt = t;
+                                hit.t = t; hit.b1 = b1; hit.b2 = b2;
+                                hit.inst = curSlot;
+                                hit.prim = (int)(first + k);
+                            }
+                        }
+                        needPop = !fin;
+                    } else { // instance leaf of the top level
+                        unsigned int first = cur & REF_INDEX, count = 1;
+                        if (cur & REF_MULTI) {
+                            const float4 n1 = __ldg(sc.topNodes + 2 * (size_t)first + 1);
+                            count = __float_as_uint(n1.w) & 0xffu;
+                            first = __float_as_uint(n1.z);
+                        }
+                        instNext = first;
+                        instEnd = first + count;
+                        doInst = true;
+                    }
+                }
+                if (doInst) {
+                    needPop = true;
+                    while (instNext < instEnd) {
+                        const unsigned int slot = instNext++;
+                        const float4* m = sc.instToObject + 3 * (size_t)slot;
+                        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+                        const int4 info = __ldg(sc.instInfo + slot);
+                        if (STATS) ts.insts++;
+                        // Transform::invertRay: the direction is not renormalised, t is shared
+                        const float3 oo = xfPoint(r0, r1, r2, o);
+                        const float3 od = xfVector(r0, r1, r2, d);
+                        if (info.x == GB_GEOM_MESH) {
+                            const int4 info2 = __ldg(sc.instInfo2 + slot);
+                            if (info2.z == 0) continue; // empty mesh: BVH::intersect returns false
+                            const float3 oinv = make3(1.0f / od.x, 1.0f / od.y, 1.0f / od.z);
+                            const unsigned int oneg = signBits(od);
+                            const float4* root = sc.modelNodes + 2 * (size_t)(unsigned int)info.y;
+                            const float4 n0 = __ldg(root), n1 = __ldg(root + 1);
+                            if (STATS) ts.nodes++;
+                            if (!rootTest(n0, n1, oo, oinv, oneg, mint, maxt)) continue;
+                            level = 1;
+                            spFloor = sp;
+                            curSlot = (int)slot;
+                            nodeBase = (unsigned int)info.y;
+                            triBase = (unsigned int)info.z;
+                            pairs = sc.modelPairs + 4 * (size_t)(unsigned int)info2.y;
+                            o = oo; d = od; inv = oinv; neg = oneg;
+                            cur = (unsigned int)info2.x;
+                            needPop = false;
+                            break;
+                        }
+                        float t;
+                        const float radius = __int_as_float(info.w);
+                        if (STATS) ts.prims++;
+                        const bool h = info.x == GB_GEOM_SPHERE ? sphereTest(radius, oo, od, mint, maxt, &t)
+                                                                : diskTest(radius, oo, od, mint, maxt, &t);
+                        if (h) {
+                            found = true;
+                            if (ANY) { fin = true; needPop = false; break; }
+                            maxt = t;
+                            hit.t = t; hit.b1 = 0.0f; hit.b2 = 0.0f;
+                            hit.inst = (int)slot;
+                            hit.prim = 0;
+                        }
+                    }
+                }
+                if (needPop) {
+                    cur = REF_NONE;
+                    while (sp > spFloor) {
+                        uint2 e = st.get(--sp);
+                        if (STATS) ts.nodes++;
+                        if (__uint_as_float(e.y) < maxt) { cur = e.x; break; }
+                    }
+                }
+            }
+            const unsigned int busy = __ballot_sync(FULL, have && !fin);
+            if (busy == 0) break;
+            if (!exhausted && __popc(busy) < kRefillBelow) break;
+        }
+        pol.finish(have && fin, item, found, hit);
+        if (fin) have = false;
+    }
+}
+
+} // namespace gb
