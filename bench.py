@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
     ap.add_argument("--wave-paths", type=int, default=0)
+    ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
@@ -212,6 +213,8 @@ def main():
     ctx.upload_scene(scene)
     if args.wave_paths:
         ctx.set_wave_paths(args.wave_paths)
+    if args.tune:
+        ctx.set_tuning([int(v) for v in args.tune.split(",")])
     spp = scene.spp_squared(args.spp or None)
     if args.scaling == "strong":
         per = (spp + world - 1) // world

@@ -33,6 +33,7 @@
 namespace gb {
 
 constexpr int kTraceBlock = 256;   // threads per traversal block
+constexpr int kTraceMinBlocks = 4; // resident blocks per SM the register allocation must allow (64 regs)
 constexpr int kShadeBlock = 128;
 constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
 constexpr size_t kMaxTraceSmem = 200 * 1024;
@@ -166,7 +167,7 @@ struct TracePolicy {
 };
 
 template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
 k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned long long n, gb_hit* __restrict__ hits,
     unsigned char* __restrict__ occluded, unsigned long long* head, unsigned long long* stats, int stackEntries) {
     GB_TRACE_SMEM(stackEntries);
@@ -249,7 +250,7 @@ struct ExtendPolicy {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
 k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
     unsigned long long* stats, int stackEntries) {
     GB_TRACE_SMEM(stackEntries);
@@ -285,7 +286,7 @@ struct ShadowPolicy {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
 k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats, int stackEntries) {
     GB_TRACE_SMEM(stackEntries);
     ShadowPolicy pol{ps};
@@ -453,7 +454,7 @@ struct AOPolicy {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
 k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr, unsigned long long* stats,
     int stackEntries) {
     GB_TRACE_SMEM(stackEntries);
@@ -604,7 +605,9 @@ struct gb_context {
     bool statsOn = false;
     uint64_t launches = 0;
     int traceGrid = 0, aoGrid = 0;
-    size_t maxWavePaths = 4u << 20;
+    size_t maxWavePaths = 32u << 20;
+    TraceTuning tune{20u, 8u, 8u, 12u};
+    int blocksPerSM = 0; // 0 = as many as fit
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;
     std::vector<cudaEvent_t> evPool;
@@ -723,6 +726,7 @@ int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
     int perSM = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraceBlock, smem));
     if (perSM < 1) return gb::failWith(GB_ERR_LIMIT, "traversal kernel does not fit on an SM");
+    if (ctx->blocksPerSM > 0) perSM = std::min(perSM, ctx->blocksPerSM);
     *grid = perSM * ctx->numSMs; // persistent: exactly one resident wave of CTAs
     return GB_OK;
 }
@@ -1015,6 +1019,7 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     GB_CUDA(cudaMalloc((void**)&ctx->film, ctx->filmPixels * sizeof(float4)));
     GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
     GB_CUDA(cudaStreamSynchronize(ctx->stream)); // host staging vectors die here
+    sc.tune = ctx->tune;
     ctx->sc = sc;
     ctx->setting = d->setting;
     ctx->haveScene = true;
@@ -1450,6 +1455,18 @@ int gb_reset_kernel_times(gb_context* ctx) {
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
     collectTimes(ctx);
     for (int k = 0; k < GB_K_COUNT; ++k) { ctx->classMs[k] = 0.0; ctx->classLaunches[k] = 0; }
+    return GB_OK;
+}
+
+int gb_set_tuning(gb_context* ctx, const int* values, int n) {
+    if (!ctx || (n && !values)) return gb::failWith(GB_ERR_INVALID, "null argument");
+    unsigned int* t[4] = {&ctx->tune.refillBelow, &ctx->tune.leafBatch, &ctx->tune.levelBatch, &ctx->tune.moveFloor};
+    for (int k = 0; k < n && k < 4; ++k) {
+        if (values[k] < 0 || values[k] > 33) return gb::failWith(GB_ERR_INVALID, "tuning value out of range");
+        *t[k] = (unsigned int)values[k];
+    }
+    if (n > 4) ctx->blocksPerSM = values[4];
+    ctx->sc.tune = ctx->tune;
     return GB_OK;
 }
 

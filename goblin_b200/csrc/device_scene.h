@@ -37,7 +37,12 @@ struct DeviceMaterial { // 32 bytes
     float4 ktEta;       // kt rgb, eta
 };
 
+struct TraceTuning { // warp scheduling of the traversal kernels (traverse.cuh)
+    unsigned int refillBelow, leafBatch, levelBatch, moveFloor;
+};
+
 struct DeviceScene {
+    TraceTuning tune;
     // ---- traversal data
     const float4* topNodes;     // 2 per node
     uint32_t nTopNodes;

@@ -15,8 +15,9 @@
 //     time, since nothing else in that test depends on maxt;
 //   * branch-free slab tests that keep the reference's comparison structure
 //     (and therefore its NaN behaviour for zero direction components);
-//   * one step per loop iteration (an interior step, then a leaf step for the
-//     lanes that hold one), so a lane never waits longer than one step;
+//   * staged scheduling: every loop iteration runs a converged interior stage
+//     and pop stage; triangle tests and level changes are batched across the
+//     warp (lanes park until enough of them need the same stage);
 //   * lanes that finish a ray pull the next one from a global cursor with a
 //     warp-aggregated atomic instead of idling until the whole warp is done.
 #pragma once
@@ -28,7 +29,10 @@ constexpr unsigned int REF_LEAF = 0x80000000u;  // child is a leaf
 constexpr unsigned int REF_MULTI = 0x40000000u; // leaf with nprims != 1: index = original node
 constexpr unsigned int REF_INDEX = 0x3FFFFFFFu;
 constexpr unsigned int REF_NONE = 0xFFFFFFFFu;  // nothing left at this level
-constexpr int kRefillBelow = 20;                // pull new rays when fewer lanes than this are busy
+constexpr unsigned int REF_POP = 0xFFFFFFFEu;   // take the next entry off the stack
+// scheduling knobs live in DeviceScene::tune (gb_set_tuning): refillBelow = pull new rays when
+// fewer lanes than this are busy; leafBatch / levelBatch = run the triangle / level stage once
+// this many lanes wait for it; moveFloor = ... or when fewer lanes than this can still move
 
 // Per-thread columns in shared memory: entry k of thread t lives at [k * blockDim.x + t],
 // so a warp's pushes / pops are contiguous.
@@ -141,51 +145,49 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
         if (__ballot_sync(FULL, have) == 0) break;
 
         // ------------------------------------------------ traversal burst
-        // One iteration = at most one interior step and one leaf step per lane; the warp leaves
-        // the burst as soon as enough lanes are idle to be worth a refill.
+        // Every iteration runs a converged interior stage (two box tests for each lane holding an
+        // interior node) and a converged pop stage.  Leaf work (triangle tests) and level changes
+        // (instance entry / exit, ray end) are longer and rarer, so the lanes that need them park
+        // until enough have gathered -- or nobody else can move -- and then run them together.
+        // Parking does not reorder anything within a ray: exactness is untouched.
         bool fin = false;
         for (;;) {
-            if (have && !fin) {
-                if (!(cur & REF_LEAF)) { // ---- interior step: two box tests
-                    const float4* p = pairs + 4 * (size_t)cur;
-                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-                    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
-                    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
-                    float tL, tR;
-                    const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
-                        nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
-                    const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
-                        nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
-                    const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
-                    const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
-                    const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
-                    const float tF = rightFirst ? tL : tR;
-                    bool needPop = false;
-                    if (STATS) {
-                        // the reference tests the near child now and the far child when it is popped
-                        ts.nodes++;
-                        st.put(sp++, farRef, hitF ? tF : INFINITY);
-                        cur = nearRef;
-                        needPop = !hitN;
-                    } else if (hitN) {
-                        cur = nearRef;
-                        if (hitF) st.put(sp++, farRef, tF);
-                    } else if (hitF) {
-                        cur = farRef;
-                    } else {
-                        needPop = true;
-                    }
-                    if (needPop) {
-                        cur = REF_NONE;
-                        while (sp > spFloor) {
-                            uint2 e = st.get(--sp);
-                            if (STATS) ts.nodes++;
-                            if (__uint_as_float(e.y) < maxt) { cur = e.x; break; }
-                        }
+            const bool live = have && !fin;
+            const bool isLeaf = live && (cur & REF_LEAF) && cur < REF_POP;
+            const bool wantTri = isLeaf && level == 1;
+            const bool wantLvl = live && (cur == REF_NONE || (isLeaf && level == 0));
+            const unsigned int nTri = __popc(__ballot_sync(FULL, wantTri));
+            const unsigned int nLvl = __popc(__ballot_sync(FULL, wantLvl));
+            const unsigned int nMove = __popc(__ballot_sync(FULL, live && !wantTri && !wantLvl));
+            const bool runTri = nTri >= sc.tune.leafBatch || (nTri && nMove < sc.tune.moveFloor);
+            const bool runLvl = nLvl >= sc.tune.levelBatch || (nLvl && nMove < sc.tune.moveFloor);
+
+            if (runTri && wantTri) { // ---- triangle leaf
+                unsigned int first = cur & REF_INDEX, count = 1;
+                if (cur & REF_MULTI) {
+                    const float4 n1 = __ldg(sc.modelNodes + 2 * ((size_t)nodeBase + first) + 1);
+                    count = __float_as_uint(n1.w) & 0xffu;
+                    first = __float_as_uint(n1.z);
+                }
+                cur = REF_POP;
+                for (unsigned int k = 0; k < count; ++k) {
+                    const float4* tr = sc.triRec + 3 * ((size_t)triBase + first + k);
+                    const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+                    if (STATS) ts.prims++;
+                    float t, b1, b2;
+                    if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), o, d, mint,
+                            maxt, &t, &b1, &b2)) {
+                        found = true;
+                        if (ANY) { fin = true; break; }
+                        maxt = t;
+                        hit.t = t; hit.b1 = b1; hit.b2 = b2;
+                        hit.inst = curSlot;
+                        hit.prim = (int)(first + k);
                     }
                 }
-                // ---- leaf step / level change
-                bool doInst = false, needPop = false;
+            }
+            if (runLvl && wantLvl) { // ---- level change: instance exit, instance entry, ray end
+                bool doInst = false;
                 if (cur == REF_NONE) {
                     if (level == 1) { // this instance is exhausted: back to world space
                         level = 0;
@@ -199,44 +201,19 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     } else {
                         fin = true;
                     }
-                } else if (cur & REF_LEAF) {
-                    if (level == 1) { // triangle leaf
-                        unsigned int first = cur & REF_INDEX, count = 1;
-                        if (cur & REF_MULTI) {
-                            const float4 n1 = __ldg(sc.modelNodes + 2 * ((size_t)nodeBase + first) + 1);
-                            count = __float_as_uint(n1.w) & 0xffu;
-                            first = __float_as_uint(n1.z);
-                        }
-                        for (unsigned int k = 0; k < count; ++k) {
-                            const float4* tr = sc.triRec + 3 * ((size_t)triBase + first + k);
-                            const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
-                            if (STATS) ts.prims++;
-                            float t, b1, b2;
-                            if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), o, d,
-                                    mint, maxt, &t, &b1, &b2)) {
-                                found = true;
-                                if (ANY) { fin = true; break; }
-                                maxt = t;
-                                hit.t = t; hit.b1 = b1; hit.b2 = b2;
-                                hit.inst = curSlot;
-                                hit.prim = (int)(first + k);
-                            }
-                        }
-                        needPop = !fin;
-                    } else { // instance leaf of the top level
-                        unsigned int first = cur & REF_INDEX, count = 1;
-                        if (cur & REF_MULTI) {
-                            const float4 n1 = __ldg(sc.topNodes + 2 * (size_t)first + 1);
-                            count = __float_as_uint(n1.w) & 0xffu;
-                            first = __float_as_uint(n1.z);
-                        }
-                        instNext = first;
-                        instEnd = first + count;
-                        doInst = true;
+                } else { // instance leaf of the top level
+                    unsigned int first = cur & REF_INDEX, count = 1;
+                    if (cur & REF_MULTI) {
+                        const float4 n1 = __ldg(sc.topNodes + 2 * (size_t)first + 1);
+                        count = __float_as_uint(n1.w) & 0xffu;
+                        first = __float_as_uint(n1.z);
                     }
+                    instNext = first;
+                    instEnd = first + count;
+                    doInst = true;
                 }
                 if (doInst) {
-                    needPop = true;
+                    cur = REF_POP;
                     while (instNext < instEnd) {
                         const unsigned int slot = instNext++;
                         const float4* m = sc.instToObject + 3 * (size_t)slot;
@@ -263,7 +240,6 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             pairs = sc.modelPairs + 4 * (size_t)(unsigned int)info2.y;
                             o = oo; d = od; inv = oinv; neg = oneg;
                             cur = (unsigned int)info2.x;
-                            needPop = false;
                             break;
                         }
                         float t;
@@ -273,7 +249,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                                                                 : diskTest(radius, oo, od, mint, maxt, &t);
                         if (h) {
                             found = true;
-                            if (ANY) { fin = true; needPop = false; break; }
+                            if (ANY) { fin = true; break; }
                             maxt = t;
                             hit.t = t; hit.b1 = 0.0f; hit.b2 = 0.0f;
                             hit.inst = (int)slot;
@@ -281,18 +257,46 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                         }
                     }
                 }
-                if (needPop) {
-                    cur = REF_NONE;
-                    while (sp > spFloor) {
-                        uint2 e = st.get(--sp);
+            }
+            if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
+                const float4* p = pairs + 4 * (size_t)cur;
+                const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
+                const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+                float tL, tR;
+                const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
+                    nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
+                const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
+                    nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
+                const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
+                const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
+                const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
+                const float tF = rightFirst ? tL : tR;
+                if (STATS) {
+                    // the reference tests the near child now and the far child when it is popped
+                    ts.nodes++;
+                    st.put(sp++, farRef, hitF ? tF : INFINITY);
+                    cur = hitN ? nearRef : REF_POP;
+                } else {
+                    if (hitN & hitF) st.put(sp++, farRef, tF);
+                    cur = hitN ? nearRef : (hitF ? farRef : REF_POP);
+                }
+            }
+            // ---- pop stage: one entry per trip for every lane that needs one
+            while (__any_sync(FULL, have && !fin && cur == REF_POP)) {
+                if (have && !fin && cur == REF_POP) {
+                    if (sp > spFloor) {
+                        const uint2 e = st.get(--sp);
                         if (STATS) ts.nodes++;
-                        if (__uint_as_float(e.y) < maxt) { cur = e.x; break; }
+                        if (__uint_as_float(e.y) < maxt) cur = e.x;
+                    } else {
+                        cur = REF_NONE;
                     }
                 }
             }
             const unsigned int busy = __ballot_sync(FULL, have && !fin);
             if (busy == 0) break;
-            if (!exhausted && __popc(busy) < kRefillBelow) break;
+            if (!exhausted && __popc(busy) < sc.tune.refillBelow) break;
         }
         pol.finish(have && fin, item, found, hit);
         if (fin) have = false;

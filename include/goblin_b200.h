@@ -296,6 +296,10 @@ int gb_reset_kernel_times(gb_context* ctx);
 /* Upper bound on the camera samples in flight per wave of the wavefront
  * integrator (path-state memory ~ 200 B per path). */
 int gb_set_wave_paths(gb_context* ctx, size_t max_paths);
+/* Warp-scheduling knobs of the traversal kernels, for experiments: values[0..3] =
+ * refill-below, leaf batch, level batch, move floor (lanes, 0..33); values[4] =
+ * resident CTAs per SM (0 = as many as fit).  Results never depend on them. */
+int gb_set_tuning(gb_context* ctx, const int* values, int n);
 
 const char* gb_last_error(void);
 const char* gb_version(void);
