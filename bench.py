@@ -33,9 +33,17 @@ SCENES = {
     "grid_small": ("grid", [512], "grid_pt.json"),
     "field": ("field", [], "field_pt.json"),
 }
-WORKLOAD_NOTE = ("S1: examples/bunny.json layout, render_method path_tracing, 512x384, 100 spp, max_ray_depth 8, "
-                 "gaussian filter r=2; stand-in bunny mesh (icosphere 6x + hashed noise, 81,920 tris): "
-                 "examples/models/bunny.obj is absent from the reference mount")
+NOTES = {
+    "bunny": ("S1: examples/bunny.json layout, render_method path_tracing, 512x384, 100 spp, max_ray_depth 8, "
+              "gaussian filter r=2; stand-in bunny mesh (icosphere 6x + hashed noise, 81,920 tris): "
+              "examples/models/bunny.obj is absent from the reference mount"),
+    "bunny_ao": "S2: S1 geometry, render_method ao, ao_sample_num 25, 1920x1080, 16 spp",
+    "spheres": "S3: 768 spheres + 256 disks (Lambert / mirror / glass), 4 disk area lights, 2048x2048, 64 spp, depth 8",
+    "grid": "S4: 9,999,392-triangle displaced grid mesh with vn, sphere area light + point light, 1920x1080, 64 spp, depth 8",
+    "grid_small": "S4 at 524,288 triangles",
+    "field": "S5: 27x27 instances of the 81,920-triangle stand-in bunny, 3840x2160, 64 spp, depth 8",
+}
+METRIC = {"bunny": "path-traced Msamples/s (bunny.json)", "bunny_ao": "AO Msamples/s (bunny.json, ao integrator)"}
 SCENE_GEN = os.path.join(ROOT, "goblin_b200", "bin", "scene_gen")
 REF_TOOL = os.path.join(ROOT, "oracle", "_ref", "ref_tool")
 
@@ -136,11 +144,11 @@ def bench_reference(args, rank):
             vals.append(last)
     value = sum(v["value"] for v in vals) / len(vals)
     secs = sum(v["seconds"] for v in vals) / len(vals)
-    line = {"impl": "reference", "metric": "path-traced Msamples/s (bunny.json)", "value": value,
+    line = {"impl": "reference", "metric": METRIC.get(args.scene, "path-traced Msamples/s (%s)" % args.scene), "value": value,
             "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NOTE, "scene": args.scene, "step": last["sample"]},
+            "config": {"workload": NOTES[args.scene], "scene": args.scene, "step": last["sample"]},
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
             "mrays_per_s": sum(v["mrays_per_s"] for v in vals) / len(vals),
@@ -353,19 +361,19 @@ def main():
                     "nodes_per_ray": (st["nodes_visited"]) / max(st["rays_closest"] + st["rays_any"], 1),
                     "kernel_share_of_step": kms[0] / total_ms,
                     "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]}}
-        line = {"metric": "path-traced Msamples/s (bunny.json)", "value": value, "unit": "Msamples/s",
+        line = {"metric": METRIC.get(args.scene, "path-traced Msamples/s (%s)" % args.scene), "value": value, "unit": "Msamples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD_NOTE, "scene": args.scene, "spp": spp, "spp_range_rank0": [spp_begin, spp_end],
+                "config": {"workload": NOTES[args.scene], "scene": args.scene, "spp": spp, "spp_range_rank0": [spp_begin, spp_end],
                            "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
                            "parallelism": f"spp x{world} (scene replica per GPU, NCCL film all-reduce)" if world > 1 else "1 GPU",
-                           "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~0.8 GB per wave) exceeds L2",
+                           "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~176 B per camera sample, GBs per wave) exceeds L2",
                            "scene_load_s": load_s},
                 "mrays_per_s": mrays, "rays_per_sample": rays_all / (samples_per_step_all * args.steps),
                 "gpu_launches": int(timed["kernel_launches"]),
                 "clocks": clocks.summary(),
-                "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(scene_bytes(scene.desc)),
+                "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(ctx.upload_bytes()),
                         "d2h_bytes_per_step": int(film_floats * 4), "steps": e2e_steps,
                         "what": "gb_upload_scene (host arrays) + gb_film_clear + gb_render + gb_film_download per step"},
                 "roofline": roofline}

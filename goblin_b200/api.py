@@ -110,7 +110,7 @@ EXPORTS = [
     "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image",
     "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
     "gb_last_kernel_ms", "gb_last_error", "gb_version", "gb_enable_kernel_timing", "gb_get_kernel_times",
-    "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning",
+    "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning", "gb_upload_bytes",
 ]
 
 KERNEL_CLASSES = ["raygen", "extend", "shade", "shadow", "ao", "film", "trace", "other"]
@@ -167,6 +167,7 @@ def lib():
         l.gb_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(KernelTimes)]
         l.gb_reset_kernel_times.argtypes = [C.c_void_p]
         l.gb_set_wave_paths.argtypes = [C.c_void_p, C.c_size_t]
+        l.gb_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         l.gb_set_tuning.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
         _lib = l
     return _lib
@@ -399,6 +400,11 @@ class Context:
 
     def set_wave_paths(self, max_paths):
         check(lib().gb_set_wave_paths(self._h, max_paths))
+
+    def upload_bytes(self):
+        n = C.c_size_t()
+        check(lib().gb_upload_bytes(self._h, C.byref(n)))
+        return n.value
 
     def set_tuning(self, values):
         arr = (C.c_int * len(values))(*values)

@@ -15,10 +15,13 @@
 //     shared memory and flushes it with one vector atomic per pixel.
 // No tensor cores, no TMA: traversal is a dependent gather of 32-byte nodes,
 // not a dense contraction (north_star).
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -590,7 +593,10 @@ struct gb_context {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool haveScene = false;
     DeviceScene sc{};
-    std::vector<void*> sceneAllocs;
+    char* arenaDev = nullptr;   // every scene array lives in one device allocation ...
+    char* arenaHost = nullptr;  // ... filled through one (pinned) staging buffer
+    size_t arenaCap = 0, uploadBytes = 0;
+    bool arenaPinned = false;
     gb_render_setting setting{};
     int stackEntries = 0; // per-thread traversal stack entries this scene needs
     float4* film = nullptr;
@@ -629,23 +635,15 @@ constexpr int kMaxDepthCtr = 66;
         }                                                                                      \
     } while (0)
 
-template <typename T>
-int uploadArray(gb_context* ctx, const T* host, size_t n, const T** dev) {
-    *dev = nullptr;
-    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-    void* p = nullptr;
-    GB_CUDA(cudaMalloc(&p, bytes));
-    ctx->sceneAllocs.push_back(p);
-    if (n) GB_CUDA(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    *dev = static_cast<const T*>(p);
-    return GB_OK;
-}
-
 void freeScene(gb_context* ctx) {
-    for (void* p : ctx->sceneAllocs) cudaFree(p);
-    ctx->sceneAllocs.clear();
+    if (ctx->arenaDev) cudaFree(ctx->arenaDev);
+    if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
+    ctx->arenaDev = nullptr;
+    ctx->arenaHost = nullptr;
+    ctx->arenaCap = 0;
     if (ctx->film) cudaFree(ctx->film);
     ctx->film = nullptr;
+    ctx->filmPixels = 0;
     ctx->haveScene = false;
 }
 
@@ -791,139 +789,244 @@ int gb_destroy(gb_context* ctx) {
     return GB_OK;
 }
 
-int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
+} // extern "C"
+
+// gb_upload_scene: validate the flattened scene, derive the device layouts (leaf-ordered instance
+// tables, 48-byte triangle records, 64-byte pair nodes) directly inside one pinned staging arena
+// and move it to the GPU with a single copy.  Device and staging arenas are kept across calls and
+// only grow, host loops run on all cores: re-uploading a scene costs the fill plus one H2D copy.
+namespace {
+
+template <typename F>
+void hostParallelFor(size_t n, size_t grain, F body) { // body(begin, end)
+    unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (n <= grain || nt == 1) { body(0, n); return; }
+    nt = (unsigned)std::min<size_t>(nt, (n + grain - 1) / grain);
+    std::vector<std::thread> pool;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        size_t b = t * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        pool.emplace_back([=]() { body(b, e); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// One linear pass over a pre-order node array: structure check, depth, pair index of every
+// interior node.  Children always follow their parent in the reference's layout
+// (left = i + 1, right = secondChildOffset > i + 1).
+bool scanTree(const gb_bvh_node* nodes, uint32_t count, uint64_t primLimit, int* depthOut,
+    std::vector<uint32_t>& pairIndex, uint32_t* nPairsOut) {
+    *depthOut = 0;
+    *nPairsOut = 0;
+    pairIndex.assign(count, 0u);
+    if (count == 0) return true;
+    std::vector<uint8_t> depth(count, 0);
+    std::vector<uint8_t> reached(count, 0);
+    reached[0] = 1;
+    uint32_t nPairs = 0;
+    int deepest = 0;
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!reached[i]) return false;
+        const gb_bvh_node& nd = nodes[i];
+        deepest = std::max(deepest, (int)depth[i]);
+        if (nd.nprims == 0) {
+            if (nd.axis > 2 || i + 1 >= count || nd.offset <= i + 1 || nd.offset >= count) return false;
+            if (depth[i] >= 2 * kMaxStack) return false;
+            if (reached[i + 1] || reached[nd.offset]) return false;
+            reached[i + 1] = reached[nd.offset] = 1;
+            depth[i + 1] = depth[nd.offset] = (uint8_t)(depth[i] + 1);
+            pairIndex[i] = nPairs++;
+        } else {
+            if ((uint64_t)nd.offset + nd.nprims > primLimit) return false;
+            if (nd.nprims == 1 ? nd.offset > REF_INDEX : i > REF_INDEX) return false;
+        }
+    }
+    if (nPairs > REF_INDEX) return false;
+    *depthOut = deepest;
+    *nPairsOut = nPairs;
+    return true;
+}
+
+inline uint32_t refOf(const gb_bvh_node* nodes, const uint32_t* pairIndex, uint32_t node) {
+    const gb_bvh_node& nd = nodes[node];
+    if (nd.nprims == 0) return pairIndex[node];
+    if (nd.nprims == 1) return REF_LEAF | nd.offset;
+    return REF_LEAF | REF_MULTI | node;
+}
+
+void fillPairs(const gb_bvh_node* nodes, uint32_t count, const uint32_t* pairIndex, float4* out) {
+    hostParallelFor(count, 1u << 16, [=](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const gb_bvh_node& nd = nodes[i];
+            if (nd.nprims != 0) continue;
+            const gb_bvh_node& l = nodes[i + 1];
+            const gb_bvh_node& r = nodes[nd.offset];
+            float4* q = out + 4 * (size_t)pairIndex[i];
+            q[0] = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], l.bmax[0]);
+            q[1] = make_float4(l.bmax[1], l.bmax[2], r.bmin[0], r.bmin[1]);
+            q[2] = make_float4(r.bmin[2], r.bmax[0], r.bmax[1], r.bmax[2]);
+            uint32_t w[4] = {refOf(nodes, pairIndex, (uint32_t)i + 1), refOf(nodes, pairIndex, nd.offset), nd.axis, 0u};
+            std::memcpy(&q[3], w, 16);
+        }
+    });
+}
+
+struct Arena { // offsets into the staging / device arena, 256-byte aligned
+    size_t size = 0;
+    size_t take(size_t bytes) {
+        size_t off = size;
+        size = (size + std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        return off;
+    }
+};
+
+} // namespace
+
+extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     if (!ctx || !d) return gb::failWith(GB_ERR_INVALID, "null argument");
     GB_CUDA(cudaSetDevice(ctx->device));
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
-    freeScene(ctx);
-    DeviceScene sc{};
-    int rc;
-    // ---- validate + measure tree depth (stack need) on the host
-    auto depthOf = [](const gb_bvh_node* nodes, uint32_t count, int* depthOut) -> bool {
-        if (count == 0) { *depthOut = 0; return true; }
-        std::vector<std::pair<uint32_t, int>> todo;
-        todo.push_back({0u, 0});
-        int deepest = 0;
-        size_t visited = 0;
-        while (!todo.empty()) {
-            auto cur = todo.back();
-            todo.pop_back();
-            if (cur.first >= count || ++visited > count) return false;
-            deepest = std::max(deepest, cur.second);
-            const gb_bvh_node& nd = nodes[cur.first];
-            if (nd.nprims == 0) {
-                if (nd.axis > 2) return false;
-                todo.push_back({nd.offset, cur.second + 1});
-                todo.push_back({cur.first + 1, cur.second + 1});
-            }
-        }
-        *depthOut = deepest;
-        return true;
-    };
+    ctx->haveScene = false;
+    const uint32_t nInst = d->n_instances;
+    const gb_film_desc& f = d->film;
+    if (f.xres <= 0 || f.yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad film resolution");
+    // ---- validate, measure tree depth (stack need), number the pair nodes
     int topDepth = 0, modelDepth = 0;
-    if (!depthOf(d->top_nodes, d->n_top_nodes, &topDepth)) return gb::failWith(GB_ERR_INVALID, "malformed top-level BVH");
+    std::vector<uint32_t> topPairIndex;
+    uint32_t nTopPairs = 0;
+    if (!scanTree(d->top_nodes, d->n_top_nodes, nInst, &topDepth, topPairIndex, &nTopPairs)) {
+        return gb::failWith(GB_ERR_INVALID, "malformed top-level BVH");
+    }
+    std::vector<std::vector<uint32_t>> modelPairIndex(d->n_models);
+    std::vector<uint32_t> modelPairBase(d->n_models, 0u), modelPairCount(d->n_models, 0u);
+    uint64_t nModelPairs = 0;
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
+        if (md.material < 0 || (uint32_t)md.material >= d->n_materials) return gb::failWith(GB_ERR_INVALID, "model material out of range");
         if (md.kind != GB_GEOM_MESH) continue;
         if ((uint64_t)md.node_offset + md.node_count > d->n_model_nodes || (uint64_t)md.tri_offset + md.tri_count > d->n_tris ||
             (uint64_t)md.vert_offset + md.vert_count > d->n_verts) {
             return gb::failWith(GB_ERR_INVALID, "model ranges exceed the scene arrays");
         }
         int dm = 0;
-        if (!depthOf(d->model_nodes + md.node_offset, md.node_count, &dm)) return gb::failWith(GB_ERR_INVALID, "malformed model BVH");
+        if (!scanTree(d->model_nodes + md.node_offset, md.node_count, md.tri_count, &dm, modelPairIndex[m], &modelPairCount[m])) {
+            return gb::failWith(GB_ERR_INVALID, "malformed model BVH");
+        }
         modelDepth = std::max(modelDepth, dm);
+        if (nModelPairs > 0xffffffffull) return gb::failWith(GB_ERR_LIMIT, "model BVHs exceed the 32-bit pair index");
+        modelPairBase[m] = (uint32_t)nModelPairs;
+        nModelPairs += modelPairCount[m];
     }
     // push-far/go-near keeps at most one entry per level; both levels share one column
     ctx->stackEntries = topDepth + modelDepth + 2;
-    // pair nodes (traverse.cuh): per interior node, both child boxes + child references
-    auto refOf = [](const gb_bvh_node* nodes, const std::vector<uint32_t>& pairIndex, uint32_t node) -> uint32_t {
-        const gb_bvh_node& nd = nodes[node];
-        if (nd.nprims == 0) return pairIndex[node];
-        if (nd.nprims == 1) return REF_LEAF | nd.offset;
-        return REF_LEAF | REF_MULTI | node;
-    };
-    auto buildPairs = [&](const gb_bvh_node* nodes, uint32_t count, std::vector<float4>& out, uint32_t* rootRef) -> bool {
-        std::vector<uint32_t> pairIndex(count, 0u);
-        uint32_t nPairs = 0;
-        for (uint32_t i = 0; i < count; ++i) {
-            if (nodes[i].nprims == 0) pairIndex[i] = nPairs++;
-            else if (nodes[i].nprims == 1 ? nodes[i].offset > REF_INDEX : i > REF_INDEX) return false;
-        }
-        if (nPairs > REF_INDEX) return false;
-        size_t base = out.size();
-        out.resize(base + 4 * (size_t)nPairs);
-        for (uint32_t i = 0; i < count; ++i) {
-            const gb_bvh_node& nd = nodes[i];
-            if (nd.nprims != 0) continue;
-            const gb_bvh_node& l = nodes[i + 1];
-            const gb_bvh_node& r = nodes[nd.offset];
-            float4* q = &out[base + 4 * (size_t)pairIndex[i]];
-            q[0] = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], l.bmax[0]);
-            q[1] = make_float4(l.bmax[1], l.bmax[2], r.bmin[0], r.bmin[1]);
-            q[2] = make_float4(r.bmin[2], r.bmax[0], r.bmax[1], r.bmax[2]);
-            uint32_t w[4] = {refOf(nodes, pairIndex, i + 1), refOf(nodes, pairIndex, nd.offset), nd.axis, 0u};
-            std::memcpy(&q[3], w, 16);
-        }
-        *rootRef = count ? refOf(nodes, pairIndex, 0) : REF_NONE;
-        return true;
-    };
-    std::vector<float4> topPairs, modelPairs;
-    uint32_t topRootRef = REF_NONE;
-    if (!buildPairs(d->top_nodes, d->n_top_nodes, topPairs, &topRootRef)) {
-        return gb::failWith(GB_ERR_LIMIT, "top-level BVH exceeds the 30-bit node reference");
-    }
-    std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE), modelPairBase(d->n_models, 0u);
-    for (uint32_t m = 0; m < d->n_models; ++m) {
-        const gb_model& md = d->models[m];
-        if (md.kind != GB_GEOM_MESH) continue;
-        modelPairBase[m] = (uint32_t)(modelPairs.size() / 4);
-        if (modelPairs.size() / 4 > 0xffffffffull ||
-            !buildPairs(d->model_nodes + md.node_offset, md.node_count, modelPairs, &modelRootRef[m])) {
-            return gb::failWith(GB_ERR_LIMIT, "model BVH exceeds the 30-bit node reference");
-        }
-    }
     if (ctx->stackEntries > 2 * kMaxStack) {
         return gb::failWith(GB_ERR_LIMIT, "BVH deeper than the traversal stack (reference: todo[64] per level)");
     }
-    // ---- top level, instances in BVH leaf order
-    const uint32_t nInst = d->n_instances;
-    std::vector<float4> instToObject(3 * (size_t)nInst), instToWorld(3 * (size_t)nInst);
-    std::vector<int4> instInfo(nInst), instShade(nInst);
-    std::vector<int4> instInfo2(nInst);
-    // triangle records are built once per distinct (node_offset, tri_offset) geometry
-    std::vector<float4> triRec(3 * (size_t)d->n_tris);
-    std::vector<int4> modelShade(d->n_models);
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        if (d->materials[m].type < 0 || d->materials[m].type > GB_MAT_TRANSPARENT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
+    }
+    std::vector<int> slotOf(nInst, -1); // original instance index -> leaf slot
+    for (uint32_t s = 0; s < nInst; ++s) {
+        uint32_t id = d->top_order[s];
+        if (id >= nInst || slotOf[id] >= 0) return gb::failWith(GB_ERR_INVALID, "top_order is not a permutation");
+        slotOf[id] = (int)s;
+        const gb_instance& in = d->instances[id];
+        if (in.model < 0 || (uint32_t)in.model >= d->n_models) return gb::failWith(GB_ERR_INVALID, "instance model out of range");
+    }
+    // ---- arena layout
+    Arena ar;
+    const size_t oTopNodes = ar.take(32 * (size_t)d->n_top_nodes);
+    const size_t oModelNodes = ar.take(32 * (size_t)d->n_model_nodes);
+    const size_t oTopPairs = ar.take(64 * (size_t)nTopPairs);
+    const size_t oModelPairs = ar.take(64 * (size_t)nModelPairs);
+    const size_t oInstToObject = ar.take(48 * (size_t)nInst);
+    const size_t oInstToWorld = ar.take(48 * (size_t)nInst);
+    const size_t oInstInfo = ar.take(16 * (size_t)nInst);
+    const size_t oInstInfo2 = ar.take(16 * (size_t)nInst);
+    const size_t oInstShade = ar.take(16 * (size_t)nInst);
+    const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
+    const size_t oModelShade = ar.take(16 * (size_t)d->n_models);
+    const size_t oTriIndex = ar.take(12 * (size_t)d->n_tris);
+    const size_t oVertNrm = ar.take(12 * (size_t)d->n_verts);
+    const size_t oVertUv = ar.take(8 * (size_t)d->n_verts);
+    const size_t oMaterials = ar.take(sizeof(DeviceMaterial) * (size_t)d->n_materials);
+    const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
+    const size_t oLightPower = ar.take(4 * (size_t)d->n_lights);
+    const size_t oLightCdf = ar.take(4 * ((size_t)d->n_lights + 1));
+    const size_t oFilter = ar.take(4 * 256);
+    if (ar.size > ctx->arenaCap) {
+        if (ctx->arenaDev) cudaFree(ctx->arenaDev);
+        if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
+        ctx->arenaDev = nullptr; ctx->arenaHost = nullptr; ctx->arenaCap = 0;
+        GB_CUDA(cudaMalloc((void**)&ctx->arenaDev, ar.size));
+        void* hp = nullptr;
+        if (cudaMallocHost(&hp, ar.size) == cudaSuccess) { ctx->arenaPinned = true; }
+        else {
+            cudaGetLastError();
+            hp = std::malloc(ar.size);
+            ctx->arenaPinned = false;
+            if (!hp) return gb::failWith(GB_ERR_INVALID, "out of host memory for the staging arena");
+        }
+        ctx->arenaHost = static_cast<char*>(hp);
+        ctx->arenaCap = ar.size;
+    }
+    char* H = ctx->arenaHost;
+    // ---- fill the staging arena
+    std::memcpy(H + oTopNodes, d->top_nodes, 32 * (size_t)d->n_top_nodes);
+    hostParallelFor(d->n_model_nodes, 1u << 18, [&](size_t b, size_t e) {
+        std::memcpy(H + oModelNodes + 32 * b, d->model_nodes + b, 32 * (e - b));
+    });
+    fillPairs(d->top_nodes, d->n_top_nodes, topPairIndex.data(), reinterpret_cast<float4*>(H + oTopPairs));
+    const uint32_t topRootRef = d->n_top_nodes ? refOf(d->top_nodes, topPairIndex.data(), 0) : REF_NONE;
+    std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE);
+    int4* modelShade = reinterpret_cast<int4*>(H + oModelShade);
+    float4* triRec = reinterpret_cast<float4*>(H + oTriRec);
+    std::string fillError;
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
         modelShade[m] = make_int4((int)md.vert_offset, (int)md.tri_offset, (md.has_normal ? 1 : 0) | (md.has_uv ? 2 : 0), 0);
         if (md.kind != GB_GEOM_MESH) continue;
-        for (uint32_t k = 0; k < md.tri_count; ++k) {
-            uint32_t face = d->model_order[md.tri_offset + k];
-            if (face >= md.tri_count) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
-            const uint32_t* vi = d->tri_index + 3 * ((size_t)md.tri_offset + face);
-            for (int c = 0; c < 3; ++c) if (vi[c] >= md.vert_count) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
-            const float* p0 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[0]);
-            const float* p1 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[1]);
-            const float* p2 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[2]);
-            // e1 = p1 - p0, e2 = p2 - p0: the reference's per-test subtractions, done once
-            float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
-            float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-            float4* r = &triRec[3 * ((size_t)md.tri_offset + k)];
-            float faceBits;
-            std::memcpy(&faceBits, &face, 4);
-            r[0] = make_float4(p0[0], p0[1], p0[2], e1[0]);
-            r[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-            r[2] = make_float4(e2[2], faceBits, 0.0f, 0.0f);
-        }
+        const gb_bvh_node* nodes = d->model_nodes + md.node_offset;
+        fillPairs(nodes, md.node_count, modelPairIndex[m].data(),
+            reinterpret_cast<float4*>(H + oModelPairs) + 4 * (size_t)modelPairBase[m]);
+        if (md.node_count) modelRootRef[m] = refOf(nodes, modelPairIndex[m].data(), 0);
+        std::vector<uint32_t>().swap(modelPairIndex[m]);
+        // triangle records in BVH leaf order: e1 = p1 - p0, e2 = p2 - p0 (the reference's per-test
+        // subtractions, done once)
+        std::atomic<int> bad(0);
+        hostParallelFor(md.tri_count, 1u << 15, [&](size_t b, size_t e) {
+            for (size_t k = b; k < e; ++k) {
+                uint32_t face = d->model_order[md.tri_offset + k];
+                if (face >= md.tri_count) { bad = 1; return; }
+                const uint32_t* vi = d->tri_index + 3 * ((size_t)md.tri_offset + face);
+                if (vi[0] >= md.vert_count || vi[1] >= md.vert_count || vi[2] >= md.vert_count) { bad = 2; return; }
+                const float* p0 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[0]);
+                const float* p1 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[1]);
+                const float* p2 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[2]);
+                float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+                float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+                float4* r = triRec + 3 * ((size_t)md.tri_offset + k);
+                float faceBits;
+                std::memcpy(&faceBits, &face, 4);
+                r[0] = make_float4(p0[0], p0[1], p0[2], e1[0]);
+                r[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+                r[2] = make_float4(e2[2], faceBits, 0.0f, 0.0f);
+            }
+        });
+        if (bad == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
+        if (bad == 2) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
     }
+    float4* instToObject = reinterpret_cast<float4*>(H + oInstToObject);
+    float4* instToWorld = reinterpret_cast<float4*>(H + oInstToWorld);
+    int4* instInfo = reinterpret_cast<int4*>(H + oInstInfo);
+    int4* instInfo2 = reinterpret_cast<int4*>(H + oInstInfo2);
+    int4* instShade = reinterpret_cast<int4*>(H + oInstShade);
     bool hasArea = false;
-    for (uint32_t s = 0; s < nInst; ++s) {
-        uint32_t id = d->top_order[s];
-        if (id >= nInst) return gb::failWith(GB_ERR_INVALID, "top_order entry out of range");
+    for (uint32_t s = 0; s < nInst; ++s) { // instances in BVH leaf order
+        const uint32_t id = d->top_order[s];
         const gb_instance& in = d->instances[id];
-        if (in.model < 0 || (uint32_t)in.model >= d->n_models) return gb::failWith(GB_ERR_INVALID, "instance model out of range");
         const gb_model& md = d->models[in.model];
-        if (md.material < 0 || (uint32_t)md.material >= d->n_materials) return gb::failWith(GB_ERR_INVALID, "model material out of range");
         for (int r = 0; r < 3; ++r) {
             instToObject[3 * (size_t)s + r] = make_float4(in.to_object[4 * r], in.to_object[4 * r + 1], in.to_object[4 * r + 2], in.to_object[4 * r + 3]);
             instToWorld[3 * (size_t)s + r] = make_float4(in.to_world[4 * r], in.to_world[4 * r + 1], in.to_world[4 * r + 2], in.to_world[4 * r + 3]);
@@ -931,27 +1034,27 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         int radiusBits;
         std::memcpy(&radiusBits, &md.radius, 4);
         instInfo[s] = make_int4(md.kind, (int)md.node_offset, (int)md.tri_offset, radiusBits);
-        instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
         instInfo2[s] = make_int4((int)modelRootRef[in.model], (int)modelPairBase[in.model],
             md.kind == GB_GEOM_MESH ? (int)md.node_count : 0, 0);
+        instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
         if (md.area_light >= 0) hasArea = true;
     }
-    std::vector<DeviceMaterial> mats(d->n_materials);
+    hostParallelFor(d->n_tris, 1u << 18, [&](size_t b, size_t e) { std::memcpy(H + oTriIndex + 12 * b, d->tri_index + 3 * b, 12 * (e - b)); });
+    hostParallelFor(d->n_verts, 1u << 18, [&](size_t b, size_t e) {
+        std::memcpy(H + oVertNrm + 12 * b, d->vert_nrm + 3 * b, 12 * (e - b));
+        std::memcpy(H + oVertUv + 8 * b, d->vert_uv + 2 * b, 8 * (e - b));
+    });
+    DeviceMaterial* mats = reinterpret_cast<DeviceMaterial*>(H + oMaterials);
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const gb_material& mm = d->materials[m];
-        if (mm.type < 0 || mm.type > GB_MAT_TRANSPARENT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
-        int t = mm.type;
         float tb;
-        std::memcpy(&tb, &t, 4);
+        std::memcpy(&tb, &mm.type, 4);
         mats[m].kdType = make_float4(mm.kd[0], mm.kd[1], mm.kd[2], tb);
         // mirror keeps k in ktEta.x (its Kt is unused)
         if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
-    // original instance index -> slot, for area lights
-    std::vector<int> slotOf(nInst, -1);
-    for (uint32_t s = 0; s < nInst; ++s) slotOf[d->top_order[s]] = (int)s;
-    std::vector<DeviceLight> lights(d->n_lights);
+    DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const gb_light& gl = d->lights[l];
         DeviceLight& dl = lights[l];
@@ -970,6 +1073,11 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             dl.toObject[r] = make_float4(gl.to_object[4 * r], gl.to_object[4 * r + 1], gl.to_object[4 * r + 2], gl.to_object[4 * r + 3]);
         }
     }
+    if (d->n_lights) {
+        std::memcpy(H + oLightPower, d->light_power, 4 * (size_t)d->n_lights);
+        std::memcpy(H + oLightCdf, d->light_cdf, 4 * ((size_t)d->n_lights + 1));
+    }
+    std::memcpy(H + oFilter, f.filter_table, 4 * 256);
     // CDF1D::mIntegral
     float integral = 0.0f;
     if (d->n_lights) {
@@ -977,28 +1085,31 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         for (uint32_t l = 0; l < d->n_lights; ++l) acc = acc + d->light_power[l] * dx;
         integral = acc;
     }
-#define UP(dst, src, n) if ((rc = uploadArray(ctx, src, n, &dst)) != GB_OK) return rc
-    const float4* tmp4;
-    UP(tmp4, reinterpret_cast<const float4*>(d->top_nodes), 2 * (size_t)d->n_top_nodes); sc.topNodes = tmp4;
-    UP(tmp4, reinterpret_cast<const float4*>(d->model_nodes), 2 * (size_t)d->n_model_nodes); sc.modelNodes = tmp4;
-    UP(sc.instToObject, instToObject.data(), instToObject.size());
-    UP(sc.instToWorld, instToWorld.data(), instToWorld.size());
-    UP(sc.instInfo, instInfo.data(), instInfo.size());
-    UP(sc.instShade, instShade.data(), instShade.size());
-    UP(sc.instInfo2, instInfo2.data(), instInfo2.size());
-    UP(sc.topPairs, topPairs.data(), topPairs.size());
-    UP(sc.modelPairs, modelPairs.data(), modelPairs.size());
-    UP(sc.triRec, triRec.data(), triRec.size());
-    UP(sc.modelShade, modelShade.data(), modelShade.size());
-    UP(sc.triIndex, d->tri_index, 3 * (size_t)d->n_tris);
-    UP(sc.vertNrm, d->vert_nrm, 3 * (size_t)d->n_verts);
-    UP(sc.vertUv, d->vert_uv, 2 * (size_t)d->n_verts);
-    UP(sc.materials, mats.data(), mats.size());
-    UP(sc.lights, lights.data(), lights.size());
-    UP(sc.lightPower, d->light_power, (size_t)d->n_lights);
-    UP(sc.lightCdf, d->light_cdf, (size_t)d->n_lights + 1);
-    UP(sc.filterTable, d->film.filter_table, (size_t)256);
-#undef UP
+    // ---- one host-to-device copy
+    GB_CUDA(cudaMemcpyAsync(ctx->arenaDev, H, ar.size, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->uploadBytes = ar.size;
+    const char* D = ctx->arenaDev;
+    DeviceScene sc{};
+    sc.tune = ctx->tune;
+    sc.topNodes = reinterpret_cast<const float4*>(D + oTopNodes);
+    sc.modelNodes = reinterpret_cast<const float4*>(D + oModelNodes);
+    sc.topPairs = reinterpret_cast<const float4*>(D + oTopPairs);
+    sc.modelPairs = reinterpret_cast<const float4*>(D + oModelPairs);
+    sc.instToObject = reinterpret_cast<const float4*>(D + oInstToObject);
+    sc.instToWorld = reinterpret_cast<const float4*>(D + oInstToWorld);
+    sc.instInfo = reinterpret_cast<const int4*>(D + oInstInfo);
+    sc.instInfo2 = reinterpret_cast<const int4*>(D + oInstInfo2);
+    sc.instShade = reinterpret_cast<const int4*>(D + oInstShade);
+    sc.triRec = reinterpret_cast<const float4*>(D + oTriRec);
+    sc.modelShade = reinterpret_cast<const int4*>(D + oModelShade);
+    sc.triIndex = reinterpret_cast<const uint32_t*>(D + oTriIndex);
+    sc.vertNrm = reinterpret_cast<const float*>(D + oVertNrm);
+    sc.vertUv = reinterpret_cast<const float*>(D + oVertUv);
+    sc.materials = reinterpret_cast<const DeviceMaterial*>(D + oMaterials);
+    sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
+    sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);
+    sc.lightCdf = reinterpret_cast<const float*>(D + oLightCdf);
+    sc.filterTable = reinterpret_cast<const float*>(D + oFilter);
     sc.nTopNodes = d->n_top_nodes;
     sc.topRootRef = topRootRef;
     sc.nInstances = nInst;
@@ -1006,8 +1117,6 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.lightIntegral = integral;
     sc.hasAreaLight = hasArea ? 1u : 0u;
     sc.camera = d->camera;
-    const gb_film_desc& f = d->film;
-    if (f.xres <= 0 || f.yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad film resolution");
     sc.xres = f.xres; sc.yres = f.yres;
     sc.xstart = f.xstart; sc.xcount = f.xcount; sc.ystart = f.ystart; sc.ycount = f.ycount;
     sc.sx0 = f.sx0; sc.sx1 = f.sx1; sc.sy0 = f.sy0; sc.sy1 = f.sy1;
@@ -1015,20 +1124,23 @@ int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.invYRes = 1.0f / (float)f.yres;
     sc.filterWidthX = f.filter_width[0];
     sc.filterWidthY = f.filter_width[1];
-    ctx->filmPixels = (size_t)f.xres * f.yres;
-    GB_CUDA(cudaMalloc((void**)&ctx->film, ctx->filmPixels * sizeof(float4)));
+    const size_t filmPixels = (size_t)f.xres * f.yres;
+    if (filmPixels != ctx->filmPixels || !ctx->film) {
+        if (ctx->film) cudaFree(ctx->film);
+        ctx->film = nullptr;
+        GB_CUDA(cudaMalloc((void**)&ctx->film, filmPixels * sizeof(float4)));
+        ctx->filmPixels = filmPixels;
+    }
     GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
-    GB_CUDA(cudaStreamSynchronize(ctx->stream)); // host staging vectors die here
-    sc.tune = ctx->tune;
+    GB_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging arena may be refilled after this
     ctx->sc = sc;
     ctx->setting = d->setting;
     ctx->haveScene = true;
-    // persistent grids for this scene's stack size
-    if (ctx->statsOn) rc = setupTraceKernel(ctx, k_trace<false, true>, &ctx->traceGrid);
-    else rc = setupTraceKernel(ctx, k_trace<false, false>, &ctx->traceGrid);
-    if (rc != GB_OK) return rc;
+    if (traceSmem(ctx) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
     return GB_OK;
 }
+
+extern "C" {
 
 static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n, gb_hit* d_hits, unsigned char* d_occ) {
     if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
@@ -1467,6 +1579,12 @@ int gb_set_tuning(gb_context* ctx, const int* values, int n) {
     }
     if (n > 4) ctx->blocksPerSM = values[4];
     ctx->sc.tune = ctx->tune;
+    return GB_OK;
+}
+
+int gb_upload_bytes(gb_context* ctx, size_t* bytes) {
+    if (!ctx || !bytes) return gb::failWith(GB_ERR_INVALID, "null argument");
+    *bytes = ctx->uploadBytes;
     return GB_OK;
 }
 

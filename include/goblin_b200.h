@@ -240,6 +240,8 @@ int gb_device_count(int* count);
 int gb_create(int device, gb_context** out);
 int gb_destroy(gb_context* ctx);
 int gb_upload_scene(gb_context* ctx, const gb_scene_desc* desc);
+/* bytes the last gb_upload_scene moved host -> device (one copy of the staging arena) */
+int gb_upload_bytes(gb_context* ctx, size_t* bytes);
 
 /* Scene::intersect / Scene::occluded (src/GoblinScene.cpp:75-87) over a ray
  * batch.  Host buffers; copies are part of the call. */
