@@ -30,6 +30,7 @@ constexpr unsigned int REF_MULTI = 0x40000000u; // leaf with nprims != 1: index 
 constexpr unsigned int REF_INDEX = 0x3FFFFFFFu;
 constexpr unsigned int REF_NONE = 0xFFFFFFFFu;  // nothing left at this level
 constexpr unsigned int REF_POP = 0xFFFFFFFEu;   // take the next entry off the stack
+constexpr int kStepsPerCheck = 2;               // interior + pop stages between two scheduling checks
 // scheduling knobs live in DeviceScene::tune (gb_set_tuning): refillBelow = pull new rays when
 // fewer lanes than this are busy; leafBatch / levelBatch = run the triangle / level stage once
 // this many lanes wait for it; moveFloor = ... or when fewer lanes than this can still move
@@ -156,11 +157,15 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
             const bool isLeaf = live && (cur & REF_LEAF) && cur < REF_POP;
             const bool wantTri = isLeaf && level == 1;
             const bool wantLvl = live && (cur == REF_NONE || (isLeaf && level == 0));
-            const unsigned int nTri = __popc(__ballot_sync(FULL, wantTri));
-            const unsigned int nLvl = __popc(__ballot_sync(FULL, wantLvl));
-            const unsigned int nMove = __popc(__ballot_sync(FULL, live && !wantTri && !wantLvl));
-            const bool runTri = nTri >= sc.tune.leafBatch || (nTri && nMove < sc.tune.moveFloor);
-            const bool runLvl = nLvl >= sc.tune.levelBatch || (nLvl && nMove < sc.tune.moveFloor);
+            const unsigned int triMask = __ballot_sync(FULL, wantTri);
+            const unsigned int lvlMask = __ballot_sync(FULL, wantLvl);
+            bool runTri = false, runLvl = false;
+            if (triMask | lvlMask) {
+                const unsigned int nTri = __popc(triMask), nLvl = __popc(lvlMask);
+                const unsigned int nMove = __popc(__ballot_sync(FULL, live)) - nTri - nLvl;
+                runTri = nTri >= sc.tune.leafBatch || (nTri && nMove < sc.tune.moveFloor);
+                runLvl = nLvl >= sc.tune.levelBatch || (nLvl && nMove < sc.tune.moveFloor);
+            }
 
             if (runTri && wantTri) { // ---- triangle leaf
                 unsigned int first = cur & REF_INDEX, count = 1;
@@ -258,39 +263,42 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     }
                 }
             }
-            if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
-                const float4* p = pairs + 4 * (size_t)cur;
-                const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-                const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
-                const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
-                float tL, tR;
-                const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
-                    nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
-                const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
-                    nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
-                const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
-                const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
-                const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
-                const float tF = rightFirst ? tL : tR;
-                if (STATS) {
-                    // the reference tests the near child now and the far child when it is popped
-                    ts.nodes++;
-                    st.put(sp++, farRef, hitF ? tF : INFINITY);
-                    cur = hitN ? nearRef : REF_POP;
-                } else {
-                    if (hitN & hitF) st.put(sp++, farRef, tF);
-                    cur = hitN ? nearRef : (hitF ? farRef : REF_POP);
-                }
-            }
-            // ---- pop stage: one entry per trip for every lane that needs one
-            while (__any_sync(FULL, have && !fin && cur == REF_POP)) {
-                if (have && !fin && cur == REF_POP) {
-                    if (sp > spFloor) {
-                        const uint2 e = st.get(--sp);
-                        if (STATS) ts.nodes++;
-                        if (__uint_as_float(e.y) < maxt) cur = e.x;
+#pragma unroll
+            for (int rep = 0; rep < kStepsPerCheck; ++rep) {
+                if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
+                    const float4* p = pairs + 4 * (size_t)cur;
+                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+                    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
+                    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+                    float tL, tR;
+                    const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
+                        nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
+                    const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
+                        nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
+                    const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
+                    const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
+                    const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
+                    const float tF = rightFirst ? tL : tR;
+                    if (STATS) {
+                        // the reference tests the near child now and the far child when it is popped
+                        ts.nodes++;
+                        st.put(sp++, farRef, hitF ? tF : INFINITY);
+                        cur = hitN ? nearRef : REF_POP;
                     } else {
-                        cur = REF_NONE;
+                        if (hitN & hitF) st.put(sp++, farRef, tF);
+                        cur = hitN ? nearRef : (hitF ? farRef : REF_POP);
+                    }
+                }
+                // ---- pop stage: one entry per trip for every lane that needs one
+                while (__any_sync(FULL, have && !fin && cur == REF_POP)) {
+                    if (have && !fin && cur == REF_POP) {
+                        if (sp > spFloor) {
+                            const uint2 e = st.get(--sp);
+                            if (STATS) ts.nodes++;
+                            if (__uint_as_float(e.y) < maxt) cur = e.x;
+                        } else {
+                            cur = REF_NONE;
+                        }
                     }
                 }
             }
