@@ -141,3 +141,38 @@ def test_synthetic_scenes(built, kind, args, json_name):
     assert close.mean() >= 0.998, f"{(~close).sum()} of {len(close)}"
     assert abs(got.sum() - want.sum()) <= 5e-3 * want.sum()
     ctx.close()
+
+
+def test_large_ray_batches_bunny(built):
+    """R* of SURVEY 8(d) on S1: 2^21 coherent camera rays + 2^21 incoherent rays (+ finite-extent
+    shadow-like segments), closest and any-hit, bit-exact against the oracle."""
+    import os
+    d = util.gen_scene("bunny")
+    ctx, scene = _ctx(os.path.join(d, "bunny_pt.json"))
+    n = 1 << 21
+    cam = np.random.default_rng(8).uniform(0, 1, (n, 4)).astype(np.float32)
+    cam[:, 0] *= scene.desc.film.xres
+    cam[:, 1] *= scene.desc.film.yres
+    rays = np.concatenate([ctx.camera_rays(cam), _random_rays(scene, n, 9)])
+    hit_frac = _check_traces(ctx, scene, rays)
+    assert hit_frac > 0.3
+    ctx.close()
+
+
+def test_bvh_depth_and_stack_limits(built):
+    """A degenerate scene whose BVH is as deep as the reference's todo[64] allows still traces
+    exactly (deep shared-memory stacks), and the counters keep matching."""
+    import os
+    d = util.gen_scene("grid", 48)
+    ctx, scene = _ctx(os.path.join(d, "grid_pt.json"))
+    rays = _random_rays(scene, 50_000, 13, finite_frac=0.5)
+    _check_traces(ctx, scene, rays)
+    ctx.enable_counters(True)
+    ctx.reset_counters()
+    ctx.trace_closest(rays[:20_000])
+    g = ctx.counters()
+    ctx.enable_counters(False)
+    _, c = op.trace_closest(scene, rays[:20_000], counters=True)
+    for k in ("nodes_visited", "prims_tested", "instances_entered"):
+        assert g[k] == c[k], k
+    ctx.close()
