@@ -947,9 +947,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oInstShade = ar.take(16 * (size_t)nInst);
     const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
     const size_t oModelShade = ar.take(16 * (size_t)d->n_models);
-    const size_t oTriIndex = ar.take(12 * (size_t)d->n_tris);
-    const size_t oVertNrm = ar.take(12 * (size_t)d->n_verts);
-    const size_t oVertUv = ar.take(8 * (size_t)d->n_verts);
+    const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
     const size_t oMaterials = ar.take(sizeof(DeviceMaterial) * (size_t)d->n_materials);
     const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
     const size_t oLightPower = ar.take(4 * (size_t)d->n_lights);
@@ -982,6 +980,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE);
     int4* modelShade = reinterpret_cast<int4*>(H + oModelShade);
     float4* triRec = reinterpret_cast<float4*>(H + oTriRec);
+    float4* triShade = reinterpret_cast<float4*>(H + oTriShade);
     std::string fillError;
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
@@ -1012,6 +1011,18 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
                 r[0] = make_float4(p0[0], p0[1], p0[2], e1[0]);
                 r[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
                 r[2] = make_float4(e2[2], faceBits, 0.0f, 0.0f);
+                // shading record: the face's vertex normals and uvs, gathered once
+                const float* n0 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[0]);
+                const float* n1 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[1]);
+                const float* n2 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[2]);
+                const float* t0 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[0]);
+                const float* t1 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[1]);
+                const float* t2 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[2]);
+                float4* q = triShade + 4 * ((size_t)md.tri_offset + k);
+                q[0] = make_float4(n0[0], n0[1], n0[2], n1[0]);
+                q[1] = make_float4(n1[1], n1[2], n2[0], n2[1]);
+                q[2] = make_float4(n2[2], t0[0], t0[1], t1[0]);
+                q[3] = make_float4(t1[1], t2[0], t2[1], 0.0f);
             }
         });
         if (bad == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
@@ -1039,11 +1050,6 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
         if (md.area_light >= 0) hasArea = true;
     }
-    hostParallelFor(d->n_tris, 1u << 18, [&](size_t b, size_t e) { std::memcpy(H + oTriIndex + 12 * b, d->tri_index + 3 * b, 12 * (e - b)); });
-    hostParallelFor(d->n_verts, 1u << 18, [&](size_t b, size_t e) {
-        std::memcpy(H + oVertNrm + 12 * b, d->vert_nrm + 3 * b, 12 * (e - b));
-        std::memcpy(H + oVertUv + 8 * b, d->vert_uv + 2 * b, 8 * (e - b));
-    });
     DeviceMaterial* mats = reinterpret_cast<DeviceMaterial*>(H + oMaterials);
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const gb_material& mm = d->materials[m];
@@ -1102,9 +1108,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.instShade = reinterpret_cast<const int4*>(D + oInstShade);
     sc.triRec = reinterpret_cast<const float4*>(D + oTriRec);
     sc.modelShade = reinterpret_cast<const int4*>(D + oModelShade);
-    sc.triIndex = reinterpret_cast<const uint32_t*>(D + oTriIndex);
-    sc.vertNrm = reinterpret_cast<const float*>(D + oVertNrm);
-    sc.vertUv = reinterpret_cast<const float*>(D + oVertUv);
+    sc.triShade = reinterpret_cast<const float4*>(D + oTriShade);
     sc.materials = reinterpret_cast<const DeviceMaterial*>(D + oMaterials);
     sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
     sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);

@@ -11,8 +11,9 @@
 //     primitives are contiguous and no order[] indirection is paid per test;
 //   * a triangle test record is p0, e1 = p1 - p0, e2 = p2 - p0 (the values the
 //     reference recomputes per test, src/GoblinTriangle.cpp:51-54) plus the
-//     face index: 10 words in 48 bytes.  Normals / uvs live in separate arrays
-//     touched only by shading.
+//     face index: 10 words in 48 bytes.  The three vertex normals and uvs of a
+//     triangle live in a parallel 64-byte record touched only by shading (one
+//     contiguous fetch per accepted hit instead of an index + vertex gather).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -59,9 +60,7 @@ struct DeviceScene {
     const float4* instToWorld;  // 3 per instance slot
     const int4* instShade;      // per slot: original instance index, model index, material, area light (-1)
     const int4* modelShade;     // per model: vert base, tri base (face order), has_normal | has_uv << 1, unused
-    const uint32_t* triIndex;   // 3 per face (model-local vertex indices), face order
-    const float* vertNrm;       // 3 per vertex
-    const float* vertUv;        // 2 per vertex
+    const float4* triShade;     // 4 per triangle slot (leaf order): the 3 vertex normals and 3 uvs, 64 bytes
     const DeviceMaterial* materials;
     const DeviceLight* lights;
     const float* lightPower;    // CDF1D::mFunction

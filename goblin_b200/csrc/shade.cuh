@@ -201,31 +201,24 @@ __device__ __forceinline__ Frag buildFragment(const DeviceScene& sc, const HitRe
         const float4* tr = sc.triRec + 3 * (size_t)(info.z + hit.prim);
         float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
         float3 e1 = make3(a.w, b.x, b.y), e2 = make3(b.z, b.w, c.x);
-        unsigned int face = __float_as_uint(c.y);
         int4 ms = __ldg(sc.modelShade + sh.y);
         float b1 = hit.b1, b2 = hit.b2;
         float b0 = 1.0f - b1 - b2;
-        const unsigned int* idx = sc.triIndex + 3 * ((size_t)ms.y + face);
-        unsigned int v0 = ms.x + __ldg(idx), v1 = ms.x + __ldg(idx + 1), v2 = ms.x + __ldg(idx + 2);
+        const float4* ts = sc.triShade + 4 * (size_t)(info.z + hit.prim);
         if (ms.z & 1) {
-            const float* n0 = sc.vertNrm + 3 * (size_t)v0;
-            const float* n1 = sc.vertNrm + 3 * (size_t)v1;
-            const float* n2 = sc.vertNrm + 3 * (size_t)v2;
-            float3 nn = b0 * make3(__ldg(n0), __ldg(n0 + 1), __ldg(n0 + 2)) +
-                b1 * make3(__ldg(n1), __ldg(n1 + 1), __ldg(n1 + 2)) +
-                b2 * make3(__ldg(n2), __ldg(n2 + 1), __ldg(n2 + 2));
+            float4 s0 = __ldg(ts), s1 = __ldg(ts + 1);
+            float n2z = __ldg(ts + 2).x;
+            float3 nn = b0 * make3(s0.x, s0.y, s0.z) + b1 * make3(s0.w, s1.x, s1.y) + b2 * make3(s1.z, s1.w, n2z);
             nObj = normalize3(nn);
         } else {
             nObj = normalize3(cross3(e1, e2));
         }
         float du1 = 1.0f, dv1 = 0.0f, du2 = 0.0f, dv2 = 1.0f;
         if (ms.z & 2) {
-            const float* t0 = sc.vertUv + 2 * (size_t)v0;
-            const float* t1 = sc.vertUv + 2 * (size_t)v1;
-            const float* t2 = sc.vertUv + 2 * (size_t)v2;
-            float u0 = __ldg(t0), vv0 = __ldg(t0 + 1);
-            du1 = __ldg(t1) - u0; dv1 = __ldg(t1 + 1) - vv0;
-            du2 = __ldg(t2) - u0; dv2 = __ldg(t2 + 1) - vv0;
+            float4 s2 = __ldg(ts + 2), s3 = __ldg(ts + 3);
+            float u0 = s2.y, vv0 = s2.z;
+            du1 = s2.w - u0; dv1 = s3.x - vv0;
+            du2 = s3.y - u0; dv2 = s3.z - vv0;
         }
         float determinant = du1 * dv2 - dv1 * du2;
         if (determinant == 0.0f) {
