@@ -306,7 +306,7 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
 // emissionOnly the kernel only resolves the pending BSDF-sampled emission
 // (the reference's trace #4 of the last iteration).
 template <int MAT>
-__global__ void __launch_bounds__(kShadeBlock)
+__global__ void __launch_bounds__(kShadeBlock, 8)
 k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounce, int emissionOnly,
     unsigned int* ctr, unsigned int* ctrNext, unsigned int* qNext) {
     const unsigned int n = ctr[C_MAT0 + MAT];
