@@ -1,0 +1,145 @@
+"""Scene-format coverage: variants of the tiny scene (thin-lens camera, every reconstruction
+filter, a crop window, spp that is not a square, no lights) through the whole stack.
+
+CPU: the host loader against the reference's own structures (needs oracle/_ref/ref_tool, built
+in this container and shipped to the GPU box) and the oracle against the reference's Li.
+GPU: the CUDA path against the oracle on the same variants."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from goblin_b200 import api, gbar
+from tests import oracle_port as op
+from tests import util
+
+
+def _variant(name):
+    sc = json.load(open(util.TINY_PT))
+    if name == "dof":
+        sc["camera"]["lens_radius"] = 0.08
+        sc["camera"]["focal_distance"] = 6.5
+    elif name == "box":
+        sc["camera"]["filter"] = {"type": "box", "width": [0.5, 0.5]}
+    elif name == "triangle":
+        sc["camera"]["filter"] = {"type": "triangle", "width": [1.5, 1.25]}
+    elif name == "mitchell":
+        sc["camera"]["filter"] = {"type": "mitchell", "width": [2.0, 2.0], "b": 0.3333333, "c": 0.3333333}
+    elif name == "wide_gaussian":
+        sc["camera"]["filter"] = {"type": "gaussian", "width": [3.0, 3.0], "falloff": 1.0}
+    elif name == "crop":
+        sc["camera"]["film"]["crop"] = [0.25, 0.75, 0.3, 0.9]
+    elif name == "spp50":
+        sc["render_setting"]["sample_per_pixel"] = 50
+    elif name == "nolights":
+        sc["lights"] = []
+    elif name == "delta_only":
+        sc["lights"] = [l for l in sc["lights"] if l["type"] != "area"]
+    else:
+        raise KeyError(name)
+    return sc
+
+
+VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only"]
+
+
+@pytest.fixture(scope="module")
+def variant_files(tmp_path_factory, built):
+    """JSON files next to the tiny scene's models (mesh paths are relative to the scene file)."""
+    out = {}
+    d = os.path.dirname(util.TINY_PT)
+    for v in VARIANTS:
+        path = os.path.join(d, f"_variant_{v}.json")
+        with open(path, "w") as f:
+            json.dump(_variant(v), f)
+        out[v] = path
+    yield out
+    for p in out.values():
+        for q in (p, p[:-5] + ".exr"):
+            if os.path.exists(q):
+                os.remove(q)
+
+
+def _ref(cmd, scene, *rest):
+    subprocess.run([util.REF_TOOL, cmd, scene, *rest], check=True, capture_output=True)
+
+
+@pytest.mark.skipif(not util.have_ref_tool(), reason="oracle/_ref/ref_tool not built")
+@pytest.mark.parametrize("v", VARIANTS)
+def test_loader_and_oracle_match_reference(variant_files, v):
+    scene = api.Scene(variant_files[v])
+    with tempfile.TemporaryDirectory() as td:
+        _ref("dump", variant_files[v], td + "/d.gbar")
+        dump = {k: a.copy() for k, a in gbar.load(td + "/d.gbar").items()}
+        f = scene.desc.film
+        assert [f.xres, f.yres, f.xstart, f.xcount, f.ystart, f.ycount, f.sx0, f.sx1, f.sy0, f.sy1] == list(dump["film"])
+        assert np.array_equal(np.array(f.filter_table[:], np.float32).view(np.uint32), dump["filter.table"].view(np.uint32))
+        assert np.array_equal(np.array(f.filter_width[:], np.float32), dump["filter.width"])
+        cam = scene.desc.camera
+        mine = np.array(list(cam.position) + list(cam.orientation) + [cam.proj00, cam.proj11, cam.lens_radius,
+                                                                      cam.focal_distance], np.float32)
+        assert np.array_equal(mine.view(np.uint32), dump["camera"].view(np.uint32))
+        nodes = np.frombuffer(np.ascontiguousarray(scene.top_nodes()).tobytes(), np.uint8).reshape(-1, 32)
+        assert np.array_equal(nodes, dump["top.nodes"])
+        assert np.array_equal(scene.top_order(), dump["top.order"])
+        if scene.desc.n_lights:
+            assert np.array_equal(scene.light_cdf().view(np.uint32), dump["light.cdf"].view(np.uint32))
+        # Li and camera rays on fresh samples
+        rng = np.random.default_rng(abs(hash(v)) % (1 << 31))
+        rows = rng.uniform(0, 1, (1500, 4 + 7 * scene.desc.setting.max_ray_depth)).astype(np.float32)
+        rows[:, 0] = rng.uniform(f.sx0, f.sx1, 1500)
+        rows[:, 1] = rng.uniform(f.sy0, f.sy1, 1500)
+        rows.tofile(td + "/rows.f32")
+        rows[:, :4].copy().tofile(td + "/cam.f32")
+        _ref("li", variant_files[v], td + "/rows.f32", td + "/l.gbar")
+        _ref("camrays", variant_files[v], td + "/cam.f32", td + "/c.gbar")
+        ref_l = {k: a.copy() for k, a in gbar.load(td + "/l.gbar").items()}
+        ref_c = gbar.load(td + "/c.gbar")["rays"].copy()
+    got_c = op.camera_rays(scene, rows[:, :4])
+    assert np.array_equal(got_c[:, [0, 1, 2, 6, 7]], ref_c[:, [0, 1, 2, 6, 7]]) or v == "dof"
+    assert np.allclose(got_c[:, :6], ref_c[:, :6], rtol=0, atol=3e-7)  # lens sampling: libm sin / cos
+    L, calls = op.li(scene, rows, calls=True)
+    same = (calls == ref_l["calls"]).all(axis=1)
+    assert same.mean() > 0.995  # a 1-ulp lens difference may flip a grazing path
+    assert np.allclose(L[same], ref_l["L"][same], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("v", VARIANTS)
+def test_gpu_matches_oracle(variant_files, v):
+    scene = api.Scene(variant_files[v])
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    f = scene.desc.film
+    rng = np.random.default_rng(5)
+    rows = rng.uniform(0, 1, (4000, 4 + 7 * scene.desc.setting.max_ray_depth)).astype(np.float32)
+    rows[:, 0] = rng.uniform(f.sx0, f.sx1, 4000)
+    rows[:, 1] = rng.uniform(f.sy0, f.sy1, 4000)
+    cam_g, cam_o = ctx.camera_rays(rows[:, :4]), op.camera_rays(scene, rows[:, :4])
+    assert np.allclose(cam_g[:, :6], cam_o[:, :6], rtol=0, atol=2e-6)  # thin lens: CUDA sincosf vs libm
+    assert np.array_equal(cam_g[:, 6:], cam_o[:, 6:])
+    hits_g, hits_o = ctx.trace_closest(cam_o), op.trace_closest(scene, cam_o)
+    assert np.array_equal(hits_g["inst"], hits_o["inst"]) and np.array_equal(hits_g["prim"], hits_o["prim"])
+    assert np.array_equal(hits_g["t"].view(np.uint32), hits_o["t"].view(np.uint32))
+    got, want = ctx.li(rows), op.li(scene, rows)
+    close = np.isclose(got, want, rtol=2e-3, atol=2e-4).all(axis=1)
+    assert close.mean() >= 0.995
+    spp = scene.spp_squared()
+    ctx.film_clear()
+    ctx.render(seed=12, spp_total=spp)
+    g = ctx.film_download()
+    c, cnt, _ = op.render(scene, seed=12, spp_total=spp)
+    assert ctx.counters()["camera_samples"] >= cnt["camera_samples"]
+    assert np.allclose(g[..., 3], c[..., 3], rtol=1e-4, atol=1e-5)
+    ok = np.isclose(g[..., :3], c[..., :3], rtol=2e-3, atol=1e-4).all(axis=2)
+    assert ok.mean() > 0.995, v
+    if v == "crop":  # nothing outside the crop window is touched
+        mask = np.zeros(g.shape[:2], bool)
+        mask[f.ystart:f.ystart + f.ycount, f.xstart:f.xstart + f.xcount] = True
+        assert (g[~mask] == 0).all() and (g[mask][:, 3] > 0).all()
+    if v == "nolights":
+        assert (g[..., :3] == 0).all() and (g[..., 3] > 0).any()
+    ctx.close()
