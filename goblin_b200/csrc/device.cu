@@ -35,8 +35,14 @@
 
 namespace gb {
 
-constexpr int kTraceBlock = 256;   // threads per traversal block
-constexpr int kTraceMinBlocks = 4; // resident blocks per SM the register allocation must allow (64 regs)
+#ifndef GB_TRACE_BLOCK
+#define GB_TRACE_BLOCK 128
+#define GB_TRACE_MIN_BLOCKS 7
+#endif
+constexpr int kTraceBlock = GB_TRACE_BLOCK;   // threads per traversal block
+// resident blocks per SM the register allocation must allow: 7 x 128 threads -> 73 registers,
+// the most the traversal loop can use without spilling
+constexpr int kTraceMinBlocks = GB_TRACE_MIN_BLOCKS;
 constexpr int kShadeBlock = 128;
 constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
 constexpr size_t kMaxTraceSmem = 200 * 1024;
@@ -612,7 +618,7 @@ struct gb_context {
     uint64_t launches = 0;
     int traceGrid = 0, aoGrid = 0;
     size_t maxWavePaths = 32u << 20;
-    TraceTuning tune{20u, 8u, 8u, 12u};
+    TraceTuning tune{20u, 6u, 4u, 10u};
     int blocksPerSM = 0; // 0 = as many as fit
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;

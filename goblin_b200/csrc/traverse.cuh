@@ -192,7 +192,11 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 }
             }
             if (runLvl && wantLvl) { // ---- level change: instance exit, instance entry, ray end
-                bool doInst = false;
+                // Everything a ray does in world space between two mesh descents happens in one
+                // visit: leave the instance, walk the remaining instances of the leaf, pop the
+                // top-level stack, handle the next instance leaf ... until the lane is inside a
+                // mesh again, stands on an interior node of the top level, or the ray ends.
+                bool iterate = true;
                 if (cur == REF_NONE) {
                     if (level == 1) { // this instance is exhausted: back to world space
                         level = 0;
@@ -202,9 +206,9 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                         d = make3(wr[3 * ws], wr[4 * ws], wr[5 * ws]);
                         inv = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                         neg = signBits(d);
-                        doInst = true;
                     } else {
                         fin = true;
+                        iterate = false;
                     }
                 } else { // instance leaf of the top level
                     unsigned int first = cur & REF_INDEX, count = 1;
@@ -215,10 +219,9 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     }
                     instNext = first;
                     instEnd = first + count;
-                    doInst = true;
                 }
-                if (doInst) {
-                    cur = REF_POP;
+                while (iterate) {
+                    bool descended = false;
                     while (instNext < instEnd) {
                         const unsigned int slot = instNext++;
                         const float4* m = sc.instToObject + 3 * (size_t)slot;
@@ -245,6 +248,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             pairs = sc.modelPairs + 4 * (size_t)(unsigned int)info2.y;
                             o = oo; d = od; inv = oinv; neg = oneg;
                             cur = (unsigned int)info2.x;
+                            descended = true;
                             break;
                         }
                         float t;
@@ -261,6 +265,24 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             hit.prim = 0;
                         }
                     }
+                    if (descended || fin) break;
+                    // the leaf is done: next entry of the top-level stack
+                    cur = REF_NONE;
+                    while (sp > 0) {
+                        const uint2 e = st.get(--sp);
+                        if (STATS) ts.nodes++;
+                        if (__uint_as_float(e.y) < maxt) { cur = e.x; break; }
+                    }
+                    if (cur == REF_NONE) { fin = true; break; }
+                    if (!(cur & REF_LEAF)) break; // an interior node of the top level: interior stage
+                    unsigned int first = cur & REF_INDEX, count = 1;
+                    if (cur & REF_MULTI) {
+                        const float4 n1 = __ldg(sc.topNodes + 2 * (size_t)first + 1);
+                        count = __float_as_uint(n1.w) & 0xffu;
+                        first = __float_as_uint(n1.z);
+                    }
+                    instNext = first;
+                    instEnd = first + count;
                 }
             }
 #pragma unroll
