@@ -178,3 +178,62 @@ def test_product_does_not_reference_the_oracle():
     so = os.path.join(util.ROOT, "goblin_b200", "libgoblin_b200.so")
     ldd = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
     assert "goblin_oracle" not in ldd
+
+
+@pytest.mark.skipif(not util.have_ref_tool(), reason="oracle/_ref/ref_tool not built")
+@pytest.mark.parametrize("kind,args,json_name", [("bunny", (), "bunny_pt.json"), ("grid", (160,), "grid_pt.json"),
+                                                  ("spheres", (), "spheres_pt.json")])
+def test_large_scenes_against_reference_dump(built, kind, args, json_name, tmp_path):
+    """The multi-threaded OBJ parse / vertex de-duplication / BVH build paths (files > 1 MB,
+    > 65,536 corners or primitives) against the reference's own structures: every BVH node,
+    the leaf order, vertices and indices bit-exact."""
+    import subprocess
+    path = os.path.join(util.gen_scene(kind, *args), json_name)
+    scene = api.Scene(path)
+    out = str(tmp_path / "d.gbar")
+    subprocess.run([util.REF_TOOL, "dump", path, out], check=True, capture_output=True)
+    dump = gbar.load(out)
+    assert np.array_equal(_node_bytes(scene.top_nodes()), dump["top.nodes"])
+    assert np.array_equal(scene.top_order(), dump["top.order"])
+    models = scene.models()
+    nodes, order = scene.model_nodes(), scene.model_order()
+    tri, pos, nrm, uv = scene.tri_index(), scene.vert_pos(), scene.vert_nrm(), scene.vert_uv()
+    checked = set()
+    for i, inst in enumerate(scene.instances()):
+        m = models[inst.model]
+        rm = int(dump["inst.model"][i])
+        assert np.array_equal(np.array(inst.to_object[:], np.float32).reshape(3, 4).view(np.uint32),
+                              dump["inst.inv"][i].reshape(4, 4)[:3].view(np.uint32))
+        if m.kind != 0 or inst.model in checked:
+            continue
+        checked.add(inst.model)
+        pre = f"model{rm}."
+        assert np.array_equal(_node_bytes(nodes[m.node_offset:m.node_offset + m.node_count]), dump[pre + "nodes"])
+        assert np.array_equal(order[m.tri_offset:m.tri_offset + m.tri_count], dump[pre + "order"])
+        assert np.array_equal(tri[m.tri_offset:m.tri_offset + m.tri_count], dump[pre + "idx"])
+        sl = slice(m.vert_offset, m.vert_offset + m.vert_count)
+        assert np.array_equal(pos[sl].view(np.uint32), dump[pre + "pos"].view(np.uint32))
+        assert np.array_equal(nrm[sl].view(np.uint32), dump[pre + "nrm"].view(np.uint32))
+        assert np.array_equal(uv[sl].view(np.uint32), dump[pre + "uv"].view(np.uint32))
+    assert checked or kind == "spheres"
+
+
+def test_obj_loader_errors(built, tmp_path):
+    """Syntax errors leave an empty mesh and the render carries on (src/GoblinPolygonMesh.cpp:60-64);
+    the first bad line in file order is the one reported, whichever thread parsed it."""
+    import json
+    d = tmp_path / "s"
+    (d / "models").mkdir(parents=True)
+    sc = json.load(open(util.TINY_PT))
+    for g in sc["geometries"]:
+        if g.get("file"):
+            src = os.path.join(os.path.dirname(util.TINY_PT), g["file"])
+            open(d / g["file"], "w").write(open(src).read())
+    big = ["v 0 0 0", "v 1 0 0", "v 0 1 0"] * 60000 + ["f 1 2 3"] * 70000
+    big[150000] = "v 1 oops 3"
+    big[190000] = "f 1 2"
+    open(d / "models" / "box.obj", "w").write("\n".join(big) + "\n")
+    json.dump(sc, open(d / "scene.json", "w"))
+    scene = api.Scene(str(d / "scene.json"))
+    box = [m for m in scene.models() if m.kind == 0 and m.tri_count == 0]
+    assert len(box) == 1 and box[0].node_count == 0
