@@ -1365,6 +1365,7 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
     if (depth > kMaxDepthCtr - 2) return gb::failWith(GB_ERR_LIMIT, "max_ray_depth above 64");
     int ao = p->ao_sample_num > 0 ? p->ao_sample_num : ctx->setting.ao_sample_num;
     if (ao < 1) ao = 1;
+    { int r = (int)ceilf(sqrtf((float)ao)); ao = r * r; } // SampleQuota::requestTwoDQuota rounds up to a square
     int sppTotal = p->spp_total;
     int root = (int)ceilf(sqrtf((float)sppTotal)); // roundToSquare, GoblinUtils.h:126-132
     if (sppTotal < 1 || root * root != sppTotal) {

@@ -243,6 +243,12 @@ struct Loader {
         out->threadNum = s.getInt("thread_num", 0);
         rs.max_ray_depth = std::max(1, s.getInt("max_ray_depth", 5));
         rs.ao_sample_num = s.getInt("ao_sample_num", 25);
+        {
+            // AORenderer::querySampleQuota -> SampleQuota::requestTwoDQuota rounds the ray count
+            // up to a perfect square (src/GoblinSampler.cpp:29-33, src/GoblinUtils.h:126-132)
+            int root = (int)std::ceil(std::sqrt((float)std::max(rs.ao_sample_num, 0)));
+            rs.ao_sample_num = root * root;
+        }
         if (method == "ao") rs.method = GB_METHOD_AO;
         else if (method == "whitted" || method == "light_tracing" || method == "bdpt" || method == "sppm") {
             // other integrators are outside the accelerated path; the caller

@@ -145,7 +145,7 @@ typedef struct gb_render_setting {
     int32_t method;        /* GB_METHOD_*                                      */
     int32_t spp;           /* sample_per_pixel as written in the scene         */
     int32_t max_ray_depth;
-    int32_t ao_sample_num;
+    int32_t ao_sample_num; /* rounded up to a perfect square, as the reference's sample quota does */
 } gb_render_setting;
 
 /* Flattened scene.  All pointers are host pointers owned by whoever filled the

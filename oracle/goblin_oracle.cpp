@@ -1013,6 +1013,7 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
     if (depth < 1) depth = 1;
     int ao = p->ao_sample_num > 0 ? p->ao_sample_num : d->setting.ao_sample_num;
     if (ao < 1) ao = 1;
+    { int r = (int)std::ceil(std::sqrt((float)ao)); ao = r * r; } // SampleQuota::requestTwoDQuota, src/GoblinSampler.cpp:29-33
     const int sppTotal = p->spp_total;
     const int root = (int)std::ceil(std::sqrt((float)sppTotal));
     if (sppTotal < 1 || root * root != sppTotal) return 1;

@@ -450,7 +450,9 @@ static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, boo
     if (!pt && !ao) { fprintf(stderr, "li: unsupported integrator\n"); return 2; }
     SampleQuota quota;
     r->querySampleQuota(v.ctx->mScene, &quota);
-    size_t row = 4 + (pt ? 7 * (size_t)pt->mMaxRayDepth : 2 * (size_t)ao->mAOSampleNum);
+    // the AO renderer shoots mAOSampleIndex.sampleNum rays: ao_sample_num rounded up to a square
+    const int aoRays = ao ? (int)ao->mAOSampleIndex.sampleNum : 0;
+    size_t row = 4 + (pt ? 7 * (size_t)pt->mMaxRayDepth : 2 * (size_t)aoRays);
     std::vector<float> sm = read_f32_file(samplesPath);
     size_t n = sm.size() / row;
     std::vector<float> out(n * 3);
@@ -483,7 +485,7 @@ static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, boo
                         s.u1D[pt->mPickLightSampleIndexes[b].offset][0] = ub[6];
                     }
                 } else {
-                    for (int a = 0; a < ao->mAOSampleNum; ++a) {
+                    for (int a = 0; a < aoRays; ++a) {
                         s.u2D[ao->mAOSampleIndex.offset][2 * a] = u[4 + 2 * a];
                         s.u2D[ao->mAOSampleIndex.offset][2 * a + 1] = u[4 + 2 * a + 1];
                     }

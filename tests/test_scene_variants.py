@@ -36,6 +36,13 @@ def _variant(name):
         sc["render_setting"]["sample_per_pixel"] = 50
     elif name == "nolights":
         sc["lights"] = []
+    elif name == "depth1":
+        sc["render_setting"]["max_ray_depth"] = 1
+    elif name == "depth2":
+        sc["render_setting"]["max_ray_depth"] = 2
+    elif name == "ao10":  # not a square: the reference shoots 16 rays (SampleQuota::requestTwoDQuota)
+        sc["render_setting"]["render_method"] = "ao"
+        sc["render_setting"]["ao_sample_num"] = 10
     elif name == "delta_only":
         sc["lights"] = [l for l in sc["lights"] if l["type"] != "area"]
     else:
@@ -43,7 +50,8 @@ def _variant(name):
     return sc
 
 
-VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only"]
+VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
+            "depth2", "ao10"]
 
 
 @pytest.fixture(scope="module")
@@ -61,6 +69,11 @@ def variant_files(tmp_path_factory, built):
         for q in (p, p[:-5] + ".exr"):
             if os.path.exists(q):
                 os.remove(q)
+
+
+def _row_floats(scene):
+    st = scene.desc.setting
+    return 4 + (2 * st.ao_sample_num if st.method == 1 else 7 * st.max_ray_depth)
 
 
 def _ref(cmd, scene, *rest):
@@ -89,7 +102,7 @@ def test_loader_and_oracle_match_reference(variant_files, v):
             assert np.array_equal(scene.light_cdf().view(np.uint32), dump["light.cdf"].view(np.uint32))
         # Li and camera rays on fresh samples
         rng = np.random.default_rng(abs(hash(v)) % (1 << 31))
-        rows = rng.uniform(0, 1, (1500, 4 + 7 * scene.desc.setting.max_ray_depth)).astype(np.float32)
+        rows = rng.uniform(0, 1, (1500, _row_floats(scene))).astype(np.float32)
         rows[:, 0] = rng.uniform(f.sx0, f.sx1, 1500)
         rows[:, 1] = rng.uniform(f.sy0, f.sy1, 1500)
         rows.tofile(td + "/rows.f32")
@@ -115,7 +128,7 @@ def test_gpu_matches_oracle(variant_files, v):
     ctx.upload_scene(scene)
     f = scene.desc.film
     rng = np.random.default_rng(5)
-    rows = rng.uniform(0, 1, (4000, 4 + 7 * scene.desc.setting.max_ray_depth)).astype(np.float32)
+    rows = rng.uniform(0, 1, (4000, _row_floats(scene))).astype(np.float32)
     rows[:, 0] = rng.uniform(f.sx0, f.sx1, 4000)
     rows[:, 1] = rng.uniform(f.sy0, f.sy1, 4000)
     cam_g, cam_o = ctx.camera_rays(rows[:, :4]), op.camera_rays(scene, rows[:, :4])
