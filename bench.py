@@ -129,14 +129,20 @@ def run_ref_tool(scene, spp, threads=0):
     return json.loads(out.split("REF_RESULT", 1)[1])
 
 
+_REF_SPP = {}
+
+
 def cpu_reference_sample(scene_json, budget_s=12.0):
     """A bounded sample of the workload on the host cores: the reference itself when its binary
-    travelled here (kind "reference"), else the oracle port (kind "port")."""
+    travelled here (kind "reference"), else the oracle port (kind "port").  The spp of the sample is
+    chosen once per scene from a 1-spp probe so that one sample costs about budget_s seconds."""
     if os.path.exists(REF_TOOL):
-        probe = run_ref_tool(scene_json, 1)
-        rate = probe["camera_samples"] / max(probe["seconds"], 1e-3)
-        root = max(1, min(10, int((budget_s * rate / probe["camera_samples"]) ** 0.5)))
-        res = run_ref_tool(scene_json, root * root) if root > 1 else probe
+        if scene_json not in _REF_SPP:
+            probe = run_ref_tool(scene_json, 1)
+            rate = probe["camera_samples"] / max(probe["seconds"], 1e-3)
+            _REF_SPP[scene_json] = max(1, min(10, int((budget_s * rate / probe["camera_samples"]) ** 0.5)))
+        root = _REF_SPP[scene_json]
+        res = run_ref_tool(scene_json, root * root)
         return {"value": res["msamples_per_s"], "unit": "Msamples/s", "cores": res["cores"], "kind": "reference",
                 "sample": f"same scene, {res['spp']} spp ({res['camera_samples']} camera samples) in "
                           f"{res['seconds']:.2f} s, g_ray thread pool on all host cores",
@@ -159,7 +165,7 @@ def bench_reference(args, rank):
     vals = []
     last = None
     for step in range(args.warmup + args.steps):
-        last = cpu_reference_sample(scene_json, budget_s=args.ref_budget)
+        last = cpu_reference_sample(scene_json, budget_s=args.ref_budget or 4.0)
         if step >= args.warmup:
             vals.append(last)
     value = sum(v["value"] for v in vals) / len(vals)
@@ -202,7 +208,8 @@ def main():
     ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
+    ap.add_argument("--ref-budget", type=float, default=0.0,
+                    help="seconds of CPU work per reference sample (default: 12 for the cpu_baseline of the CUDA arm, 4 per step of --impl reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -399,7 +406,7 @@ def main():
                 "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb = cpu_reference_sample(scene_json, budget_s=args.ref_budget)
+                cb = cpu_reference_sample(scene_json, budget_s=args.ref_budget or 12.0)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
                 line["cpu_baseline"]["mrays_per_s_reference_equivalent"] = cb["mrays_per_s"]
             except Exception as e:  # the baseline is reported, never fatal
