@@ -1,0 +1,92 @@
+"""Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, written as half-float BGR
+OpenEXR like the reference (src/GoblinImageIO.cpp:35-98), or PFM / PPM by extension."""
+import struct
+
+import numpy as np
+import pytest
+
+from goblin_b200 import api
+
+
+def _film(h=7, w=11, seed=3):
+    rng = np.random.default_rng(seed)
+    rgbw = rng.uniform(0.0, 4.0, (h, w, 4)).astype(np.float32)
+    rgbw[..., 3] = rng.uniform(0.5, 2.0, (h, w))
+    return rgbw
+
+
+def _read_exr_half(path):
+    """Minimal reader: single-part, uncompressed scanlines, HALF channels."""
+    b = open(path, "rb").read()
+    assert struct.unpack_from("<I", b, 0)[0] == 20000630
+    off = 8
+    attrs = {}
+    while b[off] != 0:
+        e = b.index(b"\0", off)
+        name = b[off:e].decode()
+        off = e + 1
+        e = b.index(b"\0", off)
+        typ = b[off:e].decode()
+        off = e + 1
+        (size,) = struct.unpack_from("<i", b, off)
+        off += 4
+        attrs[name] = (typ, b[off:off + size])
+        off += size
+    off += 1
+    assert attrs["compression"][1] == b"\0"
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    chans, c = [], attrs["channels"][1]
+    p = 0
+    while c[p] != 0:
+        e = c.index(b"\0", p)
+        chans.append(c[p:e].decode())
+        assert struct.unpack_from("<i", c, e + 1)[0] == 1  # HALF
+        p = e + 1 + 16
+    offsets = struct.unpack_from(f"<{h}Q", b, off)
+    img = {}
+    for y in range(h):
+        o = offsets[y]
+        yy, n = struct.unpack_from("<ii", b, o)
+        assert yy == y0 + y and n == 2 * w * len(chans)
+        row = np.frombuffer(b, np.float16, w * len(chans), o + 8).reshape(len(chans), w)
+        for k, name in enumerate(chans):
+            img.setdefault(name, np.zeros((h, w), np.float16))[y] = row[k]
+    return img
+
+
+def test_exr_half_bgr(built, tmp_path):
+    rgbw = _film()
+    path = str(tmp_path / "a.exr")
+    api.write_image(path, rgbw)
+    img = _read_exr_half(path)
+    assert sorted(img) == ["B", "G", "R"]
+    # Color::operator/(float) multiplies by the reciprocal (src/GoblinColor.h:76-79)
+    want = (rgbw[..., :3] * (np.float32(1.0) / rgbw[..., 3:4])).astype(np.float16)  # round-to-nearest-even
+    for k, name in enumerate("RGB"):
+        assert np.array_equal(img[name].view(np.uint16), want[..., k].view(np.uint16)), name
+
+
+def test_pfm_and_ppm(built, tmp_path):
+    rgbw = _film()
+    want = rgbw[..., :3] * (np.float32(1.0) / rgbw[..., 3:4])
+    pfm = str(tmp_path / "a.pfm")
+    api.write_image(pfm, rgbw)
+    b = open(pfm, "rb").read()
+    head = b.split(b"\n", 3)
+    assert head[0] == b"PF" and head[1].split() == [b"11", b"7"] and float(head[2]) < 0
+    data = np.frombuffer(head[3], "<f4").reshape(7, 11, 3)[::-1]  # PFM rows run bottom to top
+    assert np.array_equal(data, want)
+    ppm = str(tmp_path / "a.ppm")
+    api.write_image(ppm, rgbw)
+    b = open(ppm, "rb").read()
+    assert b.startswith(b"P6") and len(b.split(b"\n", 3)[3]) == 7 * 11 * 3
+
+
+def test_zero_weight_pixels_and_bad_path(built, tmp_path):
+    rgbw = _film()
+    rgbw[0, 0] = 0  # colour / weight with weight 0: the reference divides anyway (NaN); the file still writes
+    api.write_image(str(tmp_path / "z.pfm"), rgbw)
+    with pytest.raises(api.GoblinError) as e:
+        api.write_image(str(tmp_path / "no_such_dir" / "a.exr"), rgbw)
+    assert e.value.code == 2
