@@ -80,7 +80,9 @@ def test_pfm_and_ppm(built, tmp_path):
     ppm = str(tmp_path / "a.ppm")
     api.write_image(ppm, rgbw)
     b = open(ppm, "rb").read()
-    assert b.startswith(b"P6") and len(b.split(b"\n", 3)[3]) == 7 * 11 * 3
+    # ASCII P3, gamma 2.2, like the reference's writeImagePPM (src/GoblinImageIO.cpp:100-128)
+    tok = b.split()
+    assert tok[0] == b"P3" and tok[1:4] == [b"11", b"7", b"255"] and len(tok) == 4 + 7 * 11 * 3
 
 
 def test_zero_weight_pixels_and_bad_path(built, tmp_path):
