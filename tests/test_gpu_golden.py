@@ -173,3 +173,35 @@ def test_counters(pt):
     c = ctx.counters()
     ctx.enable_counters(False)
     assert c["rays_closest"] == 1000 and c["nodes_visited"] > 1000 and c["kernel_launches"] == 1
+
+
+@pytest.mark.skipif(not util.have_ref_tool(), reason="oracle/_ref/ref_tool not built")
+def test_bunny_converged_against_live_reference(built, tmp_path):
+    """S1 geometry (glass stand-in bunny on a Lambert floor under the spot light of
+    examples/bunny.json) at 128 x 96: 4096 spp here against 4096 spp rendered now by the
+    unmodified reference binary, both in 16 batches; relMSE < 1e-3 and the per-pixel two-sample
+    statistic must look standard normal."""
+    import os
+    import subprocess
+    from goblin_b200 import gbar
+    path = os.path.join(util.gen_scene("bunny"), "bunny_pt_small.json")
+    refs = []
+    for b in range(16):
+        out = str(tmp_path / "f.gbar")
+        subprocess.run([util.REF_TOOL, "render", path, out, "--seed", str(500 + b), "--spp", "256"], check=True,
+                       capture_output=True, cwd=str(tmp_path))
+        refs.append(util.film_image(gbar.load(out)["film"]))
+    refs = np.stack(refs)
+    gold = {"mean": refs.mean(0), "var_of_mean": refs.var(0, ddof=1) / len(refs)}
+    scene = api.Scene(path)
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    imgs, total = _batches(ctx, 16, 256, 900)
+    ctx.close()
+    assert util.rel_mse(total, gold["mean"]) < 1e-3
+    t = util.film_ttest(imgs, gold)
+    assert abs(t.mean()) < 0.1, f"biased: mean t = {t.mean():.3f}"
+    # a delta light on a smooth floor: the pixels' own variance is below the 0.2 % rounding floor of
+    # film_ttest over most of the image, so the statistic is narrower than N(0,1); it must not be wider
+    assert 0.4 < t.std() < 1.15, f"t spread {t.std():.3f}"
+    assert (np.abs(t) > 4.5).mean() < 1e-3
