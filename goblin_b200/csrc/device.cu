@@ -427,6 +427,25 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
 
 // ----------------------------------------------------------------------- AO
 // AORenderer::Li (GoblinAO.cpp:12-37): work item = (hit path, occlusion ray).
+// The hit frame of every AO path, once (instead of once per occlusion ray): position + epsilon,
+// tangent, bitangent, normal go to path-state arrays the AO integrator does not otherwise use.
+__global__ void k_ao_frames(DeviceScene sc, PathState ps, const unsigned int* ctr) {
+    const unsigned int n = ctr[C_MAT0];
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        unsigned int i = __ldg(ps.qMat[0] + q);
+        float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
+        int2 hid = ps.hitId[i];
+        HitRec h;
+        h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
+        Frag fr = buildFragment(sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
+        ShadeFrame sf = makeFrame(fr);
+        ps.shO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, 1e-3f * h.t); // Ray(fragment.getPosition(), dir, epsilon)
+        ps.thr[i] = make_float4(sf.t.x, sf.t.y, sf.t.z, 0.0f);
+        ps.pend[i] = make_float4(sf.b.x, sf.b.y, sf.b.z, 0.0f);
+        ps.shD[i] = make_float4(sf.n.x, sf.n.y, sf.n.z, 0.0f);
+    }
+}
+
 struct AOPolicy {
     const DeviceScene* sc;
     PathState ps;
@@ -438,11 +457,7 @@ struct AOPolicy {
         unsigned int a = (unsigned int)(j - (unsigned long long)q * (unsigned int)wp.aoSamples);
         unsigned int i = __ldg(ps.qMat[0] + q);
         path = i;
-        float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
-        int2 hid = ps.hitId[i];
-        HitRec h;
-        h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
-        Frag fr = buildFragment(*sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
+        float4 po = ps.shO[i], ft = ps.thr[i], fb = ps.pend[i], fn = ps.shD[i];
         int px, py, s;
         unsigned long long id = sampleIdOf(*sc, wp, i, &px, &py, &s);
         float2 u = src.aoPair(id, i, a);
@@ -451,9 +466,13 @@ struct AOPolicy {
             u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
             u.y = ((float)(a / (unsigned int)wp.aoRoot) + u.y) * sub;
         }
-        *o = fr.p;
-        *d = shadeToWorld(makeFrame(fr), uniformSampleHemisphere(u.x, u.y));
-        *mint = 1e-3f * h.t;
+        ShadeFrame sf;
+        sf.t = make3(ft.x, ft.y, ft.z);
+        sf.b = make3(fb.x, fb.y, fb.z);
+        sf.n = make3(fn.x, fn.y, fn.z);
+        *o = make3(po.x, po.y, po.z);
+        *d = shadeToWorld(sf, uniformSampleHemisphere(u.x, u.y));
+        *mint = po.w;
         *maxt = INFINITY;
         return true;
     }
@@ -1288,6 +1307,11 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     };
     if (method == GB_METHOD_AO) {
         if ((rc = extend(0, 1)) != GB_OK) return rc;
+        {
+            KernelTick tick(ctx, GB_K_OTHER);
+            k_ao_frames<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
+            ctx->launches++;
+        }
         {
             KernelTick tick(ctx, GB_K_AO);
             if (ctx->statsOn) {
