@@ -39,7 +39,7 @@ class Instance(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
-                ("k", C.c_float)]
+                ("k", C.c_float), ("exponent", C.c_float), ("fresnel", C.c_int32)]
 
 
 class Light(C.Structure):

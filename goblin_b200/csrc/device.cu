@@ -48,7 +48,7 @@ constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[6
 constexpr size_t kMaxTraceSmem = 200 * 1024;
 constexpr int kCtrStride = 16;     // counters per bounce
 // per-bounce counters; the *_HEAD cursors are 64-bit (two slots, 8-byte aligned)
-enum { C_EXTEND = 0, C_SHADOW = 1, C_MAT0 = 2, C_EXTEND_HEAD = 6, C_SHADOW_HEAD = 8, C_AO_HEAD = 10 };
+enum { C_EXTEND = 0, C_SHADOW = 1, C_MAT0 = 2 /* .. 5: one per GB_MAT_* */, C_EXTEND_HEAD = 6, C_SHADOW_HEAD = 8, C_AO_HEAD = 10 };
 // traversal statistics are kept apart for closest-hit and any-hit walks (S_ANY_BASE + ...)
 enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_ANY_BASE = 8, S_COUNT = 16 };
 
@@ -64,7 +64,7 @@ struct PathState {
     float4* shD;     // shadow ray d.xyz, maxt
     float4* shC;     // contribution rgb, __int_as_float(path)
     unsigned int* qExtend[2];
-    unsigned int* qMat[3];
+    unsigned int* qMat[GB_MAT_COUNT];
     unsigned int* aoCount;
 };
 
@@ -245,7 +245,7 @@ struct ExtendPolicy {
         }
         // warp-aggregated append to the material queues
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
+        for (int m = 0; m < GB_MAT_COUNT; ++m) {
             unsigned int mask = __ballot_sync(0xffffffffu, bin == m);
             if (mask) {
                 unsigned int leader = __ffs(mask) - 1;
@@ -361,14 +361,14 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 DeviceMaterial m;
                 m.kdType = __ldg(&mat.kdType);
                 m.ktEta = __ldg(&mat.ktEta);
-                if (MAT == GB_MAT_LAMBERT) { // specular BSDFs evaluate to black: no light sample survives
+                if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
                     LightSampleResult ls = sampleLight(sc, li, fr.p, eps, uA.y, uA.z);
                     if (!isBlack(ls.L) && ls.pdf > 0.0f) {
-                        float3 f = lambertEval(m, fr.n, wo, ls.wi);
+                        float3 f = MAT == GB_MAT_LAMBERT ? lambertEval(m, fr.n, wo, ls.wi) : blinnEval(m, fr.n, wo, ls.wi);
                         if (!isBlack(f)) {
                             float3 c = mul3(f, ls.L) * absdot3(fr.n, ls.wi);
                             if (!ls.delta) {
-                                float bsdfPdf = lambertPdf(fr.n, wo, ls.wi);
+                                float bsdfPdf = MAT == GB_MAT_LAMBERT ? lambertPdf(fr.n, wo, ls.wi) : blinnPdf(m, fr.n, wo, ls.wi);
                                 c = c * powerHeuristic(ls.pdf, bsdfPdf);
                             }
                             c = div3(c, ls.pdf);
@@ -639,6 +639,7 @@ struct gb_context {
     size_t maxWavePaths = 32u << 20;
     TraceTuning tune{20u, 6u, 4u, 10u};
     int blocksPerSM = 0; // 0 = as many as fit
+    bool hasBlinn = false; // the scene uses a Blinn material: launch its shade kernel
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;
     std::vector<cudaEvent_t> evPool;
@@ -732,7 +733,7 @@ int ensureWave(gb_context* ctx, size_t paths) {
     WA(rayO, float4); WA(rayD, float4); WA(hit, float4); WA(hitId, int2); WA(thr, float4); WA(L, float4);
     WA(pend, float4); WA(shO, float4); WA(shD, float4); WA(shC, float4);
     WA(qExtend[0], unsigned int); WA(qExtend[1], unsigned int);
-    WA(qMat[0], unsigned int); WA(qMat[1], unsigned int); WA(qMat[2], unsigned int);
+    WA(qMat[0], unsigned int); WA(qMat[1], unsigned int); WA(qMat[2], unsigned int); WA(qMat[3], unsigned int);
     WA(aoCount, unsigned int);
 #undef WA
     ctx->capacity = paths;
@@ -949,7 +950,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         return gb::failWith(GB_ERR_LIMIT, "BVH deeper than the traversal stack (reference: todo[64] per level)");
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
-        if (d->materials[m].type < 0 || d->materials[m].type > GB_MAT_TRANSPARENT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
+        if (d->materials[m].type < 0 || d->materials[m].type >= GB_MAT_COUNT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
     }
     std::vector<int> slotOf(nInst, -1); // original instance index -> leaf slot
     for (uint32_t s = 0; s < nInst; ++s) {
@@ -1076,13 +1077,19 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         if (md.area_light >= 0) hasArea = true;
     }
     DeviceMaterial* mats = reinterpret_cast<DeviceMaterial*>(H + oMaterials);
+    bool hasBlinn = false;
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const gb_material& mm = d->materials[m];
         float tb;
         std::memcpy(&tb, &mm.type, 4);
         mats[m].kdType = make_float4(mm.kd[0], mm.kd[1], mm.kd[2], tb);
         // mirror keeps k in ktEta.x (its Kt is unused)
-        if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
+        if (mm.type == GB_MAT_BLINN) {
+            float fb;
+            std::memcpy(&fb, &mm.fresnel, 4);
+            mats[m].ktEta = make_float4(mm.k, mm.exponent, fb, mm.eta);
+            hasBlinn = true;
+        } else if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
     DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
@@ -1164,6 +1171,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     GB_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging arena may be refilled after this
     ctx->sc = sc;
     ctx->setting = d->setting;
+    ctx->hasBlinn = hasBlinn;
     ctx->haveScene = true;
     if (traceSmem(ctx) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
     return GB_OK;
@@ -1343,8 +1351,9 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                 k_shade<GB_MAT_LAMBERT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
                 k_shade<GB_MAT_MIRROR><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
                 k_shade<GB_MAT_TRANSPARENT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+                if (ctx->hasBlinn) k_shade<GB_MAT_BLINN><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
             }
-            ctx->launches += 3;
+            ctx->launches += ctx->hasBlinn ? 4 : 3;
             if (!last) {
                 KernelTick tick(ctx, GB_K_SHADOW);
                 if (ctx->statsOn) {

@@ -54,6 +54,7 @@ struct Loader {
     std::vector<Geometry> geometries;
     std::map<std::string, int> geometryByName;
     std::map<std::string, Color3> colorTextures;
+    std::map<std::string, float> floatTextures;
     std::map<std::string, int> materialByName;
     std::vector<ModelDef> models;
     std::map<std::string, PrimitiveDef> primitiveByName;
@@ -81,6 +82,14 @@ struct Loader {
         m.type = GB_MAT_LAMBERT;
         m.kd[0] = kd.r; m.kd[1] = kd.g; m.kd[2] = kd.b;
         return m;
+    }
+    float getFloatTexture(const std::string& name) const {
+        auto it = floatTextures.find(name);
+        if (it == floatTextures.end()) {
+            std::cerr << "Texture " << name << " not defined!\n";
+            return 0.5f; // the "error" float texture, src/GoblinScene.cpp:116-117
+        }
+        return it->second;
     }
     Color3 getColorTexture(const std::string& name) const {
         auto it = colorTextures.find(name);
@@ -409,7 +418,15 @@ struct Loader {
             ParamSet p(t);
             std::string type = p.getString("type"), name = p.getString("name");
             std::string format = p.getString("format", "color");
-            if (format == "float") continue; // only bump / blinn exponents read these
+            if (format == "float") { // the Blinn exponent reads these (createFloatConstantTexture)
+                if (type == "checkerboard" || type == "scale" || type == "image") {
+                    err = "texture '" + name + "' of type '" + type + "' is outside the accelerated path "
+                        "(constant textures only)";
+                    return false;
+                }
+                addFirst(floatTextures, name, p.getFloat("float", 0.5f));
+                continue;
+            }
             if (format != "color") {
                 std::cerr << "unrecognize texture format" << format << std::endl;
                 continue;
@@ -436,7 +453,15 @@ struct Loader {
                 return false;
             }
             gb_material m{};
-            if (type == "blinn" || type == "subsurface" || type == "mask") {
+            if (type == "blinn") { // createBlinnMaterial, src/GoblinMaterial.cpp:834-854
+                m.type = GB_MAT_BLINN;
+                Color3 kg = getColorTexture(p.getString("Kg"));
+                m.kd[0] = kg.r; m.kd[1] = kg.g; m.kd[2] = kg.b;
+                m.exponent = getFloatTexture(p.getString("exponent"));
+                m.eta = p.getFloat("index", 1.5f);
+                m.k = p.getFloat("k", -1.0f);
+                m.fresnel = m.k > 0.0f ? GB_FRESNEL_CONDUCTOR : GB_FRESNEL_DIELECTRIC;
+            } else if (type == "subsurface" || type == "mask") {
                 err = "material '" + name + "' of type '" + type + "' is outside the accelerated path";
                 return false;
             } else if (type == "transparent") {

@@ -337,14 +337,60 @@ __device__ __forceinline__ float lambertPdf(float3 n, float3 wo, float3 wi) {
     return dot3(wo, n) * dot3(wi, n) > 0.0f ? absdot3(n, wi) * GB_INV_PI : 0.0f;
 }
 
+// BlinnMaterial (Torrance-Sparrow with a Blinn distribution), GoblinMaterial.cpp:540-644.
+// DeviceMaterial packing for blinn: kdType = (Kg, type), ktEta = (k, exponent, fresnel type, eta).
+__device__ __forceinline__ float3 blinnEval(const DeviceMaterial& m, float3 n, float3 wo, float3 wi) {
+    if (!(dot3(n, wo) * dot3(n, wi) > 0.0f)) return make3(0.0f, 0.0f, 0.0f); // Glossy | Reflection only
+    float cosi = absdot3(n, wi);
+    float coso = absdot3(n, wo);
+    if (cosi == 0.0f || coso == 0.0f) return make3(0.0f, 0.0f, 0.0f);
+    float3 wh = normalize3(wo + wi);
+    float cosh = absdot3(n, wh);
+    float e = m.ktEta.y;
+    float D = (e + 2.0f) * GB_INV_TWOPI * powf(cosh, e);
+    float woDotWh = absdot3(wo, wh);
+    float G = fminf(1.0f, fminf(2.0f * cosh * coso / woDotWh, 2.0f * cosh * cosi / woDotWh));
+    float F = __float_as_int(m.ktEta.z) == GB_FRESNEL_CONDUCTOR ? fresnelConductor(woDotWh, m.ktEta.w, m.ktEta.x)
+                                                                : fresnelDieletric(woDotWh, 1.0f, m.ktEta.w);
+    float scale = D * G * F;
+    float denom = 4.0f * cosi * coso;
+    // Color * D * G * F / (4 cosi coso): Color::operator* per factor, then operator/(float)
+    float3 c = make3(m.kdType.x * D, m.kdType.y * D, m.kdType.z * D);
+    c = c * G;
+    c = c * F;
+    (void)scale;
+    return div3(c, denom);
+}
+__device__ __forceinline__ float blinnPdf(const DeviceMaterial& m, float3 n, float3 wo, float3 wi) {
+    if (!(dot3(wo, n) * dot3(wi, n) > 0.0f)) return 0.0f;
+    float3 wh = normalize3(wo + wi);
+    float cosThetah = absdot3(wh, n);
+    float e = m.ktEta.y;
+    return (e + 1.0f) * powf(cosThetah, e) / (GB_TWO_PI * 4.0f * dot3(wo, wh));
+}
+
 __device__ __forceinline__ BsdfSample sampleBsdf(const DeviceMaterial& m, int type, const Frag& fr, float3 wo,
     float uComp, float u1, float u2) {
     BsdfSample s;
     s.f = make3(0.0f, 0.0f, 0.0f);
     s.wi = make3(0.0f, 0.0f, 0.0f);
     s.pdf = 0.0f;
-    s.specular = type != GB_MAT_LAMBERT;
-    if (type == GB_MAT_LAMBERT) {
+    s.specular = type == GB_MAT_MIRROR || type == GB_MAT_TRANSPARENT;
+    if (type == GB_MAT_BLINN) {
+        float e = m.ktEta.y;
+        float cosTheta = powf(u1, 1.0f / (e + 1.0f));
+        float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
+        float phi = u2 * GB_TWO_PI;
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        float3 whLocal = make3(sinTheta * cp, sinTheta * sp, cosTheta);
+        if (dot3(wo, fr.n) < 0.0f) whLocal = whLocal * -1.0f;
+        ShadeFrame sf = makeFrame(fr);
+        float3 wh = shadeToWorld(sf, whLocal);
+        s.wi = -wo + (2.0f * dot3(wo, wh)) * wh;
+        s.pdf = blinnPdf(m, fr.n, wo, s.wi);
+        s.f = blinnEval(m, fr.n, wo, s.wi);
+    } else if (type == GB_MAT_LAMBERT) {
         float3 wiLocal = cosineSampleHemisphere(u1, u2);
         if (dot3(wo, fr.n) < 0.0f) wiLocal = wiLocal * -1.0f;
         ShadeFrame sf = makeFrame(fr);

@@ -326,8 +326,12 @@ static void genTiny(const std::string& dir) {
               "    {\"format\": \"color\", \"name\": \"red\", \"type\": \"constant\", \"color\": [0.8, 0.25, 0.2]},\n"
               "    {\"format\": \"color\", \"name\": \"green\", \"type\": \"constant\", \"color\": [0.2, 0.7, 0.3]},\n"
               "    {\"format\": \"color\", \"name\": \"tint\", \"type\": \"constant\", \"color\": [0.9, 0.95, 1.0]},\n"
-              "    {\"format\": \"color\", \"name\": \"white\", \"type\": \"constant\", \"color\": [1, 1, 1]}\n  ],\n"
+              "    {\"format\": \"color\", \"name\": \"white\", \"type\": \"constant\", \"color\": [1, 1, 1]},\n"
+              "    {\"format\": \"float\", \"name\": \"shiny\", \"type\": \"constant\", \"float\": 40.0},\n"
+              "    {\"format\": \"float\", \"name\": \"satin\", \"type\": \"constant\", \"float\": 6.0}\n  ],\n"
               "  \"materials\": [\n"
+              "    {\"name\": \"gloss\", \"type\": \"blinn\", \"Kg\": \"red\", \"exponent\": \"shiny\", \"index\": 1.5},\n"
+              "    {\"name\": \"metal\", \"type\": \"blinn\", \"Kg\": \"tint\", \"exponent\": \"satin\", \"index\": 0.8, \"k\": 3.0},\n"
               "    {\"name\": \"grey\", \"type\": \"lambert\", \"Kd\": \"grey\"},\n"
               "    {\"name\": \"red\", \"type\": \"lambert\", \"Kd\": \"red\"},\n"
               "    {\"name\": \"green\", \"type\": \"lambert\", \"Kd\": \"green\"},\n"
@@ -335,12 +339,12 @@ static void genTiny(const std::string& dir) {
               "    {\"name\": \"glass\", \"type\": \"transparent\", \"Kr\": \"tint\", \"Kt\": \"tint\", \"index\": 1.5}\n  ],\n"
               "  \"primitives\": [\n"
               "    {\"type\": \"model\", \"name\": \"floor\", \"geometry\": \"floor\", \"material\": \"grey\"},\n"
-              "    {\"type\": \"model\", \"name\": \"ico\", \"geometry\": \"ico\", \"material\": \"red\"},\n"
+              "    {\"type\": \"model\", \"name\": \"ico\", \"geometry\": \"ico\", \"material\": \"metal\"},\n"
               "    {\"type\": \"model\", \"name\": \"blob\", \"geometry\": \"blob\", \"material\": \"glass\"},\n"
               "    {\"type\": \"model\", \"name\": \"box\", \"geometry\": \"box\", \"material\": \"green\"},\n"
               "    {\"type\": \"model\", \"name\": \"ball\", \"geometry\": \"ball\", \"material\": \"mirror\"},\n"
               "    {\"type\": \"model\", \"name\": \"gball\", \"geometry\": \"unitball\", \"material\": \"glass\"},\n"
-              "    {\"type\": \"model\", \"name\": \"plate\", \"geometry\": \"plate\", \"material\": \"red\"},\n"
+              "    {\"type\": \"model\", \"name\": \"plate\", \"geometry\": \"plate\", \"material\": \"gloss\"},\n"
               "    {\"type\": \"instance\", \"name\": \"floor\", \"model\": \"floor\", \"position\": [0.0, 0.0, 0.0], \"scale\": [6.0, 6.0, 6.0]},\n"
               "    {\"type\": \"instance\", \"name\": \"ico\", \"model\": \"ico\", \"position\": [-1.6, 0.75, 0.4], \"scale\": [0.7, 0.7, 0.7]},\n"
               "    {\"type\": \"instance\", \"name\": \"blob\", \"model\": \"blob\", \"position\": [0.3, -0.15, -1.2],\n"

@@ -66,7 +66,8 @@ typedef struct gb_hit {
 } gb_hit;
 
 enum { GB_GEOM_MESH = 0, GB_GEOM_SPHERE = 1, GB_GEOM_DISK = 2 };
-enum { GB_MAT_LAMBERT = 0, GB_MAT_MIRROR = 1, GB_MAT_TRANSPARENT = 2 };
+enum { GB_MAT_LAMBERT = 0, GB_MAT_MIRROR = 1, GB_MAT_TRANSPARENT = 2, GB_MAT_BLINN = 3, GB_MAT_COUNT = 4 };
+enum { GB_FRESNEL_DIELECTRIC = 0, GB_FRESNEL_CONDUCTOR = 1 };
 enum { GB_LIGHT_POINT = 0, GB_LIGHT_DIRECTIONAL = 1, GB_LIGHT_SPOT = 2, GB_LIGHT_AREA = 3 };
 enum { GB_METHOD_PATH_TRACING = 0, GB_METHOD_AO = 1 };
 
@@ -103,10 +104,12 @@ typedef struct gb_instance {
 
 typedef struct gb_material {
     int32_t type;          /* GB_MAT_*                                         */
-    float kd[3];           /* lambert Kd | mirror / transparent Kr             */
+    float kd[3];           /* lambert Kd | mirror / transparent Kr | blinn Kg  */
     float kt[3];           /* transparent Kt                                   */
-    float eta;             /* transparent index | mirror index                 */
-    float k;               /* mirror absorption                                */
+    float eta;             /* transparent / mirror / blinn index               */
+    float k;               /* mirror / blinn-conductor absorption              */
+    float exponent;        /* blinn: the (constant) exponent texture's value   */
+    int32_t fresnel;       /* blinn: GB_FRESNEL_*                              */
 } gb_material;
 
 typedef struct gb_light {

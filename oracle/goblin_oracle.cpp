@@ -44,6 +44,7 @@ namespace {
 const float PI = 3.14159265358979323f;          // src/GoblinUtils.h:43-46
 const float TWO_PI = 6.28318530718f;
 const float INV_PI = 0.31830988618379067154f;
+const float INV_TWOPI = 0.15915494309189533577f;
 const float INF = std::numeric_limits<float>::infinity();
 
 struct V3 {
@@ -552,19 +553,58 @@ struct Oracle {
     }
     static V3 rgb(const float* c) { return V3(c[0], c[1], c[2]); }
 
+    // BlinnMaterial::bsdf / pdf, src/GoblinMaterial.cpp:540-573, 628-644
+    static V3 blinnBsdf(const gb_material& m, const Frag& fr, V3 wo, V3 wi) {
+        V3 n = fr.n;
+        if (!(dot(n, wo) * dot(n, wi) > 0.0f)) return V3(); // getSampleType + matchType(Glossy | Reflection)
+        float cosi = absdot(n, wi);
+        float coso = absdot(n, wo);
+        if (cosi == 0.0f || coso == 0.0f) return V3();
+        V3 wh = normalize(wo + wi);
+        float cosh = absdot(n, wh);
+        float exp = m.exponent;
+        float D = (exp + 2.0f) * INV_TWOPI * (float)pow(cosh, exp);
+        float woDotWh = absdot(wo, wh);
+        float G = std::min(1.0f, std::min(2.0f * cosh * coso / woDotWh, 2.0f * cosh * cosi / woDotWh));
+        float F = m.fresnel == GB_FRESNEL_CONDUCTOR ? fresnelConductor(woDotWh, m.eta, m.k)
+                                                    : fresnelDieletric(woDotWh, 1.0f, m.eta);
+        return rgb(m.kd) * D * G * F / (4.0f * cosi * coso);
+    }
+    static float blinnPdf(const gb_material& m, const Frag& fr, V3 wo, V3 wi) {
+        if (!(dot(wo, fr.n) * dot(wi, fr.n) > 0.0f)) return 0.0f;
+        V3 wh = normalize(wo + wi);
+        float cosThetah = absdot(wh, fr.n);
+        float exp = m.exponent;
+        return (exp + 1.0f) * (float)pow(cosThetah, exp) / (TWO_PI * 4.0f * dot(wo, wh));
+    }
+
     // Material::bsdf: Lambert evaluates Kd / pi on the reflection side, the specular ones are black
     V3 bsdf(const gb_material& m, const Frag& fr, V3 wo, V3 wi) const {
+        if (m.type == GB_MAT_BLINN) return blinnBsdf(m, fr, wo, wi);
         if (m.type != GB_MAT_LAMBERT) return V3();
         if (dot(fr.n, wo) * dot(fr.n, wi) > 0.0f) return rgb(m.kd) * INV_PI;
         return V3();
     }
     float bsdfPdf(const gb_material& m, const Frag& fr, V3 wo, V3 wi) const {
+        if (m.type == GB_MAT_BLINN) return blinnPdf(m, fr, wo, wi);
         if (m.type != GB_MAT_LAMBERT) return 0.0f;
         return dot(wo, fr.n) * dot(wi, fr.n) > 0.0f ? absdot(fr.n, wi) * INV_PI : 0.0f;
     }
     V3 sampleBSDF(const gb_material& m, const Frag& fr, V3 wo, float uComp, float u1, float u2, V3* wi,
         float* pdf, bool* specular) const {
-        *specular = m.type != GB_MAT_LAMBERT;
+        *specular = m.type == GB_MAT_MIRROR || m.type == GB_MAT_TRANSPARENT;
+        if (m.type == GB_MAT_BLINN) { // BlinnMaterial::sampleBSDF, src/GoblinMaterial.cpp:596-622
+            float exp = m.exponent;
+            float cosTheta = (float)pow(u1, 1.0f / (exp + 1.0f));
+            float sinTheta = sqrtf(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+            float phi = u2 * TWO_PI;
+            V3 whLocal(sinTheta * (float)cos(phi), sinTheta * (float)sin(phi), cosTheta);
+            if (dot(wo, fr.n) < 0.0f) whLocal = whLocal * -1.0f;
+            V3 wh = shadeToWorld(fr, whLocal);
+            *wi = -wo + 2.0f * dot(wo, wh) * wh;
+            *pdf = blinnPdf(m, fr, wo, *wi);
+            return blinnBsdf(m, fr, wo, *wi);
+        }
         if (m.type == GB_MAT_LAMBERT) {
             V3 wiLocal = cosineSampleHemisphere(u1, u2);
             if (dot(wo, fr.n) < 0.0f) wiLocal = wiLocal * -1.0f;

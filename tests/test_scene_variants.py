@@ -8,6 +8,7 @@ import json
 import os
 import subprocess
 import tempfile
+import zlib
 
 import numpy as np
 import pytest
@@ -101,7 +102,7 @@ def test_loader_and_oracle_match_reference(variant_files, v):
         if scene.desc.n_lights:
             assert np.array_equal(scene.light_cdf().view(np.uint32), dump["light.cdf"].view(np.uint32))
         # Li and camera rays on fresh samples
-        rng = np.random.default_rng(abs(hash(v)) % (1 << 31))
+        rng = np.random.default_rng(zlib.crc32(v.encode()))
         rows = rng.uniform(0, 1, (1500, _row_floats(scene))).astype(np.float32)
         rows[:, 0] = rng.uniform(f.sx0, f.sx1, 1500)
         rows[:, 1] = rng.uniform(f.sy0, f.sy1, 1500)
@@ -113,7 +114,7 @@ def test_loader_and_oracle_match_reference(variant_files, v):
         ref_c = gbar.load(td + "/c.gbar")["rays"].copy()
     got_c = op.camera_rays(scene, rows[:, :4])
     assert np.array_equal(got_c[:, [0, 1, 2, 6, 7]], ref_c[:, [0, 1, 2, 6, 7]]) or v == "dof"
-    assert np.allclose(got_c[:, :6], ref_c[:, :6], rtol=0, atol=3e-7)  # lens sampling: libm sin / cos
+    assert np.allclose(got_c[:, :6], ref_c[:, :6], rtol=0, atol=1e-6)  # lens sampling: sin / cos of libm, 1 ulp at |o| ~ 6.5
     L, calls = op.li(scene, rows, calls=True)
     same = (calls == ref_l["calls"]).all(axis=1)
     assert same.mean() > 0.995  # a 1-ulp lens difference may flip a grazing path
