@@ -47,7 +47,8 @@ class Light(C.Structure):
                 ("direction", C.c_float * 3), ("cos_theta_max", C.c_float),
                 ("cos_falloff_start", C.c_float), ("geom_kind", C.c_int32), ("radius", C.c_float),
                 ("area", C.c_float), ("to_world", C.c_float * 12), ("to_object", C.c_float * 12),
-                ("instance", C.c_int32)]
+                ("instance", C.c_int32), ("model", C.c_int32), ("area_offset", C.c_uint32),
+                ("cdf_offset", C.c_uint32)]
 
 
 class Camera(C.Structure):
@@ -78,6 +79,8 @@ class SceneDesc(C.Structure):
                 ("n_verts", C.c_uint64), ("materials", C.POINTER(Material)), ("n_materials", C.c_uint32),
                 ("lights", C.POINTER(Light)), ("n_lights", C.c_uint32),
                 ("light_power", C.POINTER(C.c_float)), ("light_cdf", C.POINTER(C.c_float)),
+                ("light_tri_area", C.POINTER(C.c_float)), ("light_tri_cdf", C.POINTER(C.c_float)),
+                ("n_light_tri_area", C.c_uint32), ("n_light_tri_cdf", C.c_uint32),
                 ("world_bound", C.c_float * 6), ("camera", Camera), ("film", FilmDesc),
                 ("setting", RenderSetting)]
 

@@ -362,7 +362,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 m.kdType = __ldg(&mat.kdType);
                 m.ktEta = __ldg(&mat.ktEta);
                 if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
-                    LightSampleResult ls = sampleLight(sc, li, fr.p, eps, uA.y, uA.z);
+                    LightSampleResult ls = sampleLight(sc, li, fr.p, eps, uA.x, uA.y, uA.z);
                     if (!isBlack(ls.L) && ls.pdf > 0.0f) {
                         float3 f = MAT == GB_MAT_LAMBERT ? lambertEval(m, fr.n, wo, ls.wi) : blinnEval(m, fr.n, wo, ls.wi);
                         if (!isBlack(f)) {
@@ -978,6 +978,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
     const size_t oLightPower = ar.take(4 * (size_t)d->n_lights);
     const size_t oLightCdf = ar.take(4 * ((size_t)d->n_lights + 1));
+    const size_t oLightTris = ar.take(96 * (size_t)d->n_light_tri_area);
+    const size_t oLightTriCdf = ar.take(4 * (size_t)d->n_light_tri_cdf);
     const size_t oFilter = ar.take(4 * 256);
     if (ar.size > ctx->arenaCap) {
         if (ctx->arenaDev) cudaFree(ctx->arenaDev);
@@ -1105,6 +1107,30 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         dl.colorType = make_float4(gl.color[0], gl.color[1], gl.color[2], tb);
         dl.posRadius = make_float4(gl.position[0], gl.position[1], gl.position[2], gl.radius);
         dl.dirCos = make_float4(gl.direction[0], gl.direction[1], gl.direction[2], gl.cos_theta_max);
+        if (gl.type == GB_LIGHT_AREA && gl.geom_kind == GB_GEOM_MESH) {
+            // face-order records of the emitting mesh for GeometrySet::sample / pdf
+            if (gl.model < 0 || (uint32_t)gl.model >= d->n_models || d->models[gl.model].kind != GB_GEOM_MESH) {
+                return gb::failWith(GB_ERR_INVALID, "mesh area light without a mesh model");
+            }
+            const gb_model& md = d->models[gl.model];
+            if ((uint64_t)gl.area_offset + md.tri_count > d->n_light_tri_area ||
+                (uint64_t)gl.cdf_offset + md.tri_count + 1 > d->n_light_tri_cdf) {
+                return gb::failWith(GB_ERR_INVALID, "mesh area light ranges exceed light_tri_area / light_tri_cdf");
+            }
+            float4* lt = reinterpret_cast<float4*>(H + oLightTris) + 6 * (size_t)gl.area_offset;
+            for (uint32_t face = 0; face < md.tri_count; ++face) {
+                const uint32_t* vi = d->tri_index + 3 * ((size_t)md.tri_offset + face);
+                for (int c = 0; c < 3; ++c) {
+                    if (vi[c] >= md.vert_count) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
+                    const float* pp = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[c]);
+                    const float* pn = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[c]);
+                    lt[6 * (size_t)face + c] = make_float4(pp[0], pp[1], pp[2], c == 0 ? d->light_tri_area[gl.area_offset + face] : 0.0f);
+                    lt[6 * (size_t)face + 3 + c] = make_float4(pn[0], pn[1], pn[2], 0.0f);
+                }
+            }
+            uint32_t w[4] = {gl.area_offset, md.tri_count, md.has_normal ? 1u : 0u, gl.cdf_offset};
+            std::memcpy(&dl.dirCos, w, 16);
+        }
         dl.misc = make_float4(gl.cos_falloff_start, gl.area, kb, sb);
         for (int r = 0; r < 3; ++r) {
             dl.toWorld[r] = make_float4(gl.to_world[4 * r], gl.to_world[4 * r + 1], gl.to_world[4 * r + 2], gl.to_world[4 * r + 3]);
@@ -1116,6 +1142,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         std::memcpy(H + oLightCdf, d->light_cdf, 4 * ((size_t)d->n_lights + 1));
     }
     std::memcpy(H + oFilter, f.filter_table, 4 * 256);
+    if (d->n_light_tri_cdf) std::memcpy(H + oLightTriCdf, d->light_tri_cdf, 4 * (size_t)d->n_light_tri_cdf);
     // CDF1D::mIntegral
     float integral = 0.0f;
     if (d->n_lights) {
@@ -1145,6 +1172,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
     sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);
     sc.lightCdf = reinterpret_cast<const float*>(D + oLightCdf);
+    sc.lightTris = reinterpret_cast<const float4*>(D + oLightTris);
+    sc.lightTriCdf = reinterpret_cast<const float*>(D + oLightTriCdf);
     sc.filterTable = reinterpret_cast<const float*>(D + oFilter);
     sc.nTopNodes = d->n_top_nodes;
     sc.topRootRef = topRootRef;

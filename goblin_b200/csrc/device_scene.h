@@ -27,7 +27,7 @@ constexpr int kMaxLights = 1 << 20;
 struct DeviceLight { // 128 bytes
     float4 colorType;   // rgb, __int_as_float(type)
     float4 posRadius;   // position xyz, radius
-    float4 dirCos;      // direction xyz, cosThetaMax
+    float4 dirCos;      // direction xyz, cosThetaMax | mesh emitter: uint bits (first light triangle, count, has normals, first CDF entry)
     float4 misc;        // cosFalloffStart, area, __int_as_float(geomKind), __int_as_float(instanceSlot)
     float4 toWorld[3];  // light's own Transform (area lights)
     float4 toObject[3];
@@ -65,6 +65,8 @@ struct DeviceScene {
     const DeviceLight* lights;
     const float* lightPower;    // CDF1D::mFunction
     const float* lightCdf;      // CDF1D::mCDF (nLights + 1)
+    const float4* lightTris;    // mesh emitters, 6 per face in FACE order: p0|area, p1, p2, n0, n1, n2
+    const float* lightTriCdf;   // mesh emitters: area CDFs
     uint32_t nLights;
     float lightIntegral;        // CDF1D::mIntegral
     uint32_t hasAreaLight;

@@ -21,6 +21,7 @@ struct gb_scene {
     std::vector<gb_material> materials;
     std::vector<gb_light> lights;
     std::vector<float> lightPower, lightCdf;
+    std::vector<float> lightTriArea, lightTriCdf; // mesh emitters: per-face areas and their CDF
     float worldBound[6] = {0, 0, 0, 0, 0, 0};
     gb_camera camera{};
     gb_film_desc film{};

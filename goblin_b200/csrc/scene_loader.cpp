@@ -518,7 +518,7 @@ struct Loader {
         return true;
     }
 
-    struct PendingLight { gb_light l; Transform xf; int geometry = -1; };
+    struct PendingLight { gb_light l; Transform xf; int geometry = -1; int model = -1; };
     std::vector<PendingLight> lights;
 
     static Vec3 lightAxis(const Vec3& dir, Transform* xf) { // Light::setOrientation + onVector(UnitZ)
@@ -540,6 +540,7 @@ struct Loader {
             gb_light& l = pl.l;
             std::memset(&l, 0, sizeof l);
             l.instance = -1;
+            l.model = -1;
             if (type == "ibl") {
                 err = "light '" + name + "': image based lights are outside the accelerated path";
                 return false;
@@ -566,11 +567,6 @@ struct Loader {
                 l.color[0] = c.x; l.color[1] = c.y; l.color[2] = c.z;
                 int geo = getGeometry(p.getString("geometry"));
                 const Geometry& g = geometries[geo];
-                if (g.kind == GB_GEOM_MESH) {
-                    err = "light '" + name + "': mesh area lights are outside the accelerated path "
-                        "(sphere and disk emitters only)";
-                    return false;
-                }
                 pl.geometry = geo;
                 pl.xf = getTransform(p);
                 l.geom_kind = g.kind;
@@ -583,6 +579,34 @@ struct Loader {
                 // (GoblinContextLoader.cpp:419-441)
                 int mat = addMaterial(type + "_" + name + "_material", lambert(Color3{0, 0, 0}));
                 int model = addModel(geo, mat, (int)lights.size(), false);
+                pl.model = model;
+                if (g.kind == GB_GEOM_MESH) {
+                    // GeometrySet: one Triangle per face, areas in face order, CDF1D over them
+                    // (src/GoblinLight.cpp:289-306, src/GoblinSampler.cpp:312-330)
+                    const MeshData& md = g.mesh;
+                    const size_t nt = md.numTris();
+                    l.area_offset = (uint32_t)out->lightTriArea.size();
+                    l.cdf_offset = (uint32_t)out->lightTriCdf.size();
+                    float sum = 0.0f;
+                    for (size_t t = 0; t < nt; ++t) {
+                        const float* a = &md.pos[3 * md.idx[3 * t]];
+                        const float* b = &md.pos[3 * md.idx[3 * t + 1]];
+                        const float* c = &md.pos[3 * md.idx[3 * t + 2]];
+                        Vec3 p0(a[0], a[1], a[2]), p1(b[0], b[1], b[2]), p2(c[0], c[1], c[2]);
+                        float area = 0.5f * length(cross(p1 - p0, p2 - p0)); // Triangle::area
+                        out->lightTriArea.push_back(area);
+                        sum += area;
+                    }
+                    l.area = sum;
+                    std::vector<float> cdf(nt + 1, 0.0f);
+                    if (nt) {
+                        float dx = 1.0f / nt;
+                        for (size_t i = 1; i < nt + 1; ++i) cdf[i] = cdf[i - 1] + out->lightTriArea[l.area_offset + i - 1] * dx;
+                        float integral = cdf[nt];
+                        for (size_t i = 1; i < nt + 1; ++i) cdf[i] /= integral;
+                    }
+                    out->lightTriCdf.insert(out->lightTriCdf.end(), cdf.begin(), cdf.end());
+                }
                 PrimitiveDef pd;
                 pd.model = model;
                 addFirst(primitiveByName, type + "_" + name + "_model", pd);
@@ -666,6 +690,7 @@ struct Loader {
             }
             out->lightPower.push_back(0.212671f * pr + 0.715160f * pg + 0.072169f * pb);
             out->lights.push_back(l);
+            if (pl.model >= 0 && l.geom_kind == GB_GEOM_MESH) out->lights.back().model = flattenModel(pl.model);
         }
         size_t n = out->lightPower.size();
         out->lightCdf.assign(n + 1, 0.0f);
@@ -761,6 +786,10 @@ void gb_scene::fillDesc(gb_scene_desc* d) const {
     d->n_lights = (uint32_t)lights.size();
     d->light_power = lightPower.data();
     d->light_cdf = lightCdf.data();
+    d->light_tri_area = lightTriArea.data();
+    d->light_tri_cdf = lightTriCdf.data();
+    d->n_light_tri_area = (uint32_t)lightTriArea.size();
+    d->n_light_tri_cdf = (uint32_t)lightTriCdf.size();
     std::memcpy(d->world_bound, worldBound, sizeof worldBound);
     d->camera = camera;
     d->film = film;

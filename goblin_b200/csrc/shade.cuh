@@ -459,6 +459,37 @@ __device__ __forceinline__ float genericShapePdf(int kind, float radius, float a
     if (isinf(pdf)) pdf = 0.0f;
     return pdf;
 }
+// GeometrySet::pdf over a mesh emitter (GoblinLight.cpp:336-343): every face's Geometry::pdf
+// (GoblinGeometry.cpp:44-62 through Triangle::intersect, GoblinTriangle.cpp:38-125), area
+// weighted, summed in face order.  O(faces) per evaluation, exactly like the reference.
+__device__ __forceinline__ float meshLightPdf(const DeviceScene& sc, unsigned int triBase, unsigned int triCount,
+    bool hasNormal, float sumArea, float3 p, float3 wi) {
+    float pdf = 0.0f;
+    for (unsigned int i = 0; i < triCount; ++i) {
+        const float4* lt = sc.lightTris + 6 * (size_t)(triBase + i);
+        const float4 a = __ldg(lt), b = __ldg(lt + 1), c = __ldg(lt + 2);
+        const float3 p0 = make3(a.x, a.y, a.z), p1 = make3(b.x, b.y, b.z), p2 = make3(c.x, c.y, c.z);
+        const float3 e1 = p1 - p0, e2 = p2 - p0;
+        float t, b1, b2, gp = 0.0f;
+        if (triangleTest(p0, e1, e2, p, wi, 1e-3f, INFINITY, &t, &b1, &b2)) {
+            float3 nHit;
+            if (hasNormal) {
+                const float4 n0 = __ldg(lt + 3), n1 = __ldg(lt + 4), n2 = __ldg(lt + 5);
+                const float b0 = 1.0f - b1 - b2;
+                nHit = normalize3(b0 * make3(n0.x, n0.y, n0.z) + b1 * make3(n1.x, n1.y, n1.z) + b2 * make3(n2.x, n2.y, n2.z));
+            } else {
+                nHit = normalize3(cross3(e1, e2));
+            }
+            const float3 pHit = p + t * wi;
+            gp = sqLen3(p - pHit) / (a.w * absdot3(-wi, nHit));
+            if (isinf(gp)) gp = 0.0f;
+        }
+        pdf += a.w * gp;
+    }
+    pdf /= sumArea;
+    return pdf;
+}
+
 // Sphere::pdf (GoblinSphere.cpp:138-149) / Disk -> Geometry::pdf, then
 // GeometrySet::pdf's area weighting (GoblinLight.cpp:336-343) for one shape.
 __device__ __forceinline__ float shapePdf(int kind, float radius, float area, float3 p, float3 wi) {
@@ -493,7 +524,7 @@ struct LightSampleResult {
 // Light::sampleL for each light type (GoblinLight.cpp:87-99 point, 145-154
 // directional, 225-237 spot, 368-394 area) and Light::isDelta.
 __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, int li, float3 p, float eps,
-    float u1, float u2) {
+    float uComp, float u1, float u2) {
     LightSampleResult r;
     const DeviceLight& l = sc.lights[li];
     float4 ct = __ldg(&l.colorType);
@@ -538,7 +569,29 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
         float4 i0 = __ldg(&l.toObject[0]), i1 = __ldg(&l.toObject[1]), i2 = __ldg(&l.toObject[2]);
         float3 pLocal = xfPoint(i0, i1, i2, p);
         float3 nsLocal, psLocal;
-        if (kind == GB_GEOM_SPHERE) { // Sphere::sample(p, u1, u2, n), GoblinSphere.cpp:108-136
+        unsigned int mTriBase = 0, mTriCount = 0;
+        bool mHasNormal = false;
+        if (kind == GB_GEOM_MESH) { // GeometrySet::sample -> Triangle::sample, GoblinTriangle.cpp:165-178
+            const float4 dc = __ldg(&l.dirCos);
+            mTriBase = __float_as_uint(dc.x);
+            mTriCount = __float_as_uint(dc.y);
+            mHasNormal = __float_as_uint(dc.z) != 0u;
+            const float* cdf = sc.lightTriCdf + __float_as_uint(dc.w);
+            int lo = 0, count = (int)mTriCount + 1; // CDF1D::sampleDiscrete: std::lower_bound
+            while (count > 0) {
+                int step = count >> 1;
+                if (__ldg(cdf + lo + step) < uComp) { lo += step + 1; count -= step + 1; }
+                else count = step;
+            }
+            int face = min(max(0, lo - 1), (int)mTriCount - 1);
+            const float4* lt = sc.lightTris + 6 * (size_t)(mTriBase + (unsigned int)face);
+            const float4 a = __ldg(lt), b = __ldg(lt + 1), c = __ldg(lt + 2);
+            const float3 p0 = make3(a.x, a.y, a.z), p1 = make3(b.x, b.y, b.z), p2 = make3(c.x, c.y, c.z);
+            const float u1root = sqrtf(u1); // uniformSampleTriangle
+            const float b0 = 1.0f - u1root, b1 = u1root * u2;
+            nsLocal = normalize3(cross3(p1 - p0, p2 - p0));
+            psLocal = b0 * p0 + b1 * p1 + (1.0f - b0 - b1) * p2;
+        } else if (kind == GB_GEOM_SPHERE) { // Sphere::sample(p, u1, u2, n), GoblinSphere.cpp:108-136
             float squaredRadius = radius * radius;
             float squaredDistance = sqLen3(pLocal);
             if (squaredDistance - squaredRadius < 1e-4f) {
@@ -564,7 +617,8 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
             psLocal = make3(radius * pxy.x, radius * pxy.y, 0.0f);
         }
         float3 wiLocal = normalize3(psLocal - pLocal);
-        r.pdf = shapePdf(kind, radius, area, pLocal, wiLocal);
+        r.pdf = kind == GB_GEOM_MESH ? meshLightPdf(sc, mTriBase, mTriCount, mHasNormal, area, pLocal, wiLocal)
+                                     : shapePdf(kind, radius, area, pLocal, wiLocal);
         float3 ps = xfPoint(w0, w1, w2, psLocal);
         float3 nw = make3(i0.x * nsLocal.x + i1.x * nsLocal.y + i2.x * nsLocal.z,
                           i0.y * nsLocal.x + i1.y * nsLocal.y + i2.y * nsLocal.z,
@@ -587,6 +641,11 @@ __device__ __forceinline__ float lightPdf(const DeviceScene& sc, int li, float3 
     float4 i0 = __ldg(&l.toObject[0]), i1 = __ldg(&l.toObject[1]), i2 = __ldg(&l.toObject[2]);
     float3 pLocal = xfPoint(i0, i1, i2, p);
     float3 wiLocal = xfVector(i0, i1, i2, wi);
+    if (__float_as_int(misc.z) == GB_GEOM_MESH) {
+        const float4 dc = __ldg(&l.dirCos);
+        return meshLightPdf(sc, __float_as_uint(dc.x), __float_as_uint(dc.y), __float_as_uint(dc.z) != 0u, misc.y, pLocal,
+            wiLocal);
+    }
     return shapePdf(__float_as_int(misc.z), pr.w, misc.y, pLocal, wiLocal);
 }
 

@@ -303,6 +303,8 @@ static void genTiny(const std::string& dir) {
     const uint32_t q[24] = {0, 3, 2, 1, 4, 5, 6, 7, 0, 1, 5, 4, 2, 3, 7, 6, 1, 2, 6, 5, 0, 4, 7, 3};
     box.idx.assign(q, q + 24);
     writeObj(dir + "/models/box.obj", box, 3, true);
+    // a small bumpy panel with vn: the mesh emitter (GeometrySet over 8 triangles)
+    writeObj(dir + "/models/panel.obj", gridMesh(2, 0.5, 0.06, 9, true), 2);
 
     const char* methods[2] = {"path_tracing", "ao"};
     const char* names[2] = {"tiny_pt.json", "tiny_ao.json"};
@@ -320,7 +322,8 @@ static void genTiny(const std::string& dir) {
               "    {\"name\": \"unitball\", \"type\": \"sphere\"},\n"
               "    {\"name\": \"plate\", \"type\": \"disk\", \"radius\": 0.8},\n"
               "    {\"name\": \"lamp\", \"type\": \"disk\", \"radius\": 0.7},\n"
-              "    {\"name\": \"bulb\", \"type\": \"sphere\", \"radius\": 0.25}\n  ],\n"
+              "    {\"name\": \"bulb\", \"type\": \"sphere\", \"radius\": 0.25},\n"
+              "    {\"name\": \"panel\", \"type\": \"mesh\", \"file\": \"models/panel.obj\"}\n  ],\n"
               "  \"textures\": [\n"
               "    {\"format\": \"color\", \"name\": \"grey\", \"type\": \"constant\", \"color\": [0.6, 0.6, 0.6]},\n"
               "    {\"format\": \"color\", \"name\": \"red\", \"type\": \"constant\", \"color\": [0.8, 0.25, 0.2]},\n"
@@ -362,6 +365,8 @@ static void genTiny(const std::string& dir) {
               "     \"position\": [0.5, 4.0, 0.0], \"euler\": [90.0, 0.0, 0.0]},\n"
               "    {\"name\": \"bulb\", \"type\": \"area\", \"geometry\": \"bulb\", \"radiance\": [9.0, 9.0, 12.0],\n"
               "     \"position\": [-2.2, 1.4, -1.4]},\n"
+              "    {\"name\": \"panel\", \"type\": \"area\", \"geometry\": \"panel\", \"radiance\": [5.0, 6.0, 8.0],\n"
+              "     \"position\": [2.2, 2.8, 1.2], \"euler\": [150.0, 20.0, 0.0], \"scale\": [1.5, 1.5, 1.5]},\n"
               "    {\"name\": \"pt\", \"type\": \"point\", \"intensity\": [6.0, 5.0, 4.0], \"position\": [3.0, 2.5, -2.5]},\n"
               "    {\"name\": \"spot\", \"type\": \"spot\", \"intensity\": [30.0, 30.0, 24.0], \"position\": [-3.0, 4.0, -3.0],\n"
               "     \"target\": [0.0, 0.0, 0.0], \"theta_max\": 25.0, \"falloff_start\": 15.0},\n"

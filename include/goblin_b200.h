@@ -119,12 +119,16 @@ typedef struct gb_light {
     float direction[3];    /* directional: getDirection(); spot: cone axis     */
     float cos_theta_max;   /* spot                                             */
     float cos_falloff_start;
-    int32_t geom_kind;     /* area: GB_GEOM_SPHERE / GB_GEOM_DISK              */
-    float radius;          /* area                                             */
+    int32_t geom_kind;     /* area: GB_GEOM_SPHERE / GB_GEOM_DISK / GB_GEOM_MESH */
+    float radius;          /* area (sphere / disk)                             */
     float area;            /* area: GeometrySet::mSumArea                      */
     float to_world[12];    /* area: light's own Transform                      */
     float to_object[12];
     int32_t instance;      /* area: scene instance that carries the geometry   */
+    /* mesh emitters (GeometrySet over the mesh's triangles, src/GoblinLight.cpp:289-343): */
+    int32_t model;         /* the emitting mesh model, -1 otherwise            */
+    uint32_t area_offset;  /* first per-face area in light_tri_area            */
+    uint32_t cdf_offset;   /* first of tri_count + 1 entries in light_tri_cdf  */
 } gb_light;
 
 typedef struct gb_camera {
@@ -179,6 +183,9 @@ typedef struct gb_scene_desc {
     uint32_t n_lights;
     const float* light_power;       /* CDF1D::mFunction, n_lights             */
     const float* light_cdf;         /* CDF1D::mCDF, n_lights + 1              */
+    const float* light_tri_area;    /* mesh emitters: GeometrySet::mGeometriesArea, face order */
+    const float* light_tri_cdf;     /* mesh emitters: mAreaDistribution->mCDF  */
+    uint32_t n_light_tri_area, n_light_tri_cdf;
     float world_bound[6];           /* Scene BVH AABB (getBoundingSphere)     */
     gb_camera camera;
     gb_film_desc film;

@@ -657,6 +657,47 @@ struct Oracle {
         if (std::isinf(pdf)) pdf = 0.0f;
         return pdf;
     }
+    // ---- mesh emitters: GeometrySet over the mesh's triangles (src/GoblinLight.cpp:289-343)
+    struct TriVerts { V3 p0, p1, p2; };
+    TriVerts lightFace(const gb_model& m, uint32_t face) const {
+        const uint32_t* ti = d->tri_index + 3 * ((size_t)m.tri_offset + face);
+        return TriVerts{vpos(m, ti[0]), vpos(m, ti[1]), vpos(m, ti[2])};
+    }
+    static float faceArea(const TriVerts& t) { return 0.5f * len(cross(t.p1 - t.p0, t.p2 - t.p0)); } // Triangle::area
+    float meshSumArea(const gb_model& m) const {
+        float sum = 0.0f;
+        for (uint32_t f = 0; f < m.tri_count; ++f) sum += faceArea(lightFace(m, f));
+        return sum;
+    }
+    // CDF1D over the face areas + sampleDiscrete (src/GoblinSampler.cpp:312-342)
+    uint32_t meshPickFace(const gb_model& m, float u) const {
+        const uint32_t n = m.tri_count;
+        std::vector<float> cdf(n + 1, 0.0f);
+        const float dx = 1.0f / n;
+        for (uint32_t i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + faceArea(lightFace(m, i - 1)) * dx;
+        const float integral = cdf[n];
+        for (uint32_t i = 1; i < n + 1; ++i) cdf[i] /= integral;
+        const float* lb = std::lower_bound(cdf.data(), cdf.data() + n + 1, u);
+        int offset = std::max(0, (int)(lb - cdf.data() - 1));
+        return (uint32_t)std::min(offset, (int)n - 1);
+    }
+    float meshPdf(const gb_model& m, float sumArea, V3 p, V3 wi) const {
+        float pdf = 0.0f;
+        for (uint32_t f = 0; f < m.tri_count; ++f) { // Geometry::pdf per face, area weighted, in face order
+            Ray ray{p, wi, 1e-3f, INF};
+            float eps;
+            Frag fr;
+            float gp = 0.0f;
+            if (triangleIntersect(m, f, ray, &eps, &fr)) {
+                gp = sqLen(p - fr.p) / (faceArea(lightFace(m, f)) * absdot(-wi, fr.n));
+                if (std::isinf(gp)) gp = 0.0f;
+            }
+            pdf += faceArea(lightFace(m, f)) * gp;
+        }
+        pdf /= sumArea;
+        return pdf;
+    }
+
     // GeometrySet::pdf over the light's single shape (src/GoblinLight.cpp:336-343, src/GoblinSphere.cpp:138-149)
     static float shapePdf(const gb_light& l, V3 p, V3 wi) {
         float gpdf;
@@ -677,7 +718,8 @@ struct Oracle {
         pdf /= l.area;
         return pdf;
     }
-    V3 sampleL(const gb_light& l, V3 p, float epsilon, float u1, float u2, V3* wi, float* pdf, Ray* shadow) const {
+    V3 sampleL(const gb_light& l, V3 p, float epsilon, float uComp, float u1, float u2, V3* wi, float* pdf,
+        Ray* shadow) const {
         shadow->o = p;
         shadow->mint = epsilon;
         shadow->maxt = INF;
@@ -709,7 +751,14 @@ struct Oracle {
         // AreaLight::sampleL
         V3 pLocal = xfPoint(l.to_object, p);
         V3 nsLocal, psLocal;
-        if (l.geom_kind == GB_GEOM_SPHERE) { // Sphere::sample(p, u1, u2, n), src/GoblinSphere.cpp:108-136
+        if (l.geom_kind == GB_GEOM_MESH) { // GeometrySet::sample -> Triangle::sample, src/GoblinTriangle.cpp:165-178
+            const gb_model& m = d->models[l.model];
+            TriVerts t = lightFace(m, meshPickFace(m, uComp));
+            float u1root = sqrtf(u1); // uniformSampleTriangle, src/GoblinSampler.cpp:420-424
+            float b0 = 1.0f - u1root, b1 = u1root * u2;
+            nsLocal = normalize(cross(t.p1 - t.p0, t.p2 - t.p0));
+            psLocal = b0 * t.p0 + b1 * t.p1 + (1.0f - b0 - b1) * t.p2;
+        } else if (l.geom_kind == GB_GEOM_SPHERE) { // Sphere::sample(p, u1, u2, n), src/GoblinSphere.cpp:108-136
             float squaredRadius = l.radius * l.radius;
             float squaredDistance = sqLen(pLocal);
             if (squaredDistance - squaredRadius < 1e-4f) {
@@ -737,7 +786,12 @@ struct Oracle {
             psLocal = V3(l.radius * px, l.radius * py, 0.0f);
         }
         V3 wiLocal = normalize(psLocal - pLocal);
-        *pdf = shapePdf(l, pLocal, wiLocal);
+        if (l.geom_kind == GB_GEOM_MESH) {
+            const gb_model& m = d->models[l.model];
+            *pdf = meshPdf(m, meshSumArea(m), pLocal, wiLocal);
+        } else {
+            *pdf = shapePdf(l, pLocal, wiLocal);
+        }
         V3 ps = xfPoint(l.to_world, psLocal);
         V3 ns = normalize(xfNormal(l.to_object, nsLocal));
         *wi = normalize(ps - p);
@@ -747,6 +801,10 @@ struct Oracle {
     }
     float lightPdf(const gb_light& l, V3 p, V3 wi) const { // Light::pdf / AreaLight::pdf
         if (l.type != GB_LIGHT_AREA) return 0.0f;
+        if (l.geom_kind == GB_GEOM_MESH) {
+            const gb_model& m = d->models[l.model];
+            return meshPdf(m, meshSumArea(m), xfPoint(l.to_object, p), xfVector(l.to_object, wi));
+        }
         return shapePdf(l, xfPoint(l.to_object, p), xfVector(l.to_object, wi));
     }
     // Intersection::Le, src/GoblinPrimitive.cpp:8-14
@@ -785,7 +843,7 @@ struct Oracle {
             V3 n = fragment.n;
             float lightPdfV, bsdfPdfV;
             Ray shadowRay;
-            V3 L = sampleL(light, p, epsilon, ub[1], ub[2], &wi, &lightPdfV, &shadowRay);
+            V3 L = sampleL(light, p, epsilon, ub[0], ub[1], ub[2], &wi, &lightPdfV, &shadowRay);
             if (!isBlack(L) && lightPdfV > 0.0f) {
                 V3 f = bsdf(material, fragment, wo, wi);
                 if (!isBlack(f)) {
