@@ -311,8 +311,8 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
 // hit carries material MAT.  `bounce` is the reference's loop variable; with
 // emissionOnly the kernel only resolves the pending BSDF-sampled emission
 // (the reference's trace #4 of the last iteration).
-template <int MAT>
-__global__ void __launch_bounds__(kShadeBlock, 8)
+template <int MAT, bool ML>
+__global__ void __launch_bounds__(kShadeBlock, (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) ? 6 : 8)
 k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounce, int emissionOnly,
     unsigned int* ctr, unsigned int* ctrNext, unsigned int* qNext) {
     const unsigned int n = ctr[C_MAT0 + MAT];
@@ -362,7 +362,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 m.kdType = __ldg(&mat.kdType);
                 m.ktEta = __ldg(&mat.ktEta);
                 if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
-                    LightSampleResult ls = sampleLight(sc, li, fr.p, eps, uA.x, uA.y, uA.z);
+                    LightSampleResult ls = sampleLight<ML>(sc, li, fr.p, eps, uA.x, uA.y, uA.z);
                     if (!isBlack(ls.L) && ls.pdf > 0.0f) {
                         float3 f = MAT == GB_MAT_LAMBERT ? lambertEval(m, fr.n, wo, ls.wi) : blinnEval(m, fr.n, wo, ls.wi);
                         if (!isBlack(f)) {
@@ -382,7 +382,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 float4 pendOut = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
                 if (!isBlack(bs.f) && bs.pdf > 0.0f) {
                     float fWeight = 1.0f;
-                    if (!bs.specular) fWeight = powerHeuristic(bs.pdf, lightPdf(sc, li, fr.p, bs.wi));
+                    if (!bs.specular) fWeight = powerHeuristic(bs.pdf, lightPdf<ML>(sc, li, fr.p, bs.wi));
                     int ltype = __float_as_int(__ldg(&sc.lights[li].colorType).w);
                     if (ltype == GB_LIGHT_AREA) {
                         float3 w = div3(bs.f * absdot3(bs.wi, fr.n) * fWeight, bs.pdf);
@@ -640,6 +640,7 @@ struct gb_context {
     TraceTuning tune{20u, 6u, 4u, 10u};
     int blocksPerSM = 0; // 0 = as many as fit
     bool hasBlinn = false; // the scene uses a Blinn material: launch its shade kernel
+    bool hasMeshLight = false; // the scene has a mesh emitter: shade kernels with the GeometrySet loop
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;
     std::vector<cudaEvent_t> evPool;
@@ -1095,6 +1096,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
     DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
+    bool hasMeshLight = false;
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const gb_light& gl = d->lights[l];
         DeviceLight& dl = lights[l];
@@ -1130,6 +1132,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             }
             uint32_t w[4] = {gl.area_offset, md.tri_count, md.has_normal ? 1u : 0u, gl.cdf_offset};
             std::memcpy(&dl.dirCos, w, 16);
+            hasMeshLight = true;
         }
         dl.misc = make_float4(gl.cos_falloff_start, gl.area, kb, sb);
         for (int r = 0; r < 3; ++r) {
@@ -1201,6 +1204,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     ctx->sc = sc;
     ctx->setting = d->setting;
     ctx->hasBlinn = hasBlinn;
+    ctx->hasMeshLight = hasMeshLight;
     ctx->haveScene = true;
     if (traceSmem(ctx) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
     return GB_OK;
@@ -1377,10 +1381,15 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             int eo = last ? 1 : 0;
             {
                 KernelTick tick(ctx, GB_K_SHADE);
-                k_shade<GB_MAT_LAMBERT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
-                k_shade<GB_MAT_MIRROR><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
-                k_shade<GB_MAT_TRANSPARENT><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
-                if (ctx->hasBlinn) k_shade<GB_MAT_BLINN><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);
+#define GB_SHADE(MATV, MLV) k_shade<MATV, MLV><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
+                if (ctx->hasMeshLight) {
+                    GB_SHADE(GB_MAT_LAMBERT, true); GB_SHADE(GB_MAT_MIRROR, true); GB_SHADE(GB_MAT_TRANSPARENT, true);
+                    if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, true);
+                } else {
+                    GB_SHADE(GB_MAT_LAMBERT, false); GB_SHADE(GB_MAT_MIRROR, false); GB_SHADE(GB_MAT_TRANSPARENT, false);
+                    if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, false);
+                }
+#undef GB_SHADE
             }
             ctx->launches += ctx->hasBlinn ? 4 : 3;
             if (!last) {

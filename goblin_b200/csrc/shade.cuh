@@ -462,7 +462,8 @@ __device__ __forceinline__ float genericShapePdf(int kind, float radius, float a
 // GeometrySet::pdf over a mesh emitter (GoblinLight.cpp:336-343): every face's Geometry::pdf
 // (GoblinGeometry.cpp:44-62 through Triangle::intersect, GoblinTriangle.cpp:38-125), area
 // weighted, summed in face order.  O(faces) per evaluation, exactly like the reference.
-__device__ __forceinline__ float meshLightPdf(const DeviceScene& sc, unsigned int triBase, unsigned int triCount,
+// (kept out of line: mesh emitters are rare and their loop must not cost the common shade path registers)
+__device__ __noinline__ float meshLightPdf(const DeviceScene& sc, unsigned int triBase, unsigned int triCount,
     bool hasNormal, float sumArea, float3 p, float3 wi) {
     float pdf = 0.0f;
     for (unsigned int i = 0; i < triCount; ++i) {
@@ -488,6 +489,27 @@ __device__ __forceinline__ float meshLightPdf(const DeviceScene& sc, unsigned in
     }
     pdf /= sumArea;
     return pdf;
+}
+
+// GeometrySet::sample -> Triangle::sample (GoblinLight.cpp:308-320, GoblinTriangle.cpp:165-178):
+// face by area CDF (CDF1D::sampleDiscrete = std::lower_bound), point by uniformSampleTriangle.
+__device__ __noinline__ void sampleMeshEmitter(const DeviceScene& sc, unsigned int triBase, unsigned int triCount,
+    unsigned int cdfBase, float uComp, float u1, float u2, float3* ps, float3* ns) {
+    const float* cdf = sc.lightTriCdf + cdfBase;
+    int lo = 0, count = (int)triCount + 1;
+    while (count > 0) {
+        int step = count >> 1;
+        if (__ldg(cdf + lo + step) < uComp) { lo += step + 1; count -= step + 1; }
+        else count = step;
+    }
+    const int face = min(max(0, lo - 1), (int)triCount - 1);
+    const float4* lt = sc.lightTris + 6 * (size_t)(triBase + (unsigned int)face);
+    const float4 a = __ldg(lt), b = __ldg(lt + 1), c = __ldg(lt + 2);
+    const float3 p0 = make3(a.x, a.y, a.z), p1 = make3(b.x, b.y, b.z), p2 = make3(c.x, c.y, c.z);
+    const float u1root = sqrtf(u1); // uniformSampleTriangle
+    const float b0 = 1.0f - u1root, b1 = u1root * u2;
+    *ns = normalize3(cross3(p1 - p0, p2 - p0));
+    *ps = b0 * p0 + b1 * p1 + (1.0f - b0 - b1) * p2;
 }
 
 // Sphere::pdf (GoblinSphere.cpp:138-149) / Disk -> Geometry::pdf, then
@@ -523,6 +545,9 @@ struct LightSampleResult {
 
 // Light::sampleL for each light type (GoblinLight.cpp:87-99 point, 145-154
 // directional, 225-237 spot, 368-394 area) and Light::isDelta.
+// ML: the scene has mesh emitters (compiled out otherwise: their loop would cost every shade
+// kernel registers).
+template <bool ML>
 __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, int li, float3 p, float eps,
     float uComp, float u1, float u2) {
     LightSampleResult r;
@@ -571,26 +596,12 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
         float3 nsLocal, psLocal;
         unsigned int mTriBase = 0, mTriCount = 0;
         bool mHasNormal = false;
-        if (kind == GB_GEOM_MESH) { // GeometrySet::sample -> Triangle::sample, GoblinTriangle.cpp:165-178
+        if (ML && kind == GB_GEOM_MESH) {
             const float4 dc = __ldg(&l.dirCos);
             mTriBase = __float_as_uint(dc.x);
             mTriCount = __float_as_uint(dc.y);
             mHasNormal = __float_as_uint(dc.z) != 0u;
-            const float* cdf = sc.lightTriCdf + __float_as_uint(dc.w);
-            int lo = 0, count = (int)mTriCount + 1; // CDF1D::sampleDiscrete: std::lower_bound
-            while (count > 0) {
-                int step = count >> 1;
-                if (__ldg(cdf + lo + step) < uComp) { lo += step + 1; count -= step + 1; }
-                else count = step;
-            }
-            int face = min(max(0, lo - 1), (int)mTriCount - 1);
-            const float4* lt = sc.lightTris + 6 * (size_t)(mTriBase + (unsigned int)face);
-            const float4 a = __ldg(lt), b = __ldg(lt + 1), c = __ldg(lt + 2);
-            const float3 p0 = make3(a.x, a.y, a.z), p1 = make3(b.x, b.y, b.z), p2 = make3(c.x, c.y, c.z);
-            const float u1root = sqrtf(u1); // uniformSampleTriangle
-            const float b0 = 1.0f - u1root, b1 = u1root * u2;
-            nsLocal = normalize3(cross3(p1 - p0, p2 - p0));
-            psLocal = b0 * p0 + b1 * p1 + (1.0f - b0 - b1) * p2;
+            sampleMeshEmitter(sc, mTriBase, mTriCount, __float_as_uint(dc.w), uComp, u1, u2, &psLocal, &nsLocal);
         } else if (kind == GB_GEOM_SPHERE) { // Sphere::sample(p, u1, u2, n), GoblinSphere.cpp:108-136
             float squaredRadius = radius * radius;
             float squaredDistance = sqLen3(pLocal);
@@ -617,7 +628,7 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
             psLocal = make3(radius * pxy.x, radius * pxy.y, 0.0f);
         }
         float3 wiLocal = normalize3(psLocal - pLocal);
-        r.pdf = kind == GB_GEOM_MESH ? meshLightPdf(sc, mTriBase, mTriCount, mHasNormal, area, pLocal, wiLocal)
+        r.pdf = (ML && kind == GB_GEOM_MESH) ? meshLightPdf(sc, mTriBase, mTriCount, mHasNormal, area, pLocal, wiLocal)
                                      : shapePdf(kind, radius, area, pLocal, wiLocal);
         float3 ps = xfPoint(w0, w1, w2, psLocal);
         float3 nw = make3(i0.x * nsLocal.x + i1.x * nsLocal.y + i2.x * nsLocal.z,
@@ -632,6 +643,7 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
 }
 
 // Light::pdf(p, wi): 0 for delta lights (GoblinLight.h:110-112), AreaLight::pdf otherwise (GoblinLight.cpp:456-460)
+template <bool ML>
 __device__ __forceinline__ float lightPdf(const DeviceScene& sc, int li, float3 p, float3 wi) {
     const DeviceLight& l = sc.lights[li];
     int type = __float_as_int(__ldg(&l.colorType).w);
@@ -641,7 +653,7 @@ __device__ __forceinline__ float lightPdf(const DeviceScene& sc, int li, float3 
     float4 i0 = __ldg(&l.toObject[0]), i1 = __ldg(&l.toObject[1]), i2 = __ldg(&l.toObject[2]);
     float3 pLocal = xfPoint(i0, i1, i2, p);
     float3 wiLocal = xfVector(i0, i1, i2, wi);
-    if (__float_as_int(misc.z) == GB_GEOM_MESH) {
+    if (ML && __float_as_int(misc.z) == GB_GEOM_MESH) {
         const float4 dc = __ldg(&l.dirCos);
         return meshLightPdf(sc, __float_as_uint(dc.x), __float_as_uint(dc.y), __float_as_uint(dc.z) != 0u, misc.y, pLocal,
             wiLocal);
