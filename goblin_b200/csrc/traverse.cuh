@@ -320,6 +320,10 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             if (__uint_as_float(e.y) < maxt) cur = e.x;
                         } else {
                             cur = REF_NONE;
+                            // world space with an empty stack, or nothing left in this instance, in
+                            // its top-level leaf and on the top-level stack: the ray ends here, no
+                            // level change needed
+                            if (level == 1 && spFloor == 0 && instNext >= instEnd) fin = true;
                         }
                     }
                 }
