@@ -203,6 +203,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="bunny", choices=sorted(SCENES))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--accel", default="equal_count", choices=["equal_count", "middle", "sah"],
+                    help="BVH split method: equal_count = the reference's tree (the headline, parity mode); "
+                         "sah = the non-parity fast tree (SURVEY 8(f) rank 1)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
     ap.add_argument("--wave-paths", type=int, default=0)
     ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
@@ -243,7 +246,7 @@ def main():
     barrier()
     scene_json = scene_path(args.scene)
     t0 = time.perf_counter()
-    scene = api.Scene(scene_json)
+    scene = api.Scene(scene_json, accel=args.accel)
     load_s = time.perf_counter() - t0
     if args.stats_only:
         seed, spp_total, b, e = (int(v) for v in args.stats_only.split(","))
@@ -266,7 +269,7 @@ def main():
             rng0 = (0, min(spp0, per0))
         else:
             rng0 = (0, spp0)
-        cmd = [sys.executable, os.path.abspath(__file__), "--scene", args.scene, "--stats-only",
+        cmd = [sys.executable, os.path.abspath(__file__), "--scene", args.scene, "--accel", args.accel, "--stats-only",
                f"1000,{spp0},{rng0[0]},{rng0[1]}"]
         if args.wave_paths:
             cmd += ["--wave-paths", str(args.wave_paths)]
@@ -431,8 +434,8 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": NOTES[args.scene], "scene": args.scene, "spp": spp, "spp_range_rank0": [spp_begin, spp_end],
-                           "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
+                "config": {"workload": NOTES[args.scene], "scene": args.scene, "accel": args.accel, "spp": spp,
+                           "spp_range_rank0": [spp_begin, spp_end], "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
                            "parallelism": f"spp x{world} (scene replica per GPU, NCCL film all-reduce)" if world > 1 else "1 GPU",
                            "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~176 B per camera sample, GBs per wave) exceeds L2",
                            "scene_load_s": load_s},

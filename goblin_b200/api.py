@@ -85,6 +85,15 @@ class SceneDesc(C.Structure):
                 ("setting", RenderSetting)]
 
 
+class LoadOptions(C.Structure):
+    _fields_ = [("bvh_method", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+# GB_BVH_*: equal_count = the reference's tree (parity), middle = its unused other method,
+# sah = the non-parity fast tree
+BVH_METHODS = {"equal_count": 0, "middle": 1, "sah": 2}
+
+
 class RenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("spp_total", C.c_int32), ("spp_begin", C.c_int32),
                 ("spp_end", C.c_int32), ("max_ray_depth", C.c_int32), ("method", C.c_int32),
@@ -106,8 +115,9 @@ NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offse
 
 # every symbol include/goblin_b200.h declares
 EXPORTS = [
-    "gb_scene_load_json", "gb_scene_load_json_string", "gb_scene_destroy", "gb_scene_get_desc",
-    "gb_scene_output_path", "gb_bvh_build", "gb_device_count", "gb_create", "gb_destroy",
+    "gb_scene_load_json", "gb_scene_load_json_string", "gb_scene_load_json_ex",
+    "gb_scene_load_json_string_ex", "gb_scene_destroy", "gb_scene_get_desc",
+    "gb_scene_output_path", "gb_bvh_build", "gb_bvh_build_method", "gb_device_count", "gb_create", "gb_destroy",
     "gb_upload_scene", "gb_trace_closest", "gb_trace_any", "gb_trace_closest_device",
     "gb_trace_any_device", "gb_camera_rays", "gb_li", "gb_render", "gb_film_clear",
     "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image",
@@ -141,6 +151,11 @@ def lib():
         l.gb_scene_destroy.argtypes = [C.c_void_p]
         l.gb_scene_load_json.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         l.gb_scene_load_json_string.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        l.gb_scene_load_json_ex.argtypes = [C.c_char_p, C.POINTER(LoadOptions), C.POINTER(C.c_void_p)]
+        l.gb_scene_load_json_string_ex.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(LoadOptions),
+                                                   C.POINTER(C.c_void_p)]
+        l.gb_bvh_build_method.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
+                                          C.c_void_p]
         l.gb_scene_get_desc.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
         l.gb_bvh_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
         l.gb_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -194,13 +209,15 @@ class Scene:
     """Host-side flattened scene: ContextLoader::load of the reference
     (src/GoblinContextLoader.cpp:447-503)."""
 
-    def __init__(self, path=None, json_text=None, scene_dir=None):
+    def __init__(self, path=None, json_text=None, scene_dir=None, accel="equal_count"):
         self._h = C.c_void_p()
+        self.accel = accel
+        opt = LoadOptions(bvh_method=BVH_METHODS[accel])
         if path is not None:
-            check(lib().gb_scene_load_json(os.fsencode(path), C.byref(self._h)))
+            check(lib().gb_scene_load_json_ex(os.fsencode(path), C.byref(opt), C.byref(self._h)))
         else:
-            check(lib().gb_scene_load_json_string(json_text.encode(), os.fsencode(scene_dir or "."),
-                                                  C.byref(self._h)))
+            check(lib().gb_scene_load_json_string_ex(json_text.encode(), os.fsencode(scene_dir or "."),
+                                                     C.byref(opt), C.byref(self._h)))
         self.desc = SceneDesc()
         check(lib().gb_scene_get_desc(self._h, C.byref(self.desc)))
 
@@ -274,14 +291,15 @@ class Scene:
         return (sx1 - sx0) * (sy1 - sy0) * self.spp_squared(spp)
 
 
-def bvh_build(aabbs):
+def bvh_build(aabbs, method="equal_count"):
     """BVH::BVH on raw boxes (n x 6 float32) -> (nodes, order)."""
     aabbs = np.ascontiguousarray(aabbs, dtype=np.float32).reshape(-1, 6)
     n = aabbs.shape[0]
     nodes = np.zeros(max(2 * n, 1), dtype=NODE_DTYPE)
     order = np.zeros(max(n, 1), dtype=np.uint32)
     cnt = C.c_uint32()
-    check(lib().gb_bvh_build(aabbs.ctypes.data, n, nodes.ctypes.data, C.byref(cnt), order.ctypes.data))
+    check(lib().gb_bvh_build_method(aabbs.ctypes.data, n, BVH_METHODS[method], nodes.ctypes.data, C.byref(cnt),
+                                    order.ctypes.data))
     return nodes[:cnt.value].copy(), order[:n].copy()
 
 

@@ -1,6 +1,7 @@
 #include "bvh_builder.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <future>
 #include <thread>
@@ -18,9 +19,79 @@ struct CenterLess {
     bool operator()(const BuildItem& a, const BuildItem& b) const { return a.center[dim] < b.center[dim]; }
 };
 
+struct CenterBelow { // MidComparator, src/GoblinBVH.cpp:16-23
+    int dim;
+    float midPoint;
+    bool operator()(const BuildItem& a) const { return a.center[dim] < midPoint; }
+};
+
+inline float halfArea(const BBox& b) {
+    const Vec3 d = b.pMax - b.pMin;
+    return d.x * d.y + d.y * d.z + d.z * d.x;
+}
+
+// levels a subtree over n primitives needs at least (one primitive per leaf)
+inline int minLevels(uint32_t n) {
+    int l = 0;
+    while ((1ull << l) < n) ++l;
+    return l;
+}
+
 struct Builder {
     const std::vector<BBox>& boxes;
     std::vector<BuildItem>& items;
+    BvhMethod method = BvhMethod::EqualCount;
+    int depthLimit = 0; // Sah: deepest level a node may sit on
+
+    // Binned SAH over the three axes of the centroid bounds.  Returns false when no plane
+    // separates the centroids into two sides that both still fit under the depth limit.
+    bool sahPlane(uint32_t start, uint32_t end, int depth, const BBox& centers, int* dimOut, float* planeOut) {
+        constexpr int K = 32;
+        const uint32_t n = end - start;
+        const int levelsLeft = depthLimit - depth - 1; // levels available to each child's subtree
+        const uint64_t sideCap = levelsLeft >= 31 ? 0xffffffffull : (1ull << std::max(levelsLeft, 0));
+        float best = INFINITY;
+        bool have = false;
+        for (int dim = 0; dim < 3; ++dim) {
+            const float lo = centers.pMin[dim], hi = centers.pMax[dim];
+            if (!(hi > lo)) continue;
+            const float scale = (float)K / (hi - lo);
+            BBox binBox[K];
+            uint32_t binCount[K] = {};
+            for (uint32_t i = start; i < end; ++i) {
+                int b = (int)((items[i].center[dim] - lo) * scale);
+                b = b < 0 ? 0 : (b >= K ? K - 1 : b);
+                binBox[b].expand(boxes[items[i].index]);
+                ++binCount[b];
+            }
+            float rightArea[K]; // area of bins [b, K); only read where that range is non-empty
+            BBox acc;
+            uint32_t nacc = 0;
+            for (int b = K - 1; b > 0; --b) {
+                if (binCount[b]) acc.expand(binBox[b]);
+                nacc += binCount[b];
+                rightArea[b] = nacc ? halfArea(acc) : 0.0f;
+            }
+            BBox left;
+            uint32_t nl = 0;
+            for (int b = 0; b < K - 1; ++b) {
+                if (binCount[b]) left.expand(binBox[b]);
+                nl += binCount[b];
+                const uint32_t nr = n - nl;
+                if (nl == 0 || nr == 0 || nl > sideCap || nr > sideCap) continue;
+                const float cost = halfArea(left) * (float)nl + rightArea[b + 1] * (float)nr;
+                if (cost < best) {
+                    best = cost;
+                    have = true;
+                    *dimOut = dim;
+                    // items with bin index <= b go left: the same float arithmetic decides the
+                    // partition below
+                    *planeOut = (float)(b + 1);
+                }
+            }
+        }
+        return have;
+    }
 
     static void setBox(gb_bvh_node& nd, const BBox& b) {
         nd.bmin[0] = b.pMin.x; nd.bmin[1] = b.pMin.y; nd.bmin[2] = b.pMin.z;
@@ -36,7 +107,7 @@ struct Builder {
     // Decide leaf / split for [start, end) exactly as buildLinearBVH does
     // (src/GoblinBVH.cpp:93-141): one primitive, or all centres equal along the longest axis of
     // the centre bounds -> leaf; else nth_element at the median of that axis.
-    bool split(uint32_t start, uint32_t end, int* dimOut, uint32_t* midOut) {
+    bool split(uint32_t start, uint32_t end, int depth, int* dimOut, uint32_t* midOut) {
         if (end - start == 1) return false;
         BBox centers;
         for (uint32_t i = start; i < end; ++i) {
@@ -44,6 +115,34 @@ struct Builder {
         }
         const int dim = centers.longestAxis();
         if (centers.pMin[dim] == centers.pMax[dim]) return false;
+        if (method == BvhMethod::Sah) {
+            int sdim = 0;
+            float plane = 0.0f;
+            if (sahPlane(start, end, depth, centers, &sdim, &plane)) {
+                const float lo = centers.pMin[sdim], scale = 32.0f / (centers.pMax[sdim] - lo);
+                auto it = std::partition(items.begin() + start, items.begin() + end, [=](const BuildItem& a) {
+                    int b = (int)((a.center[sdim] - lo) * scale);
+                    b = b < 0 ? 0 : (b >= 32 ? 31 : b);
+                    return (float)b < plane;
+                });
+                const uint32_t m = (uint32_t)(it - items.begin());
+                if (m != start && m != end) {
+                    *dimOut = sdim;
+                    *midOut = m;
+                    return true;
+                }
+            }
+        } else if (method == BvhMethod::Middle) {
+            const float midPoint = 0.5f * (centers.pMin[dim] + centers.pMax[dim]);
+            auto it = std::partition(items.begin() + start, items.begin() + end, CenterBelow{dim, midPoint});
+            const uint32_t m = (uint32_t)(it - items.begin());
+            if (m != start && m != end) {
+                *dimOut = dim;
+                *midOut = m;
+                return true;
+            }
+            // "can't split down further with middle method": the equal_count case follows
+        }
         const uint32_t mid = (start + end) / 2;
         std::nth_element(items.begin() + start, items.begin() + mid, items.begin() + end, CenterLess{dim});
         *dimOut = dim;
@@ -80,7 +179,7 @@ struct Builder {
             if (f.stage == 0) {
                 int dim = 0;
                 uint32_t mid = 0;
-                if (!split(f.start, f.end, &dim, &mid)) {
+                if (!split(f.start, f.end, f.depth, &dim, &mid)) {
                     makeLeaf(out[f.node], f.start, f.end);
                     st.pop_back();
                     continue;
@@ -121,7 +220,7 @@ struct Builder {
         *maxDepth = std::max(*maxDepth, depth);
         gb_bvh_node nd;
         std::memset(&nd, 0, sizeof nd);
-        if (!split(start, end, &dim, &mid)) {
+        if (!split(start, end, depth, &dim, &mid)) {
             makeLeaf(nd, start, end);
             out.push_back(nd);
             return;
@@ -153,7 +252,7 @@ struct Builder {
 
 } // namespace
 
-void buildBVH(const std::vector<BBox>& boxes, BuiltBVH* out) {
+void buildBVH(const std::vector<BBox>& boxes, BuiltBVH* out, BvhMethod method) {
     out->nodes.clear();
     out->order.clear();
     out->bound = BBox();
@@ -167,7 +266,7 @@ void buildBVH(const std::vector<BBox>& boxes, BuiltBVH* out) {
         Vec3 c = 0.5f * (boxes[i].pMin + boxes[i].pMax); // BVHPrimitiveInfo::center
         items[i] = BuildItem{{c.x, c.y, c.z}, i};
     }
-    Builder b{boxes, items};
+    Builder b{boxes, items, method, minLevels(n) + kSahDepthSlack};
     // 2^levels concurrent subtrees: a few more than there are cores
     int levels = 0;
     for (unsigned c = std::max(1u, std::thread::hardware_concurrency()); (1u << levels) < 2 * c && levels < 8; ++levels) {}

@@ -22,13 +22,27 @@ extern "C" {
 const char* gb_last_error(void) { return gb::g_lastError.c_str(); }
 const char* gb_version(void) { return "goblin_b200 0.1 (sm_100a)"; }
 
-int gb_scene_load_json(const char* path, gb_scene** out) {
+static int bvhMethodOf(const gb_load_options* o, int* method) {
+    *method = o ? o->bvh_method : GB_BVH_EQUAL_COUNT;
+    if (*method < GB_BVH_EQUAL_COUNT || *method > GB_BVH_SAH) return gb::failWith(GB_ERR_INVALID, "unknown bvh_method");
+    return GB_OK;
+}
+
+int gb_scene_load_json(const char* path, gb_scene** out) { return gb_scene_load_json_ex(path, nullptr, out); }
+
+int gb_scene_load_json_string(const char* json, const char* scene_dir, gb_scene** out) {
+    return gb_scene_load_json_string_ex(json, scene_dir, nullptr, out);
+}
+
+int gb_scene_load_json_ex(const char* path, const gb_load_options* options, gb_scene** out) {
     if (!path || !out) return gb::failWith(GB_ERR_INVALID, "null argument");
     *out = nullptr;
+    int method = 0;
+    if (int rc = bvhMethodOf(options, &method)) return rc;
     try {
         gb_scene* s = new gb_scene();
         std::string err;
-        int rc = gb::loadSceneFile(path, s, &err);
+        int rc = gb::loadSceneFile(path, s, &err, method);
         if (rc != GB_OK) {
             delete s;
             return gb::failWith(rc, err);
@@ -40,14 +54,17 @@ int gb_scene_load_json(const char* path, gb_scene** out) {
     }
 }
 
-int gb_scene_load_json_string(const char* json, const char* scene_dir, gb_scene** out) {
+int gb_scene_load_json_string_ex(const char* json, const char* scene_dir, const gb_load_options* options,
+    gb_scene** out) {
     if (!json || !out) return gb::failWith(GB_ERR_INVALID, "null argument");
     *out = nullptr;
+    int method = 0;
+    if (int rc = bvhMethodOf(options, &method)) return rc;
     try {
         gb_scene* s = new gb_scene();
         std::string err;
         std::string dir = scene_dir ? scene_dir : ".";
-        int rc = gb::loadSceneString(json, dir, dir + "/goblin.exr", s, &err);
+        int rc = gb::loadSceneString(json, dir, dir + "/goblin.exr", s, &err, method);
         if (rc != GB_OK) {
             delete s;
             return gb::failWith(rc, err);
@@ -70,7 +87,13 @@ int gb_scene_get_desc(const gb_scene* scene, gb_scene_desc* out) {
 const char* gb_scene_output_path(const gb_scene* scene) { return scene ? scene->outputPath.c_str() : ""; }
 
 int gb_bvh_build(const float* aabbs, uint32_t n, gb_bvh_node* nodes, uint32_t* n_nodes, uint32_t* order) {
+    return gb_bvh_build_method(aabbs, n, GB_BVH_EQUAL_COUNT, nodes, n_nodes, order);
+}
+
+int gb_bvh_build_method(const float* aabbs, uint32_t n, int method, gb_bvh_node* nodes, uint32_t* n_nodes,
+    uint32_t* order) {
     if ((n && (!aabbs || !nodes || !order)) || !n_nodes) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (method < GB_BVH_EQUAL_COUNT || method > GB_BVH_SAH) return gb::failWith(GB_ERR_INVALID, "unknown bvh method");
     try {
         std::vector<gb::BBox> boxes(n);
         for (uint32_t i = 0; i < n; ++i) {
@@ -78,7 +101,7 @@ int gb_bvh_build(const float* aabbs, uint32_t n, gb_bvh_node* nodes, uint32_t* n
             boxes[i].pMax = gb::Vec3(aabbs[6 * i + 3], aabbs[6 * i + 4], aabbs[6 * i + 5]);
         }
         gb::BuiltBVH bvh;
-        gb::buildBVH(boxes, &bvh);
+        gb::buildBVH(boxes, &bvh, (gb::BvhMethod)method);
         *n_nodes = (uint32_t)bvh.nodes.size();
         if (!bvh.nodes.empty()) std::memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(gb_bvh_node));
         if (n) std::memcpy(order, bvh.order.data(), n * sizeof(uint32_t));

@@ -7,6 +7,9 @@
 //   --gpus N                   shard the per-pixel samples over N GPUs
 //   --seed S  --out FILE       Philox seed, output image (.exr .pfm .ppm)
 //   --stats                    print Msamples/s and Mrays/s as a JSON line
+//   --accel equal_count|middle|sah
+//                              BVH split method: equal_count (default) is the reference's tree,
+//                              sah the non-parity fast tree (same image in distribution)
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -22,7 +25,7 @@ int main(int argc, char** argv) {
     }
     int gpus = 1, spp = 0, depth = 0;
     unsigned long long seed = 1;
-    std::string method, outFile;
+    std::string method, outFile, accel = "equal_count";
     bool stats = false;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
@@ -34,12 +37,20 @@ int main(int argc, char** argv) {
         else if (a == "--method") method = next();
         else if (a == "--out") outFile = next();
         else if (a == "--stats") stats = true;
+        else if (a == "--accel") accel = next();
         else {
-            std::cout << "Usage: g_ray scene.json [--method m] [--spp n] [--depth n] [--gpus n] [--seed s] [--out file] [--stats]" << std::endl;
+            std::cout << "Usage: g_ray scene.json [--method m] [--spp n] [--depth n] [--gpus n] [--seed s] [--out file] [--stats] [--accel equal_count|middle|sah]" << std::endl;
             return 0;
         }
     }
-    std::unique_ptr<gb::RenderContext> renderContext(gb::ContextLoader::load(argv[1], gpus, seed));
+    int bvhMethod = GB_BVH_EQUAL_COUNT;
+    if (accel == "middle") bvhMethod = GB_BVH_MIDDLE;
+    else if (accel == "sah") bvhMethod = GB_BVH_SAH;
+    else if (accel != "equal_count") {
+        std::cerr << "g_ray: --accel must be equal_count, middle or sah" << std::endl;
+        return 1;
+    }
+    std::unique_ptr<gb::RenderContext> renderContext(gb::ContextLoader::load(argv[1], gpus, seed, bvhMethod));
     if (renderContext) {
         gb_render_setting& rs = renderContext->mScene->desc().setting;
         if (method == "path_tracing") rs.method = GB_METHOD_PATH_TRACING;

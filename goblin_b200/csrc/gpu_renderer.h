@@ -161,9 +161,13 @@ public:
 class ContextLoader {
 public:
     // returns nullptr on an unreadable / ill-formed scene, like the reference
-    static RenderContext* load(const std::string& filename, int gpuNum = 1, unsigned long long seed = 1) {
+    // bvhMethod: GB_BVH_EQUAL_COUNT = the reference's tree; GB_BVH_SAH = the non-parity fast tree
+    static RenderContext* load(const std::string& filename, int gpuNum = 1, unsigned long long seed = 1,
+        int bvhMethod = GB_BVH_EQUAL_COUNT) {
         gb_scene* s = nullptr;
-        if (gb_scene_load_json(filename.c_str(), &s) != GB_OK) {
+        gb_load_options opt{};
+        opt.bvh_method = bvhMethod;
+        if (gb_scene_load_json_ex(filename.c_str(), &opt, &s) != GB_OK) {
             std::fprintf(stderr, "%s\n", gb_last_error());
             return nullptr;
         }

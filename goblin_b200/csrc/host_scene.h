@@ -27,6 +27,7 @@ struct gb_scene {
     gb_film_desc film{};
     gb_render_setting setting{};
     int threadNum = 0;
+    int bvhMethod = 0;      // GB_BVH_* every BVH of this scene was built with
     int topDepth = 0;       // deepest level of the top-level BVH
     int modelDepth = 0;     // deepest level over all per-model BVHs
     std::string outputPath; // film "file" or <scene>.exr
@@ -38,8 +39,8 @@ struct gb_scene {
 namespace gb {
 
 // Loads and flattens a scene; returns a GB_* status and sets *error.
-int loadSceneFile(const std::string& path, gb_scene* out, std::string* error);
+int loadSceneFile(const std::string& path, gb_scene* out, std::string* error, int bvhMethod = 0);
 int loadSceneString(const std::string& json, const std::string& sceneDir,
-    const std::string& defaultOutput, gb_scene* out, std::string* error);
+    const std::string& defaultOutput, gb_scene* out, std::string* error, int bvhMethod = 0);
 
 } // namespace gb

@@ -205,7 +205,7 @@ struct Loader {
             boxes[t] = b;
         }
         BuiltBVH bvh;
-        buildBVH(boxes, &bvh);
+        buildBVH(boxes, &bvh, (BvhMethod)out->bvhMethod);
         g.nodeOffset = (uint32_t)out->modelNodes.size();
         g.nodeCount = (uint32_t)bvh.nodes.size();
         out->modelNodes.insert(out->modelNodes.end(), bvh.nodes.begin(), bvh.nodes.end());
@@ -650,7 +650,7 @@ struct Loader {
             boxes.push_back(wb);
         }
         BuiltBVH top;
-        buildBVH(boxes, &top); // Scene::mBVH
+        buildBVH(boxes, &top, (BvhMethod)out->bvhMethod); // Scene::mBVH
         out->topNodes = top.nodes;
         out->topOrder = top.order;
         out->topDepth = top.maxDepth;
@@ -707,7 +707,7 @@ struct Loader {
 } // namespace
 
 int loadSceneString(const std::string& json, const std::string& sceneDir,
-    const std::string& defaultOutput, gb_scene* out, std::string* error) {
+    const std::string& defaultOutput, gb_scene* out, std::string* error, int bvhMethod) {
     JsonValue root;
     std::string perr;
     if (!parseJson(json, &root, &perr)) {
@@ -719,6 +719,7 @@ int loadSceneString(const std::string& json, const std::string& sceneDir,
         return GB_ERR_INVALID;
     }
     *out = gb_scene();
+    out->bvhMethod = bvhMethod;
     Loader L;
     L.sceneDir = sceneDir;
     L.out = out;
@@ -733,7 +734,7 @@ int loadSceneString(const std::string& json, const std::string& sceneDir,
     return GB_OK;
 }
 
-int loadSceneFile(const std::string& filename, gb_scene* out, std::string* error) {
+int loadSceneFile(const std::string& filename, gb_scene* out, std::string* error, int bvhMethod) {
     std::ifstream in(filename, std::ios::binary);
     if (!in.is_open()) {
         if (error) *error = "error reading scene file: " + filename;
@@ -757,7 +758,7 @@ int loadSceneFile(const std::string& filename, gb_scene* out, std::string* error
     } else {
         defaultOutput = filename + ".exr";
     }
-    return loadSceneString(ss.str(), sceneDir, defaultOutput, out, error);
+    return loadSceneString(ss.str(), sceneDir, defaultOutput, out, error, bvhMethod);
 }
 
 } // namespace gb

@@ -70,6 +70,13 @@ enum { GB_MAT_LAMBERT = 0, GB_MAT_MIRROR = 1, GB_MAT_TRANSPARENT = 2, GB_MAT_BLI
 enum { GB_FRESNEL_DIELECTRIC = 0, GB_FRESNEL_CONDUCTOR = 1 };
 enum { GB_LIGHT_POINT = 0, GB_LIGHT_DIRECTIONAL = 1, GB_LIGHT_SPOT = 2, GB_LIGHT_AREA = 3 };
 enum { GB_METHOD_PATH_TRACING = 0, GB_METHOD_AO = 1 };
+/* BVH split methods.  EQUAL_COUNT is what every BVH of the reference is built
+ * with (src/GoblinModel.cpp:24, src/GoblinScene.cpp:15) and the only parity
+ * mode; MIDDLE is the reference's other, unused method
+ * (src/GoblinBVH.cpp:124-134); SAH is this library's non-parity "fast" tree
+ * (binned surface-area heuristic, same node format, same kernels): closest-hit
+ * distances are unchanged, hit ids can differ where two primitives tie. */
+enum { GB_BVH_EQUAL_COUNT = 0, GB_BVH_MIDDLE = 1, GB_BVH_SAH = 2 };
 
 /* Model = geometry + material (+ area light) (src/GoblinModel.cpp:10-26).
  * Mesh models own a private BVH over their triangles; the node / order /
@@ -234,6 +241,14 @@ typedef struct gb_context gb_context; /* one GPU                              */
 int gb_scene_load_json(const char* path, gb_scene** out);
 /* The same from a JSON string; mesh paths resolve against scene_dir. */
 int gb_scene_load_json_string(const char* json, const char* scene_dir, gb_scene** out);
+/* Loader options; zero-initialise for the reference's behaviour. */
+typedef struct gb_load_options {
+    int32_t bvh_method;    /* GB_BVH_* for the top-level and every per-model BVH */
+    int32_t reserved[7];
+} gb_load_options;
+int gb_scene_load_json_ex(const char* path, const gb_load_options* options, gb_scene** out);
+int gb_scene_load_json_string_ex(const char* json, const char* scene_dir, const gb_load_options* options,
+                                 gb_scene** out);
 void gb_scene_destroy(gb_scene* scene);
 int gb_scene_get_desc(const gb_scene* scene, gb_scene_desc* out);
 /* film output path chosen by the loader (film "file" or <scene>.exr) */
@@ -243,6 +258,9 @@ const char* gb_scene_output_path(const gb_scene* scene);
  * 2 * n entries, order n entries.  Returns the node count in *n_nodes. */
 int gb_bvh_build(const float* aabbs /* n x 6 */, uint32_t n, gb_bvh_node* nodes,
                  uint32_t* n_nodes, uint32_t* order);
+/* The same with an explicit GB_BVH_* split method. */
+int gb_bvh_build_method(const float* aabbs /* n x 6 */, uint32_t n, int method, gb_bvh_node* nodes,
+                        uint32_t* n_nodes, uint32_t* order);
 
 /* --------------------------------------------------------------- device */
 
