@@ -60,7 +60,8 @@ class FilmDesc(C.Structure):
     _fields_ = [("xres", C.c_int32), ("yres", C.c_int32), ("xstart", C.c_int32), ("xcount", C.c_int32),
                 ("ystart", C.c_int32), ("ycount", C.c_int32), ("sx0", C.c_int32), ("sx1", C.c_int32),
                 ("sy0", C.c_int32), ("sy1", C.c_int32), ("filter_width", C.c_float * 2),
-                ("filter_table", C.c_float * 256)]
+                ("filter_table", C.c_float * 256), ("tone_mapping", C.c_int32), ("bloom_radius", C.c_float),
+                ("bloom_weight", C.c_float)]
 
 
 class RenderSetting(C.Structure):
@@ -120,7 +121,7 @@ EXPORTS = [
     "gb_scene_output_path", "gb_bvh_build", "gb_bvh_build_method", "gb_device_count", "gb_create", "gb_destroy",
     "gb_upload_scene", "gb_trace_closest", "gb_trace_any", "gb_trace_closest_device",
     "gb_trace_any_device", "gb_camera_rays", "gb_li", "gb_render", "gb_film_clear",
-    "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image",
+    "gb_film_download", "gb_film_upload", "gb_film_device_ptr", "gb_film_write", "gb_write_image", "gb_film_resolve", "gb_write_rgb",
     "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
     "gb_last_kernel_ms", "gb_last_error", "gb_version", "gb_enable_kernel_timing", "gb_get_kernel_times",
     "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning", "gb_upload_bytes",
@@ -175,6 +176,8 @@ def lib():
         l.gb_film_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         l.gb_film_write.argtypes = [C.c_void_p, C.c_char_p]
         l.gb_write_image.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+        l.gb_film_resolve.argtypes = [C.c_void_p, C.c_void_p]
+        l.gb_write_rgb.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         l.gb_synchronize.argtypes = [C.c_void_p]
         l.gb_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.gb_enable_counters.argtypes = [C.c_void_p, C.c_int]
@@ -388,6 +391,14 @@ class Context:
     def film_write(self, path):
         check(lib().gb_film_write(self._h, os.fsencode(path)))
 
+    def film_resolve(self):
+        """colour / weight + the film's bloom, on the device: what Film::writeImage hands to
+        Goblin::writeImage (yres x xres x 3)."""
+        f = self.scene.desc.film
+        out = np.zeros((f.yres, f.xres, 3), dtype=np.float32)
+        check(lib().gb_film_resolve(self._h, out.ctypes.data))
+        return out
+
     def synchronize(self):
         check(lib().gb_synchronize(self._h))
 
@@ -441,6 +452,11 @@ def device_count():
     n = C.c_int()
     check(lib().gb_device_count(C.byref(n)))
     return n.value
+
+
+def write_rgb(path, rgb, tone_mapping=False):
+    rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+    check(lib().gb_write_rgb(os.fsencode(path), rgb.ctypes.data, rgb.shape[1], rgb.shape[0], int(tone_mapping)))
 
 
 def write_image(path, rgbw):

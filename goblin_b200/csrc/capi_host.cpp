@@ -118,4 +118,11 @@ int gb_write_image(const char* path, const float* rgbw, int xres, int yres) {
     return GB_OK;
 }
 
+int gb_write_rgb(const char* path, const float* rgb, int xres, int yres, int tone_mapping) {
+    if (!path || !rgb || xres <= 0 || yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad argument");
+    std::string err;
+    if (!gb::writeRgb(path, rgb, xres, yres, tone_mapping != 0, &err)) return gb::failWith(GB_ERR_IO, err);
+    return GB_OK;
+}
+
 } // extern "C"

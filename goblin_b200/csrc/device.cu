@@ -584,6 +584,51 @@ k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* fi
     }
 }
 
+// ------------------------------------------------------------ image post-processing
+// Film::writeImage's normalisation: Color::operator/(float) = multiply by 1 / weight.
+__global__ void k_resolve(const float4* __restrict__ film, unsigned int n, float* __restrict__ rgb) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = film[i];
+    const float inv = 1.0f / p.w;
+    rgb[3 * i] = p.x * inv;
+    rgb[3 * i + 1] = p.y * inv;
+    rgb[3 * i + 2] = p.z * inv;
+}
+
+// Goblin::bloom (src/GoblinImageIO.cpp:169-218): every pixel gathers its (2 fw - 1)^2 neighbourhood
+// (itself excluded) with the radial weight table, in the reference's row-major order so that the
+// float sums are the reference's bit for bit, then blends.  One thread per pixel; a warp covers 32
+// consecutive x, so each tap is one coalesced row segment served from L1 / L2.
+__global__ void k_bloom(const float* __restrict__ in, float* __restrict__ out, int w, int h, int fw,
+    const float* __restrict__ table, float bloomWeight) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int x0 = max(0, x - fw + 1), x1 = min(x + fw - 1, w - 1);
+    const int y0 = max(0, y - fw + 1), y1 = min(y + fw - 1, h - 1);
+    float r = 0.0f, g = 0.0f, b = 0.0f, weightSum = 0.0f;
+    for (int py = y0; py <= y1; ++py) {
+        const int fy = abs(py - y);
+        for (int px = x0; px <= x1; ++px) {
+            const int fx = abs(px - x);
+            if (fx == 0 && fy == 0) continue;
+            const float wgt = __ldg(table + fy * fw + fx);
+            const float* c = in + 3 * ((size_t)py * w + px);
+            r += c[0] * wgt;
+            g += c[1] * wgt;
+            b += c[2] * wgt;
+            weightSum += wgt;
+        }
+    }
+    const float inv = 1.0f / weightSum; // Color::operator/=(float)
+    r *= inv; g *= inv; b *= inv;
+    const size_t i = 3 * ((size_t)y * w + x);
+    const float keep = 1.0f - bloomWeight;
+    out[i] = in[i] * keep + r * bloomWeight;
+    out[i + 1] = in[i + 1] * keep + g * bloomWeight;
+    out[i + 2] = in[i + 2] * keep + b * bloomWeight;
+}
+
 __global__ void k_copy_L(PathState ps, unsigned int n, float* out) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -626,6 +671,7 @@ struct gb_context {
     int stackEntries = 0; // per-thread traversal stack entries this scene needs
     float4* film = nullptr;
     size_t filmPixels = 0;
+    gb_film_desc filmDesc{};
     // wavefront buffers
     size_t capacity = 0;
     PathState ps{};
@@ -1199,6 +1245,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         GB_CUDA(cudaMalloc((void**)&ctx->film, filmPixels * sizeof(float4)));
         ctx->filmPixels = filmPixels;
     }
+    ctx->filmDesc = d->film;
     GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
     GB_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging arena may be refilled after this
     ctx->sc = sc;
@@ -1564,14 +1611,52 @@ int gb_film_device_ptr(gb_context* ctx, void** ptr, size_t* n_floats) {
     return GB_OK;
 }
 
+int gb_film_resolve(gb_context* ctx, float* rgb) {
+    if (!ctx || !rgb) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
+    GB_CUDA(cudaSetDevice(ctx->device));
+    const int w = ctx->sc.xres, h = ctx->sc.yres;
+    const size_t n = ctx->filmPixels;
+    const gb_film_desc& fd = ctx->filmDesc;
+    const bool doBloom = fd.bloom_radius > 0.0f && fd.bloom_weight > 0.0f; // Film::writeImage, GoblinFilm.cpp:187-189
+    const int fw = doBloom ? gb::bloomFilterWidth(fd.bloom_radius, w, h) : 0;
+    float *d_rgb = nullptr, *d_out = nullptr, *d_tab = nullptr;
+    GB_CUDA(cudaMalloc((void**)&d_rgb, n * 3 * sizeof(float)));
+    auto release = [&]() { cudaFree(d_rgb); cudaFree(d_out); cudaFree(d_tab); };
+    k_resolve<<<(unsigned int)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->film, (unsigned int)n, d_rgb);
+    ctx->launches++;
+    const float* result = d_rgb;
+    if (doBloom) {
+        // fw == 0 (a radius below two pixels) divides 0 by 0 in the reference's table: NaN everywhere;
+        // the same arithmetic runs here
+        std::vector<float> table((size_t)std::max(fw, 1) * std::max(fw, 1), 0.0f);
+        gb::bloomFilterTable(fw, table.data());
+        cudaError_t e = cudaMalloc((void**)&d_out, n * 3 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_tab, table.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_tab, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { release(); return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e)); }
+        dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+        k_bloom<<<grd, blk, 0, ctx->stream>>>(d_rgb, d_out, w, h, fw, d_tab, fd.bloom_weight);
+        ctx->launches++;
+        result = d_out;
+    }
+    cudaError_t e = cudaMemcpyAsync(rgb, result, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    release();
+    if (e != cudaSuccess) return gb::failWith(GB_ERR_CUDA, cudaGetErrorString(e));
+    return GB_OK;
+}
+
 int gb_film_write(gb_context* ctx, const char* path) {
     if (!ctx || !path) return gb::failWith(GB_ERR_INVALID, "null argument");
     if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
-    std::vector<float> host(ctx->filmPixels * 4);
-    int rc = gb_film_download(ctx, host.data());
+    std::vector<float> host(ctx->filmPixels * 3);
+    int rc = gb_film_resolve(ctx, host.data());
     if (rc != GB_OK) return rc;
     std::string err;
-    if (!gb::writeFilm(path, host.data(), ctx->sc.xres, ctx->sc.yres, &err)) return gb::failWith(GB_ERR_IO, err);
+    if (!gb::writeRgb(path, host.data(), ctx->sc.xres, ctx->sc.yres, ctx->filmDesc.tone_mapping != 0, &err)) {
+        return gb::failWith(GB_ERR_IO, err);
+    }
     return GB_OK;
 }
 

@@ -57,9 +57,12 @@ public:
     void merge(const std::vector<float>& rgbw) {
         for (size_t i = 0; i < mPixels.size(); ++i) mPixels[i] += rgbw[i];
     }
-    void writeImage() {
+    // Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, bloom, then the writer
+    // (tone mapping for .ppm).  The resolve and the bloom run on `ctx`'s GPU over the merged film.
+    void writeImage(gb_context* ctx) {
         std::printf("write image to : %s\n", mFilename.c_str());
-        checkRc(gb_write_image(mFilename.c_str(), mPixels.data(), mDesc.xres, mDesc.yres), "writeImage");
+        checkRc(gb_film_upload(ctx, mPixels.data()), "gb_film_upload");
+        checkRc(gb_film_write(ctx, mFilename.c_str()), "writeImage");
     }
     const std::vector<float>& pixels() const { return mPixels; }
     void setFilename(const std::string& f) { mFilename = f; }
@@ -134,7 +137,7 @@ public:
             mStats.raysAny += c.rays_any;
             mStats.launches += c.kernel_launches;
         }
-        film->writeImage();
+        film->writeImage(mContexts[0]);
     }
     const RenderStats& stats() const { return mStats; }
     int gpuNum() const { return mGpuNum; }

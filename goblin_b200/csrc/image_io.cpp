@@ -1,5 +1,6 @@
 #include "image_io.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -137,7 +138,53 @@ bool writePPM(const std::string& path, const std::vector<float>& rgb, int w, int
     return true;
 }
 
+
+// Goblin::toneMapping (src/GoblinImageIO.cpp:220-237): Reinhard's global operator around the
+// log-average "world adaptation" luminance.  Serial float sums and the host libm, like the
+// reference, so the result is the same bit for bit.
+void toneMap(std::vector<float>& rgb, int w, int h) {
+    auto lum = [&](size_t i) { return 0.212671f * rgb[3 * i] + 0.715160f * rgb[3 * i + 1] + 0.072169f * rgb[3 * i + 2]; };
+    float Ywa = 0.0f;
+    for (size_t i = 0; i < (size_t)w * h; ++i) Ywa += logf(1e4f + lum(i));
+    Ywa = expf(Ywa / (w * h));
+    const float invy2 = 1.0f / (Ywa * Ywa);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        const float y = lum(i);
+        const float s = (1.0f + y * invy2) / (1.0f + y);
+        rgb[3 * i] *= s;
+        rgb[3 * i + 1] *= s;
+        rgb[3 * i + 2] *= s;
+    }
+}
+
 } // namespace
+
+int bloomFilterWidth(float bloomRadius, int xres, int yres) {
+    // ceilInt(bloomRadius * std::max(width, height)) / 2, integer division
+    return (int)ceilf(bloomRadius * (float)(xres > yres ? xres : yres)) / 2;
+}
+
+void bloomFilterTable(int filterWidth, float* table) {
+    for (int y = 0; y < filterWidth; ++y) {
+        for (int x = 0; x < filterWidth; ++x) {
+            float d = sqrtf((float)(x * x + y * y)) / (float)filterWidth;
+            table[y * filterWidth + x] = powf(std::max(0.0f, 1.0f - d), 4.0f);
+        }
+    }
+}
+
+bool writeRgb(const std::string& path, const float* rgbIn, int xres, int yres, bool toneMapping, std::string* error) {
+    std::vector<float> rgb(rgbIn, rgbIn + (size_t)xres * yres * 3);
+    size_t dot = path.rfind('.');
+    std::string ext = dot == std::string::npos ? "" : path.substr(dot);
+    if (ext == ".exr" || ext == ".EXR") return writeEXR(path, rgb, xres, yres, error);
+    if (ext == ".pfm" || ext == ".PFM") return writePFM(path, rgb, xres, yres, error);
+    if (ext == ".ppm" || ext == ".PPM") {
+        if (toneMapping) toneMap(rgb, xres, yres);
+        return writePPM(path, rgb, xres, yres, error);
+    }
+    return writePPM(path + ".ppm", rgb, xres, yres, error); // the reference's fallback (no tone mapping there)
+}
 
 bool writeFilm(const std::string& path, const float* rgbw, int xres, int yres, std::string* error) {
     std::vector<float> rgb((size_t)xres * yres * 3);
@@ -147,12 +194,7 @@ bool writeFilm(const std::string& path, const float* rgbw, int xres, int yres, s
         rgb[3 * i + 1] = rgbw[4 * i + 1] * inv;
         rgb[3 * i + 2] = rgbw[4 * i + 2] * inv;
     }
-    size_t dot = path.rfind('.');
-    std::string ext = dot == std::string::npos ? "" : path.substr(dot);
-    if (ext == ".exr" || ext == ".EXR") return writeEXR(path, rgb, xres, yres, error);
-    if (ext == ".pfm" || ext == ".PFM") return writePFM(path, rgb, xres, yres, error);
-    if (ext == ".ppm" || ext == ".PPM") return writePPM(path, rgb, xres, yres, error);
-    return writePPM(path + ".ppm", rgb, xres, yres, error); // the reference's fallback
+    return writeRgb(path, rgb.data(), xres, yres, false, error);
 }
 
 } // namespace gb

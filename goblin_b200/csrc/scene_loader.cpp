@@ -372,6 +372,9 @@ struct Loader {
         film.xcount = std::max(1, (int)ceil(film.xres * crop.y) - film.xstart);
         film.ystart = (int)ceil(film.yres * crop.z);
         film.ycount = std::max(1, (int)ceil(film.yres * crop.w) - film.ystart);
+        film.tone_mapping = fp.getBool("tone_mapping") ? 1 : 0; // createImageFilm, GoblinFilm.cpp:207-209
+        film.bloom_radius = fp.getFloat("bloom_radius");
+        film.bloom_weight = fp.getFloat("bloom_weight");
         buildFilter(*cc);
         float xw = film.filter_width[0], yw = film.filter_width[1];
         film.sx0 = (int)floor(film.xstart + 0.5f - xw); // Film::getSampleRange

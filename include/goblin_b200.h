@@ -153,6 +153,10 @@ typedef struct gb_film_desc {
     int32_t sx0, sx1, sy0, sy1;               /* Film::getSampleRange          */
     float filter_width[2];
     float filter_table[256];                  /* FilterTable, 16 x 16          */
+    /* Film::writeImage post-processing (src/GoblinFilm.cpp:164-192,203-212) */
+    int32_t tone_mapping;                     /* Reinhard, applied to .ppm only */
+    float bloom_radius;                       /* fraction of max(xres, yres)   */
+    float bloom_weight;
 } gb_film_desc;
 
 typedef struct gb_render_setting {
@@ -306,7 +310,16 @@ int gb_film_device_ptr(gb_context* ctx, void** ptr, size_t* n_floats);
 /* Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, written as
  * .exr (half, like src/GoblinImageIO.cpp:35-98), .pfm or .ppm by extension. */
 int gb_film_write(gb_context* ctx, const char* path);
+/* The image Film::writeImage hands to Goblin::writeImage: colour / weight, then
+ * Goblin::bloom (src/GoblinImageIO.cpp:169-218) when the film's bloom_radius
+ * and bloom_weight are positive -- both on the device.  rgb: yres x xres x 3. */
+int gb_film_resolve(gb_context* ctx, float* rgb);
+/* Host-only writers.  gb_write_image takes a raw film (colour / weight, no
+ * bloom); gb_write_rgb takes a resolved image and applies the reference's
+ * Reinhard tone mapping (src/GoblinImageIO.cpp:220-237) when asked and the
+ * target is a .ppm, like Goblin::writeImage (:146-167). */
 int gb_write_image(const char* path, const float* rgbw, int xres, int yres);
+int gb_write_rgb(const char* path, const float* rgb, int xres, int yres, int tone_mapping);
 
 int gb_synchronize(gb_context* ctx);
 int gb_stream(gb_context* ctx, void** cuda_stream);

@@ -12,6 +12,7 @@
  *   li      PathTracer::Li / AORenderer::Li on explicit sample values
  *   render  timed RenderContext::render() with Scene::intersect/occluded call
  *           counters (linker --wrap) and a raw float dump of the film
+ *   post    Goblin::bloom / Goblin::toneMapping / the PPM writer on a raw rgb image
  * Only this TU is compiled with -fno-access-control so it can read private
  * members; it observes the reference, it never reimplements it.
  *
@@ -35,6 +36,7 @@
 #include "GoblinAO.h"
 #include "GoblinRay.h"
 #include "GoblinThreadLocalStorage.h"
+#include "GoblinImageIO.h"
 
 #include <atomic>
 #include <chrono>
@@ -567,12 +569,42 @@ static void usage() {
         "       ref_tool camrays scene.json samples.f32 out.gbar\n"
         "       ref_tool trace   scene.json rays.f32 out.gbar\n"
         "       ref_tool li      scene.json samples.f32 out.gbar [--record]\n"
-        "       ref_tool render  scene.json film.gbar|- [--seed S] [--threads T] [--spp N]\n");
+        "       ref_tool render  scene.json film.gbar|- [--seed S] [--threads T] [--spp N]\n"
+        "       ref_tool post    in.f32 out.f32|out.ppm W H bloomRadius bloomWeight tone\n");
+}
+
+// post in.f32 out.f32|out.ppm W H bloomRadius bloomWeight tone: the reference's image
+// post-processing (src/GoblinImageIO.cpp:169-237) on W*H rgb floats; a .ppm output goes
+// through Goblin::writeImage (tone mapping there), anything else is the raw float result
+static int cmdPost(int argc, char** argv) {
+    if (argc < 9) return 1;
+    int w = atoi(argv[4]), h = atoi(argv[5]);
+    float radius = (float)atof(argv[6]), weight = (float)atof(argv[7]);
+    bool tone = atoi(argv[8]) != 0;
+    std::vector<float> in((size_t)w * h * 3);
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(in.data(), 4, in.size(), f) != in.size()) return 2;
+    fclose(f);
+    std::vector<Color> c((size_t)w * h);
+    for (size_t i = 0; i < c.size(); ++i) c[i] = Color(in[3 * i], in[3 * i + 1], in[3 * i + 2]);
+    if (radius > 0.0f && weight > 0.0f) bloom(c.data(), w, h, radius, weight); // Film::writeImage
+    std::string out = argv[3];
+    if (out.size() > 4 && out.substr(out.size() - 4) == ".ppm") {
+        return writeImage(out, c.data(), w, h, tone) ? 0 : 3;
+    }
+    if (tone) toneMapping(c.data(), w, h);
+    for (size_t i = 0; i < c.size(); ++i) { in[3 * i] = c[i].r; in[3 * i + 1] = c[i].g; in[3 * i + 2] = c[i].b; }
+    f = fopen(out.c_str(), "wb");
+    if (!f) return 3;
+    fwrite(in.data(), 4, in.size(), f);
+    fclose(f);
+    return 0;
 }
 
 int main(int argc, char** argv) {
     if (argc < 4) { usage(); return 1; }
     std::string cmd = argv[1];
+    if (cmd == "post") return cmdPost(argc, argv);
     // the loader echoes every parameter to stdout; silence it while loading
     std::streambuf* old = std::cout.rdbuf();
     std::ostringstream sink;

@@ -16,6 +16,7 @@ Outputs (all under tests/golden/):
     tiny_li_ao.npz        AORenderer::Li on explicit sample values
     tiny_film_pt.npz      converged reference film: mean and variance of the mean
     tiny_film_ao.npz
+    post.npz              Goblin::bloom / toneMapping / the PPM writer on a small HDR image
 """
 import json
 import os
@@ -139,6 +140,32 @@ def make_film(scene, batches, spp):
             "camera_samples": np.int64(info["camera_samples"])}
 
 
+def make_post(rng):
+    """The reference's image post-processing (ref_tool post) on a 40 x 28 HDR image with a few very
+    bright pixels: bloom alone, tone mapping alone, and the PPM text Goblin::writeImage produces
+    with and without tone mapping."""
+    w, h = 40, 28
+    img = rng.uniform(0.0, 1.5, (h, w, 3)).astype(np.float32)
+    hot = rng.uniform(size=(h, w)) < 0.03
+    img[hot] *= 60.0
+    out = {"rgb": img, "bloom_radius": np.float32(0.2), "bloom_weight": np.float32(0.3)}
+    with tempfile.TemporaryDirectory() as td:
+        inp = os.path.join(td, "in.f32")
+        img.tofile(inp)
+
+        def post(name, radius, weight, tone):
+            o = os.path.join(td, name)
+            run(REF, "post", inp, o, str(w), str(h), repr(radius), repr(weight), str(tone))
+            return o
+        out["bloom"] = np.fromfile(post("a.f32", 0.2, 0.3, 0), np.float32).reshape(h, w, 3)
+        out["bloom_wide"] = np.fromfile(post("w.f32", 2.5, 1.0, 0), np.float32).reshape(h, w, 3)
+        out["tone"] = np.fromfile(post("b.f32", 0.0, 0.0, 1), np.float32).reshape(h, w, 3)
+        out["ppm_plain"] = np.frombuffer(open(post("c.ppm", 0.0, 0.0, 0), "rb").read(), np.uint8)
+        out["ppm_tone"] = np.frombuffer(open(post("d.ppm", 0.0, 0.0, 1), "rb").read(), np.uint8)
+        out["ppm_bloom_tone"] = np.frombuffer(open(post("e.ppm", 0.2, 0.3, 1), "rb").read(), np.uint8)
+    return out
+
+
 def main():
     assert os.path.exists(REF), "build the reference oracle first: make -C oracle ref"
     tiny = os.path.join(OUT, "tiny")
@@ -148,6 +175,9 @@ def main():
     ref("dump", pt, os.path.join(OUT, "tiny_dump.gbar"))
     dump = gbar.load(os.path.join(OUT, "tiny_dump.gbar"))
     rng = np.random.default_rng(20261018)
+    if "--post-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "post.npz"), **make_post(np.random.default_rng(77)))
+        return
     if "--films-only" in sys.argv:
         np.savez_compressed(os.path.join(OUT, "tiny_film_pt.npz"), **make_film(pt, 24, 256))
         np.savez_compressed(os.path.join(OUT, "tiny_film_ao.npz"), **make_film(ao, 16, 64))
@@ -159,6 +189,7 @@ def main():
     # estimated from the batches, and the two-sample t-test in tests/ needs it to be stable
     np.savez_compressed(os.path.join(OUT, "tiny_film_pt.npz"), **make_film(pt, 24, 256))
     np.savez_compressed(os.path.join(OUT, "tiny_film_ao.npz"), **make_film(ao, 16, 64))
+    np.savez_compressed(os.path.join(OUT, "post.npz"), **make_post(np.random.default_rng(77)))
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         if os.path.isfile(p):

@@ -92,3 +92,71 @@ def test_zero_weight_pixels_and_bad_path(built, tmp_path):
     with pytest.raises(api.GoblinError) as e:
         api.write_image(str(tmp_path / "no_such_dir" / "a.exr"), rgbw)
     assert e.value.code == 2
+
+
+# ---- Film::writeImage post-processing: Goblin::bloom, Goblin::toneMapping (src/GoblinImageIO.cpp:169-237)
+# against tests/golden/post.npz, produced by the unmodified reference (ref_tool post).
+
+def _post_golden():
+    import os
+    from tests import util
+    return dict(np.load(os.path.join(util.GOLDEN, "post.npz")))
+
+
+def test_ppm_and_tone_mapping_match_the_reference_writer(built, tmp_path):
+    g = _post_golden()
+    p = str(tmp_path / "plain.ppm")
+    api.write_rgb(p, g["rgb"], tone_mapping=False)
+    assert open(p, "rb").read() == g["ppm_plain"].tobytes()
+    p = str(tmp_path / "tone.ppm")
+    api.write_rgb(p, g["rgb"], tone_mapping=True)
+    assert open(p, "rb").read() == g["ppm_tone"].tobytes()
+    # tone mapping is a .ppm-only step in Goblin::writeImage: the float formats ignore the flag
+    p = str(tmp_path / "tone.pfm")
+    api.write_rgb(p, g["rgb"], tone_mapping=True)
+    raw = np.frombuffer(open(p, "rb").read()[-g["rgb"].size * 4:], np.float32).reshape(g["rgb"].shape)[::-1]
+    assert np.array_equal(raw, g["rgb"])
+
+
+def _post_scene(radius, weight, tone):
+    import json
+    import os
+    from tests import util
+    g = _post_golden()
+    h, w, _ = g["rgb"].shape
+    js = json.load(open(util.TINY_PT))
+    js["camera"]["film"] = {"resolution": [float(w), float(h)], "tone_mapping": bool(tone),
+                            "bloom_radius": radius, "bloom_weight": weight}
+    return api.Scene(json_text=json.dumps(js), scene_dir=os.path.dirname(util.TINY_PT)), g
+
+
+def test_loader_reads_the_film_post_parameters(built):
+    scene, _ = _post_scene(0.2, 0.3, True)
+    f = scene.desc.film
+    assert (f.tone_mapping, f.bloom_radius, f.bloom_weight) == (1, np.float32(0.2), np.float32(0.3))
+    f = api.Scene(__import__("tests.util", fromlist=["x"]).TINY_PT).desc.film
+    assert (f.tone_mapping, f.bloom_radius, f.bloom_weight) == (0, 0.0, 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius,weight,key", [(0.2, 0.3, "bloom"), (2.5, 1.0, "bloom_wide"), (0.0, 0.0, "rgb")])
+def test_device_bloom_is_bit_exact(built, radius, weight, key):
+    scene, g = _post_scene(radius, weight, False)
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    rgbw = np.concatenate([g["rgb"], np.ones(g["rgb"].shape[:2] + (1,), np.float32)], 2)
+    ctx.film_upload(rgbw)
+    got = ctx.film_resolve()
+    assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_film_write_bloom_then_tone_mapped_ppm(built, tmp_path):
+    scene, g = _post_scene(0.2, 0.3, True)
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    rgbw = np.concatenate([g["rgb"], np.ones(g["rgb"].shape[:2] + (1,), np.float32)], 2)
+    ctx.film_upload(rgbw * np.float32(4.0))  # colour / weight: the weight 4 divides back out exactly
+    p = str(tmp_path / "out.ppm")
+    ctx.film_write(p)
+    assert open(p, "rb").read() == g["ppm_bloom_tone"].tobytes()
