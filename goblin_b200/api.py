@@ -39,7 +39,14 @@ class Instance(C.Structure):
 
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
-                ("k", C.c_float), ("exponent", C.c_float), ("fresnel", C.c_int32)]
+                ("k", C.c_float), ("exponent", C.c_float), ("fresnel", C.c_int32),
+                ("kd_tex", C.c_int32), ("kt_tex", C.c_int32), ("exponent_tex", C.c_int32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("type", C.c_int32), ("is_float", C.c_int32), ("value", C.c_float * 3),
+                ("child", C.c_int32 * 2), ("filter", C.c_int32), ("mapping", C.c_int32),
+                ("map_scale", C.c_float * 2), ("map_offset", C.c_float * 2), ("to_tex", C.c_float * 12)]
 
 
 class Light(C.Structure):
@@ -83,7 +90,7 @@ class SceneDesc(C.Structure):
                 ("light_tri_area", C.POINTER(C.c_float)), ("light_tri_cdf", C.POINTER(C.c_float)),
                 ("n_light_tri_area", C.c_uint32), ("n_light_tri_cdf", C.c_uint32),
                 ("world_bound", C.c_float * 6), ("camera", Camera), ("film", FilmDesc),
-                ("setting", RenderSetting)]
+                ("setting", RenderSetting), ("textures", C.POINTER(Texture)), ("n_textures", C.c_uint32)]
 
 
 class LoadOptions(C.Structure):

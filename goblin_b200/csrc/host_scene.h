@@ -19,6 +19,7 @@ struct gb_scene {
     std::vector<uint32_t> triIndex;
     std::vector<float> vertPos, vertNrm, vertUv;
     std::vector<gb_material> materials;
+    std::vector<gb_texture> textures;
     std::vector<gb_light> lights;
     std::vector<float> lightPower, lightCdf;
     std::vector<float> lightTriArea, lightTriCdf; // mesh emitters: per-face areas and their CDF

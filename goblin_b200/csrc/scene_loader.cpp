@@ -53,8 +53,8 @@ struct Loader {
 
     std::vector<Geometry> geometries;
     std::map<std::string, int> geometryByName;
-    std::map<std::string, Color3> colorTextures;
-    std::map<std::string, float> floatTextures;
+    std::map<std::string, int> colorTextures; // name -> index into out->textures
+    std::map<std::string, int> floatTextures;
     std::map<std::string, int> materialByName;
     std::vector<ModelDef> models;
     std::map<std::string, PrimitiveDef> primitiveByName;
@@ -83,21 +83,54 @@ struct Loader {
         m.kd[0] = kd.r; m.kd[1] = kd.g; m.kd[2] = kd.b;
         return m;
     }
-    float getFloatTexture(const std::string& name) const {
+    // SceneCache::getFloatTexture / getColorTexture (src/GoblinScene.cpp:197-216): index of the named
+    // texture, the "error" entry (0.5 / magenta) when it was never defined
+    int floatTextureIndex(const std::string& name) const {
         auto it = floatTextures.find(name);
         if (it == floatTextures.end()) {
             std::cerr << "Texture " << name << " not defined!\n";
-            return 0.5f; // the "error" float texture, src/GoblinScene.cpp:116-117
+            return floatTextures.find("error")->second;
         }
         return it->second;
     }
-    Color3 getColorTexture(const std::string& name) const {
+    int colorTextureIndex(const std::string& name) const {
         auto it = colorTextures.find(name);
         if (it == colorTextures.end()) {
             std::cerr << "Texture " << name << " not defined!\n";
             return colorTextures.find("error")->second;
         }
         return it->second;
+    }
+    int addTexture(const gb_texture& t) {
+        out->textures.push_back(t);
+        return (int)out->textures.size() - 1;
+    }
+    static gb_texture constantTexture(bool isFloat, float a, float b = 0.0f, float c = 0.0f) {
+        gb_texture t{};
+        t.type = GB_TEX_CONSTANT;
+        t.is_float = isFloat ? 1 : 0;
+        t.value[0] = a; t.value[1] = b; t.value[2] = c;
+        t.child[0] = t.child[1] = -1;
+        return t;
+    }
+    // A material slot: the constant folded in, or a reference (1 + index) to a procedural texture.
+    struct ColorSlot { Color3 c; int tex = 0; };
+    ColorSlot getColorTexture(const std::string& name) const {
+        const int i = colorTextureIndex(name);
+        const gb_texture& t = out->textures[i];
+        ColorSlot s;
+        if (t.type == GB_TEX_CONSTANT) s.c = Color3{t.value[0], t.value[1], t.value[2]};
+        else s.tex = i + 1;
+        return s;
+    }
+    struct FloatSlot { float v = 0.0f; int tex = 0; };
+    FloatSlot getFloatTexture(const std::string& name) const {
+        const int i = floatTextureIndex(name);
+        const gb_texture& t = out->textures[i];
+        FloatSlot s;
+        if (t.type == GB_TEX_CONSTANT) s.v = t.value[0];
+        else s.tex = i + 1;
+        return s;
     }
     int getMaterial(const std::string& name) const {
         auto it = materialByName.find(name);
@@ -169,7 +202,8 @@ struct Loader {
 
     void initDefault() { // SceneCache::initDefault
         Color3 magenta{1.0f, 0.0f, 1.0f};
-        colorTextures["error"] = magenta;
+        colorTextures["error"] = addTexture(constantTexture(false, 1.0f, 0.0f, 1.0f));
+        floatTextures["error"] = addTexture(constantTexture(true, 0.5f));
         int errMat = addMaterial("error", lambert(magenta));
         int errGeo = addSphere(1.0f);
         geometryByName["error"] = errGeo;
@@ -414,33 +448,68 @@ struct Loader {
         return true;
     }
 
+    // getTextureMapping, src/GoblinTexture.cpp:600-615
+    void readMapping(const ParamSet& p, gb_texture* t) {
+        std::string type = p.getString("mapping", "uv");
+        t->mapping = GB_MAPPING_UV;
+        t->map_scale[0] = t->map_scale[1] = 1.0f;
+        t->map_offset[0] = t->map_offset[1] = 0.0f;
+        if (type == "uv") {
+            Vec2 one; one.x = 1.0f; one.y = 1.0f;
+            Vec2 zero; zero.x = 0.0f; zero.y = 0.0f;
+            Vec2 sc = p.getVector2("scale", one), of = p.getVector2("offset", zero);
+            t->map_scale[0] = sc.x; t->map_scale[1] = sc.y;
+            t->map_offset[0] = of.x; t->map_offset[1] = of.y;
+        } else if (type == "spherical") {
+            t->mapping = GB_MAPPING_SPHERICAL;
+            Transform toTex = getTransform(p);
+            store3x4(toTex.matrix, t->to_tex); // SphericalMapping::pointToST applies mToTex.onPoint
+        } else {
+            std::cerr << "undefined mapping type " << type << std::endl;
+        }
+    }
+
+    // createTextures, src/GoblinContextLoader.cpp:246-303: file order, children resolved by name at
+    // creation (so only earlier textures are visible), first definition of a name wins
     bool createTextures(const JsonValue& root) {
         const JsonValue* list = root.find("textures");
         if (!list || !list->isArray()) return true;
-        for (const JsonValue& t : list->arr) {
-            ParamSet p(t);
+        for (const JsonValue& tj : list->arr) {
+            ParamSet p(tj);
             std::string type = p.getString("type"), name = p.getString("name");
             std::string format = p.getString("format", "color");
-            if (format == "float") { // the Blinn exponent reads these (createFloatConstantTexture)
-                if (type == "checkerboard" || type == "scale" || type == "image") {
-                    err = "texture '" + name + "' of type '" + type + "' is outside the accelerated path "
-                        "(constant textures only)";
-                    return false;
-                }
-                addFirst(floatTextures, name, p.getFloat("float", 0.5f));
-                continue;
-            }
-            if (format != "color") {
+            if (format != "float" && format != "color") {
                 std::cerr << "unrecognize texture format" << format << std::endl;
                 continue;
             }
-            if (type == "checkerboard" || type == "scale" || type == "image") {
-                err = "texture '" + name + "' of type '" + type + "' is outside the accelerated path "
-                    "(constant textures only)";
+            const bool isFloat = format == "float";
+            if (type == "image") {
+                err = "texture '" + name + "' of type 'image' is outside the accelerated path "
+                    "(constant, checkerboard and scale textures only)";
                 return false;
             }
-            Vec3 c = p.getVector3("color");
-            addFirst(colorTextures, name, Color3{c.x, c.y, c.z});
+            gb_texture t{};
+            if (type == "checkerboard") { // createFloat/ColorCheckerboardTexture
+                t.type = GB_TEX_CHECKERBOARD;
+                t.is_float = isFloat ? 1 : 0;
+                readMapping(p, &t);
+                t.child[0] = isFloat ? floatTextureIndex(p.getString("texture1")) : colorTextureIndex(p.getString("texture1"));
+                t.child[1] = isFloat ? floatTextureIndex(p.getString("texture2")) : colorTextureIndex(p.getString("texture2"));
+                t.filter = p.getBool("filter", false) ? 1 : 0;
+            } else if (type == "scale") { // createFloat/ColorScaleTexture: the scale is looked up first
+                t.type = GB_TEX_SCALE;
+                t.is_float = isFloat ? 1 : 0;
+                std::string textureName = p.getString("texture"), scaleName = p.getString("scale");
+                t.child[1] = floatTextureIndex(scaleName);
+                t.child[0] = isFloat ? floatTextureIndex(textureName) : colorTextureIndex(textureName);
+            } else if (isFloat) { // "constant" and the fallback
+                t = constantTexture(true, p.getFloat("float", 0.5f));
+            } else {
+                Vec3 c = p.getVector3("color");
+                t = constantTexture(false, c.x, c.y, c.z);
+            }
+            const int id = addTexture(t);
+            addFirst(isFloat ? floatTextures : colorTextures, name, id);
         }
         return true;
     }
@@ -458,9 +527,12 @@ struct Loader {
             gb_material m{};
             if (type == "blinn") { // createBlinnMaterial, src/GoblinMaterial.cpp:834-854
                 m.type = GB_MAT_BLINN;
-                Color3 kg = getColorTexture(p.getString("Kg"));
-                m.kd[0] = kg.r; m.kd[1] = kg.g; m.kd[2] = kg.b;
-                m.exponent = getFloatTexture(p.getString("exponent"));
+                ColorSlot kg = getColorTexture(p.getString("Kg"));
+                m.kd[0] = kg.c.r; m.kd[1] = kg.c.g; m.kd[2] = kg.c.b;
+                m.kd_tex = kg.tex;
+                FloatSlot ex = getFloatTexture(p.getString("exponent"));
+                m.exponent = ex.v;
+                m.exponent_tex = ex.tex;
                 m.eta = p.getFloat("index", 1.5f);
                 m.k = p.getFloat("k", -1.0f);
                 m.fresnel = m.k > 0.0f ? GB_FRESNEL_CONDUCTOR : GB_FRESNEL_DIELECTRIC;
@@ -469,18 +541,23 @@ struct Loader {
                 return false;
             } else if (type == "transparent") {
                 m.type = GB_MAT_TRANSPARENT;
-                Color3 kr = getColorTexture(p.getString("Kr")), kt = getColorTexture(p.getString("Kt"));
-                m.kd[0] = kr.r; m.kd[1] = kr.g; m.kd[2] = kr.b;
-                m.kt[0] = kt.r; m.kt[1] = kt.g; m.kt[2] = kt.b;
+                ColorSlot kr = getColorTexture(p.getString("Kr")), kt = getColorTexture(p.getString("Kt"));
+                m.kd[0] = kr.c.r; m.kd[1] = kr.c.g; m.kd[2] = kr.c.b;
+                m.kt[0] = kt.c.r; m.kt[1] = kt.c.g; m.kt[2] = kt.c.b;
+                m.kd_tex = kr.tex;
+                m.kt_tex = kt.tex;
                 m.eta = p.getFloat("index", 1.5f);
             } else if (type == "mirror") {
                 m.type = GB_MAT_MIRROR;
-                Color3 kr = getColorTexture(p.getString("Kr"));
-                m.kd[0] = kr.r; m.kd[1] = kr.g; m.kd[2] = kr.b;
+                ColorSlot kr = getColorTexture(p.getString("Kr"));
+                m.kd[0] = kr.c.r; m.kd[1] = kr.c.g; m.kd[2] = kr.c.b;
+                m.kd_tex = kr.tex;
                 m.eta = p.getFloat("index", 0.8f);
                 m.k = p.getFloat("k", 6.0f);
             } else { // "lambert" and the fallback
-                m = lambert(getColorTexture(p.getString("Kd")));
+                ColorSlot kd = getColorTexture(p.getString("Kd"));
+                m = lambert(kd.c);
+                m.kd_tex = kd.tex;
             }
             addMaterial(name, m);
         }
@@ -798,4 +875,6 @@ void gb_scene::fillDesc(gb_scene_desc* d) const {
     d->camera = camera;
     d->film = film;
     d->setting = setting;
+    d->textures = textures.data();
+    d->n_textures = (uint32_t)textures.size();
 }

@@ -117,7 +117,33 @@ typedef struct gb_material {
     float k;               /* mirror / blinn-conductor absorption              */
     float exponent;        /* blinn: the (constant) exponent texture's value   */
     int32_t fresnel;       /* blinn: GB_FRESNEL_*                              */
+    /* Non-constant textures: 1 + index into gb_scene_desc.textures, 0 = the
+     * constant above.  kd_tex replaces kd (Kd / Kr / Kg), kt_tex replaces kt,
+     * exponent_tex (a float texture) replaces exponent. */
+    int32_t kd_tex;
+    int32_t kt_tex;
+    int32_t exponent_tex;
 } gb_material;
+
+/* Procedural textures (src/GoblinTexture.cpp:292-427): constant, checkerboard
+ * over two child textures (point-sampled or box-filtered with the primary
+ * ray's uv differentials), scale = float texture x texture.  Children are
+ * indices of EARLIER entries of the table (textures are created in file
+ * order and look their children up by name at creation,
+ * src/GoblinContextLoader.cpp:246-303).  Image textures are not supported. */
+enum { GB_TEX_CONSTANT = 0, GB_TEX_CHECKERBOARD = 1, GB_TEX_SCALE = 2 };
+enum { GB_MAPPING_UV = 0, GB_MAPPING_SPHERICAL = 1 };
+typedef struct gb_texture {
+    int32_t type;          /* GB_TEX_*                                         */
+    int32_t is_float;      /* float texture: value[0] only                     */
+    float value[3];        /* constant                                         */
+    int32_t child[2];      /* checkerboard: texture1, texture2; scale: texture, scale */
+    int32_t filter;        /* checkerboard "filter"                            */
+    int32_t mapping;       /* GB_MAPPING_* (checkerboard)                      */
+    float map_scale[2];    /* UVMapping                                        */
+    float map_offset[2];
+    float to_tex[12];      /* SphericalMapping: world -> texture space, 3x4    */
+} gb_texture;
 
 typedef struct gb_light {
     int32_t type;          /* GB_LIGHT_*                                       */
@@ -201,6 +227,8 @@ typedef struct gb_scene_desc {
     gb_camera camera;
     gb_film_desc film;
     gb_render_setting setting;
+    const gb_texture* textures;     /* only entries materials reach are read  */
+    uint32_t n_textures;
 } gb_scene_desc;
 
 typedef struct gb_render_params {

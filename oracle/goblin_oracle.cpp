@@ -92,6 +92,16 @@ inline V3 xfNormal(const float* inv, V3 n) { // transpose(inverse) * n
 // path tracer reads it (position, normal, dpdu)
 struct Frag {
     V3 p, n, dpdu;
+    // what only the procedural textures read (src/GoblinGeometry.h Fragment)
+    float u = 0.0f, v = 0.0f;
+    V3 dpdv, dpdx, dpdy;
+    float dudx = 0.0f, dvdx = 0.0f, dudy = 0.0f, dvdy = 0.0f;
+};
+
+// RayDifferential's auxiliary rays (src/GoblinRay.h), set by the camera only
+struct RayDiff {
+    bool has = false;
+    V3 dxO, dxD, dyO, dyD;
 };
 
 struct Isect {
@@ -198,6 +208,16 @@ bool sphereIntersect(float radius, Ray& ray, float* epsilon, Frag* frag) {
     frag->p = pHit;
     frag->n = normalize(pHit);
     frag->dpdu = V3(-TWO_PI * pHit.y, TWO_PI * pHit.x, 0.0f);
+    // uv and dpdv, src/GoblinSphere.cpp:62-77
+    float phi = (float)atan2(pHit.y, pHit.x);
+    if (phi < 0.0f) phi += TWO_PI;
+    frag->u = phi * INV_TWOPI;
+    float theta = (float)acos(pHit.z / radius);
+    frag->v = theta * INV_PI;
+    float invR = 1.0f / (float)sqrt(pHit.x * pHit.x + pHit.y * pHit.y);
+    float cosPhi = pHit.x * invR;
+    float sinPhi = pHit.y * invR;
+    frag->dpdv = PI * V3(pHit.z * cosPhi, pHit.z * sinPhi, -radius * (float)sin(theta));
     return true;
 }
 // Sphere::occluded, src/GoblinSphere.cpp:81-98: the same acceptance test
@@ -229,6 +249,13 @@ bool diskIntersect(float radius, Ray& ray, float* epsilon, Frag* frag) {
     frag->p = p;
     frag->n = V3(0.0f, 0.0f, 1.0f);
     frag->dpdu = V3(-TWO_PI * p.y, TWO_PI * p.x, 0.0f);
+    // uv and dpdv, src/GoblinDisk.cpp:50-61
+    float r = (float)sqrt(squareR);
+    float phi = (float)atan2(p.y, p.x);
+    if (phi < 0.0f) phi += TWO_PI;
+    frag->u = phi * INV_TWOPI;
+    frag->v = r / radius;
+    frag->dpdv = V3(radius * p.x / r, radius * p.y / r, 0.0f);
     return true;
 }
 bool diskOccluded(float radius, const Ray& ray) {
@@ -291,17 +318,22 @@ struct Oracle {
         float du2 = uv[2][0] - uv[0][0];
         float dv2 = uv[2][1] - uv[0][1];
         float determinant = du1 * dv2 - dv1 * du2;
-        V3 dpdu;
+        V3 dpdu, dpdv;
         if (determinant == 0.0f) {
-            V3 unused; // divergence D1: the reference reads the stale output fragment here
-            coordinateAxises(normal, &dpdu, &unused);
+            // divergence D1: the reference reads the stale output fragment here
+            coordinateAxises(normal, &dpdu, &dpdv);
         } else {
             float invDet = 1.0f / determinant;
             dpdu = invDet * (dv2 * e1 - dv1 * e2);
+            dpdv = invDet * (-du2 * e1 + du1 * e2);
         }
         frag->p = position;
         frag->n = normal;
         frag->dpdu = dpdu;
+        frag->dpdv = dpdv;
+        // Vector2 uv(b0 * uvs[0] + b1 * uvs[1] + b2 * uvs[2]), src/GoblinTriangle.cpp:105
+        frag->u = b0 * uv[0][0] + b1 * uv[1][0] + b2 * uv[2][0];
+        frag->v = b0 * uv[0][1] + b1 * uv[1][1] + b2 * uv[2][1];
         return true;
     }
     // Triangle::occluded, src/GoblinTriangle.cpp:127-163
@@ -417,6 +449,7 @@ struct Oracle {
                 isect->frag.p = xfPoint(in.to_world, isect->frag.p);
                 isect->frag.n = normalize(xfNormal(in.to_object, isect->frag.n));
                 isect->frag.dpdu = xfVector(in.to_world, isect->frag.dpdu);
+                isect->frag.dpdv = xfVector(in.to_world, isect->frag.dpdv);
                 ray.maxt = r.maxt;
             }
             return hit;
@@ -459,6 +492,156 @@ struct Oracle {
         uuv = uuv * 2.0f;
         return p + uv + uuv;
     }
+    // the dx / dy auxiliary rays of PerspectiveCamera::generateRay, src/GoblinCamera.cpp:103-142
+    RayDiff cameraRayDiff(float imageX, float imageY, float lensU1, float lensU2) const {
+        const gb_camera& c = d->camera;
+        float invXRes = 1.0f / (float)d->film.xres;
+        float invYRes = 1.0f / (float)d->film.yres;
+        float xNDC = +2.0f * imageX * invXRes - 1.0f;
+        float yNDC = -2.0f * imageY * invYRes + 1.0f;
+        float dxNDC = +2.0f * (imageX + 1.0f) * invXRes - 1.0f;
+        float dyNDC = -2.0f * (imageY + 1.0f) * invYRes + 1.0f;
+        float xView = xNDC / c.proj00;
+        float yView = yNDC / c.proj11;
+        V3 viewDir(xView, yView, 1.0f);
+        V3 dxViewDir(dxNDC / c.proj00, yView, 1.0f);
+        V3 dyViewDir(xView, dyNDC / c.proj11, 1.0f);
+        V3 pos(c.position[0], c.position[1], c.position[2]);
+        RayDiff rd;
+        rd.has = true;
+        if (c.lens_radius == 0.0f) {
+            rd.dxO = rd.dyO = pos;
+            rd.dxD = quatRotate(c.orientation, normalize(dxViewDir));
+            rd.dyD = quatRotate(c.orientation, normalize(dyViewDir));
+        } else {
+            float ft = c.focal_distance / viewDir.z;
+            V3 pDxFocus = dxViewDir * ft;
+            V3 pDyFocus = dyViewDir * ft;
+            float lx, ly;
+            uniformSampleDisk(lensU1, lensU2, &lx, &ly);
+            V3 viewOrigin(c.lens_radius * lx, c.lens_radius * ly, 0.0f);
+            rd.dxO = rd.dyO = quatRotate(c.orientation, viewOrigin) + pos;
+            rd.dxD = quatRotate(c.orientation, normalize(pDxFocus - viewOrigin));
+            rd.dyD = quatRotate(c.orientation, normalize(pDyFocus - viewOrigin));
+        }
+        return rd;
+    }
+
+    // Intersection::computeUVDifferential, src/GoblinPrimitive.cpp:32-97
+    static void computeUVDifferential(Frag& fragment, const RayDiff& ray) {
+        float dudx, dvdx, dudy, dvdy;
+        dudx = dvdx = dudy = dvdy = 0.0f;
+        if (ray.has) {
+            V3 p = fragment.p;
+            V3 n = fragment.n;
+            float minusD = dot(p, n);
+            float tdx = (minusD - dot(ray.dxO, n)) / dot(ray.dxD, n);
+            float tdy = (minusD - dot(ray.dyO, n)) / dot(ray.dyD, n);
+            if (!(tdx != tdx) && !(tdy != tdy)) {
+                V3 pdx = ray.dxO + tdx * ray.dxD;
+                V3 pdy = ray.dyO + tdy * ray.dyD;
+                V3 dpdx = pdx - p;
+                V3 dpdy = pdy - p;
+                fragment.dpdx = dpdx;
+                fragment.dpdy = dpdy;
+                int axis[2];
+                if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) { axis[0] = 1; axis[1] = 2; }
+                else if (fabsf(n.y) > fabsf(n.z)) { axis[0] = 0; axis[1] = 2; }
+                else { axis[0] = 0; axis[1] = 1; }
+                auto comp = [](V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); };
+                float A[2][2] = {{comp(fragment.dpdu, axis[0]), comp(fragment.dpdv, axis[0])},
+                                 {comp(fragment.dpdu, axis[1]), comp(fragment.dpdv, axis[1])}};
+                float Bx[2] = {comp(dpdx, axis[0]), comp(dpdx, axis[1])};
+                if (!solve2x2(A, Bx, &dudx, &dvdx)) dudx = dvdx = 0.0f;
+                float By[2] = {comp(dpdy, axis[0]), comp(dpdy, axis[1])};
+                if (!solve2x2(A, By, &dudy, &dvdy)) dudy = dvdy = 0.0f;
+            }
+        }
+        fragment.dudx = dudx; fragment.dvdx = dvdx; fragment.dudy = dudy; fragment.dvdy = dvdy;
+    }
+    // solve2x2LinearSystem, src/GoblinUtils.h:151-165
+    static bool solve2x2(const float A[2][2], const float B[2], float* x, float* y) {
+        float det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+        if (fabsf(det) < 1e-10f) return false;
+        *x = (+A[1][1] * B[0] - A[0][1] * B[1]) / det;
+        *y = (-A[1][0] * B[0] + A[0][0] * B[1]) / det;
+        if (*x != *x || *y != *y) return false;
+        return true;
+    }
+
+    // ---- procedural textures, src/GoblinTexture.cpp:292-427
+    struct TexCoord { float s, t, dsdx, dtdx, dsdy, dtdy; };
+    static int floorInt(float f) { return (int)floor(f); }
+    void pointToST(const gb_texture& t, V3 p, float* s, float* tt) const { // SphericalMapping::pointToST
+        V3 v = normalize(xfPoint(t.to_tex, p));
+        float theta = (float)acos(clampf(v.z, -1.0f, 1.0f));
+        float phi = (float)atan2(v.y, v.x);
+        phi = phi < 0.0f ? phi + TWO_PI : phi;
+        *s = phi * INV_TWOPI;
+        *tt = theta * INV_PI;
+    }
+    TexCoord mapTexture(const gb_texture& t, const Frag& f) const {
+        TexCoord tc;
+        if (t.mapping == GB_MAPPING_SPHERICAL) { // SphericalMapping::map
+            float s, tt;
+            pointToST(t, f.p, &s, &tt);
+            tc.s = s; tc.t = tt;
+            float sdx, tdx, sdy, tdy;
+            pointToST(t, f.p + f.dpdx, &sdx, &tdx);
+            pointToST(t, f.p + f.dpdy, &sdy, &tdy);
+            float dsdx = sdx - s;
+            if (dsdx > 0.5f) dsdx -= 1.0f; else if (dsdx < -0.5f) dsdx += 1.0f;
+            float dsdy = sdy - s;
+            if (dsdy > 0.5f) dsdy -= 1.0f; else if (dsdy < -0.5f) dsdy += 1.0f;
+            tc.dsdx = dsdx; tc.dtdx = tdx - tt; tc.dsdy = dsdy; tc.dtdy = tdy - tt;
+        } else { // UVMapping::map
+            tc.s = t.map_scale[0] * f.u + t.map_offset[0];
+            tc.t = t.map_scale[1] * f.v + t.map_offset[1];
+            tc.dsdx = t.map_scale[0] * f.dudx;
+            tc.dtdx = t.map_scale[1] * f.dvdx;
+            tc.dsdy = t.map_scale[0] * f.dudy;
+            tc.dtdy = t.map_scale[1] * f.dvdy;
+        }
+        return tc;
+    }
+    static float integrateChecker(float x) {
+        float xHalf = 0.5f * x;
+        return (float)floor(xHalf) + 2.0f * std::max(xHalf - (float)floor(xHalf) - 0.5f, 0.0f);
+    }
+    // Texture<T>::lookup; float textures live in .x
+    V3 texLookup(int index, const Frag& f) const {
+        const gb_texture& t = d->textures[index];
+        if (t.type == GB_TEX_SCALE) { // mScale->lookup(f) * mTexture->lookup(f)
+            float sc = texLookup(t.child[1], f).x;
+            return texLookup(t.child[0], f) * sc;
+        }
+        if (t.type != GB_TEX_CHECKERBOARD) return V3(t.value[0], t.value[1], t.value[2]);
+        TexCoord tc = mapTexture(t, f);
+        float s = tc.s, tt = tc.t;
+        if (!t.filter) {
+            return (floorInt(s) + floorInt(tt)) % 2 == 0 ? texLookup(t.child[0], f) : texLookup(t.child[1], f);
+        }
+        float ds = std::max(fabsf(tc.dsdx), fabsf(tc.dsdy));
+        float dt = std::max(fabsf(tc.dtdx), fabsf(tc.dtdy));
+        float s0 = s - ds, s1 = s + ds, t0 = tt - dt, t1 = tt + dt;
+        if (floorInt(s0) == floorInt(s1) && floorInt(t0) == floorInt(t1)) {
+            return (floorInt(s) + floorInt(tt)) % 2 == 0 ? texLookup(t.child[0], f) : texLookup(t.child[1], f);
+        }
+        float sTex2Ratio = (integrateChecker(s1) - integrateChecker(s0)) / (2.0f * ds);
+        float tTex2Ratio = (integrateChecker(t1) - integrateChecker(t0)) / (2.0f * dt);
+        float tex2Area = sTex2Ratio + tTex2Ratio - 2.0f * sTex2Ratio * tTex2Ratio;
+        if (ds > 1.0f || dt > 1.0f) tex2Area = 0.5f;
+        return (1.0f - tex2Area) * texLookup(t.child[0], f) + tex2Area * texLookup(t.child[1], f);
+    }
+    // the material as the BSDF code reads it at this fragment: textured slots looked up
+    gb_material resolveMaterial(const gb_material& m, const Frag& f) const {
+        gb_material r = m;
+        if (m.kd_tex) { V3 c = texLookup(m.kd_tex - 1, f); r.kd[0] = c.x; r.kd[1] = c.y; r.kd[2] = c.z; }
+        if (m.kt_tex) { V3 c = texLookup(m.kt_tex - 1, f); r.kt[0] = c.x; r.kt[1] = c.y; r.kt[2] = c.z; }
+        if (m.exponent_tex) r.exponent = texLookup(m.exponent_tex - 1, f).x;
+        return r;
+    }
+
     Ray cameraRay(float imageX, float imageY, float lensU1, float lensU2) const {
         const gb_camera& c = d->camera;
         float invXRes = 1.0f / (float)d->film.xres;
@@ -819,7 +1002,7 @@ struct Oracle {
     // With no BSDFnullptr material in the supported set, trace #4 == trace #6 and
     // evalAttenuation == 1; those calls are counted (refIntersect) but not traced.
     template <typename U>
-    V3 liPath(Ray ray, int maxDepth, U u, Stats& st) const {
+    V3 liPath(Ray ray, RayDiff rayDiff, int maxDepth, U u, Stats& st) const {
         if (d->n_lights == 0) return V3();
         V3 Li;
         float epsilon;
@@ -835,8 +1018,10 @@ struct Oracle {
             int li = pickLight(ub[6], &pickLightPdf);
             const gb_light& light = d->lights[li];
             V3 Ld;
-            const gb_material& material = d->materials[d->models[d->instances[is.inst].model].material];
+            computeUVDifferential(is.frag, rayDiff); // src/GoblinPathtracer.cpp:77
             const Frag& fragment = is.frag;
+            const gb_material material =
+                resolveMaterial(d->materials[d->models[d->instances[is.inst].model].material], fragment);
             V3 wo = -ray.d;
             V3 wi;
             V3 p = fragment.p;
@@ -889,6 +1074,7 @@ struct Oracle {
             }
             if (!nextHit) break;
             ray = r;
+            rayDiff.has = false; // RayDifferential(p, wi, epsilon): no auxiliary rays after the camera
             is = next;
             epsilon = nextEps;
         }
@@ -1084,7 +1270,8 @@ int go_li(const gb_scene_desc* d, const float* samples, size_t n, size_t row, fl
             if (method == GB_METHOD_AO) {
                 L = o.liAO(ray, ao, [&](int a, float* uv) { uv[0] = s[4 + 2 * a]; uv[1] = s[4 + 2 * a + 1]; }, st);
             } else {
-                L = o.liPath(ray, depth, [&](int bn, float* ub) { std::memcpy(ub, s + 4 + 7 * bn, 7 * sizeof(float)); }, st);
+                L = o.liPath(ray, o.cameraRayDiff(s[0], s[1], s[2], s[3]), depth,
+                    [&](int bn, float* ub) { std::memcpy(ub, s + 4 + 7 * bn, 7 * sizeof(float)); }, st);
             }
             out_rgb[3 * i] = L.x; out_rgb[3 * i + 1] = L.y; out_rgb[3 * i + 2] = L.z;
             if (ref_calls) {
@@ -1152,7 +1339,7 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                         uv[1] = ((float)(a / aoRoot) + uy) * asub;
                     }, st);
                 } else {
-                    L = o.liPath(ray, depth, [&](int bn, float* ub) {
+                    L = o.liPath(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, [&](int bn, float* ub) {
                         float a4[4], b4[4];
                         block(p->seed, id, 1u + 2u * (uint32_t)bn, a4);
                         block(p->seed, id, 2u + 2u * (uint32_t)bn, b4);

@@ -46,13 +46,44 @@ def _variant(name):
         sc["render_setting"]["ao_sample_num"] = 10
     elif name == "delta_only":
         sc["lights"] = [l for l in sc["lights"] if l["type"] != "area"]
+    elif name.startswith("tex_"):
+        # procedural textures (src/GoblinTexture.cpp:292-427) on every material slot that takes one
+        tex = sc["textures"]
+        filt = name != "tex_point"
+        tex += [
+            {"format": "color", "name": "check", "type": "checkerboard", "texture1": "red", "texture2": "white",
+             "mapping": "uv", "scale": [7.0, 5.0], "offset": [0.25, 0.1], "filter": filt},
+            {"format": "float", "name": "half", "type": "constant", "float": 0.5},
+            {"format": "float", "name": "one", "type": "constant", "float": 1.0},
+            {"format": "float", "name": "fcheck", "type": "checkerboard", "texture1": "half", "texture2": "one",
+             "mapping": "uv", "scale": [3.0, 3.0], "filter": filt},
+            {"format": "color", "name": "dimmed", "type": "scale", "texture": "check", "scale": "fcheck"},
+            {"format": "color", "name": "globe", "type": "checkerboard", "texture1": "green", "texture2": "dimmed",
+             "mapping": "spherical", "position": [0.0, 0.85, 1.6], "scale": [1.0, 1.0, 1.0], "filter": filt},
+            {"format": "float", "name": "rough", "type": "checkerboard", "texture1": "satin", "texture2": "shiny",
+             "mapping": "uv", "scale": [4.0, 4.0], "filter": filt},
+            {"format": "color", "name": "undefined_child", "type": "checkerboard", "texture1": "nope", "texture2": "grey",
+             "scale": [2.0, 2.0]},
+        ]
+        by = {m["name"]: m for m in sc["materials"]}
+        by["grey"]["Kd"] = "check"          # floor: mesh with vt
+        by["green"]["Kd"] = "dimmed"        # box
+        by["mirror"]["Kr"] = "globe"        # sphere, spherical mapping in world space
+        by["glass"]["Kt"] = "check"         # blob meshes + unit sphere: sphere uv
+        by["glass"]["Kr"] = "undefined_child"
+        by["gloss"]["Kg"] = "globe"         # disk
+        by["gloss"]["exponent"] = "rough"
+        by["metal"]["exponent"] = "rough"
+        if name == "tex_dof":
+            sc["camera"]["lens_radius"] = 0.08
+            sc["camera"]["focal_distance"] = 6.5
     else:
         raise KeyError(name)
     return sc
 
 
 VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
-            "depth2", "ao10"]
+            "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof"]
 
 
 @pytest.fixture(scope="module")
@@ -113,7 +144,7 @@ def test_loader_and_oracle_match_reference(variant_files, v):
         ref_l = {k: a.copy() for k, a in gbar.load(td + "/l.gbar").items()}
         ref_c = gbar.load(td + "/c.gbar")["rays"].copy()
     got_c = op.camera_rays(scene, rows[:, :4])
-    assert np.array_equal(got_c[:, [0, 1, 2, 6, 7]], ref_c[:, [0, 1, 2, 6, 7]]) or v == "dof"
+    assert np.array_equal(got_c[:, [0, 1, 2, 6, 7]], ref_c[:, [0, 1, 2, 6, 7]]) or "dof" in v
     assert np.allclose(got_c[:, :6], ref_c[:, :6], rtol=0, atol=1e-6)  # lens sampling: sin / cos of libm, 1 ulp at |o| ~ 6.5
     L, calls = op.li(scene, rows, calls=True)
     same = (calls == ref_l["calls"]).all(axis=1)
