@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +33,7 @@
 #include "rt_core.cuh"
 #include "traverse.cuh"
 #include "shade.cuh"
+#include "texture.cuh"
 
 namespace gb {
 
@@ -311,7 +313,7 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
 // hit carries material MAT.  `bounce` is the reference's loop variable; with
 // emissionOnly the kernel only resolves the pending BSDF-sampled emission
 // (the reference's trace #4 of the last iteration).
-template <int MAT, bool ML>
+template <int MAT, bool ML, bool TEX>
 __global__ void __launch_bounds__(kShadeBlock, (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) ? 6 : 8)
 k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounce, int emissionOnly,
     unsigned int* ctr, unsigned int* ctrNext, unsigned int* qNext) {
@@ -361,6 +363,15 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 DeviceMaterial m;
                 m.kdType = __ldg(&mat.kdType);
                 m.ktEta = __ldg(&mat.ktEta);
+                if (TEX) { // some material slot of this scene is a procedural texture
+                    float imageX = 0.0f, imageY = 0.0f;
+                    float4 u0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (bounce == 0) { // only the camera ray carries differentials
+                        u0 = src.block(id, i, 0);
+                        imagePosition(wp, px, py, s, u0, src.table != nullptr, &imageX, &imageY);
+                    }
+                    applyTextures(sc, fr.material, MAT, h, o, d, fr, bounce == 0, imageX, imageY, u0.z, u0.w, &m);
+                }
                 if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
                     LightSampleResult ls = sampleLight<ML>(sc, li, fr.p, eps, uA.x, uA.y, uA.z);
                     if (!isBlack(ls.L) && ls.pdf > 0.0f) {
@@ -945,6 +956,58 @@ void fillPairs(const gb_bvh_node* nodes, uint32_t count, const uint32_t* pairInd
     });
 }
 
+// Postfix programs for the textured material slots: a texture's children come before it, so the
+// device evaluates a program left to right on a value stack.  Validates the part of the texture
+// table the materials reach (types, child indices pointing at EARLIER entries: no cycles, float
+// children where a float is read) and the stack / length bounds of the evaluator.
+bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, std::vector<unsigned int>* prog,
+    std::string* err) {
+    auto emit = [&](int root, bool wantFloat, int* offset) -> bool {
+        std::vector<unsigned int> out;
+        int depth = 0, maxDepth = 0;
+        bool ok = true;
+        // recursion depth is bounded by the index order (children < parent)
+        std::function<void(int, bool)> rec = [&](int t, bool isFloat) {
+            if (!ok) return;
+            if (t < 0 || (uint32_t)t >= d->n_textures || out.size() > 4096) { ok = false; return; }
+            const gb_texture& g = d->textures[t];
+            if ((g.is_float != 0) != isFloat) { ok = false; return; }
+            if (g.type == GB_TEX_CHECKERBOARD || g.type == GB_TEX_SCALE) {
+                if (g.child[0] >= t || g.child[1] >= t) { ok = false; return; }
+                rec(g.child[0], isFloat);
+                rec(g.child[1], g.type == GB_TEX_SCALE ? true : isFloat);
+                if (!ok) return;
+                if (g.type == GB_TEX_CHECKERBOARD && g.mapping != GB_MAPPING_UV && g.mapping != GB_MAPPING_SPHERICAL) { ok = false; return; }
+                --depth; // two values in, one out
+            } else if (g.type == GB_TEX_CONSTANT) {
+                ++depth;
+                maxDepth = std::max(maxDepth, depth);
+            } else {
+                ok = false;
+                return;
+            }
+            out.push_back((unsigned int)t);
+        };
+        rec(root, wantFloat);
+        if (!ok) { *err = "malformed texture table (type, child order or format)"; return false; }
+        if (maxDepth > kTexStack) { *err = "texture nesting exceeds the evaluator's stack"; return false; }
+        if (prog->empty()) prog->push_back(0u); // offset 0 means "constant"
+        *offset = (int)prog->size();
+        prog->push_back((unsigned int)out.size());
+        prog->insert(prog->end(), out.begin(), out.end());
+        return true;
+    };
+    for (uint32_t m = 0; m < d->n_materials; ++m) {
+        const gb_material& mm = d->materials[m];
+        int4 slots = make_int4(0, 0, 0, 0);
+        if (mm.kd_tex && !emit(mm.kd_tex - 1, false, &slots.x)) return false;
+        if (mm.kt_tex && mm.type == GB_MAT_TRANSPARENT && !emit(mm.kt_tex - 1, false, &slots.y)) return false;
+        if (mm.exponent_tex && mm.type == GB_MAT_BLINN && !emit(mm.exponent_tex - 1, true, &slots.z)) return false;
+        (*matTex)[m] = slots;
+    }
+    return true;
+}
+
 struct Arena { // offsets into the staging / device arena, 256-byte aligned
     size_t size = 0;
     size_t take(size_t bytes) {
@@ -1022,6 +1085,17 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oModelShade = ar.take(16 * (size_t)d->n_models);
     const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
     const size_t oMaterials = ar.take(sizeof(DeviceMaterial) * (size_t)d->n_materials);
+    // procedural textures: postfix programs of the textured material slots
+    std::vector<int4> matTex(d->n_materials, make_int4(0, 0, 0, 0));
+    std::vector<unsigned int> texProg;
+    {
+        std::string terr;
+        if (!compileTexturePrograms(d, &matTex, &texProg, &terr)) return gb::failWith(GB_ERR_INVALID, terr);
+    }
+    const bool hasTextures = !texProg.empty();
+    const size_t oMatTex = ar.take(hasTextures ? 16 * (size_t)d->n_materials : 0);
+    const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
+    const size_t oTexNodes = ar.take(hasTextures ? 16 * (size_t)kTexNodeVec4 * d->n_textures : 0);
     const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
     const size_t oLightPower = ar.take(4 * (size_t)d->n_lights);
     const size_t oLightCdf = ar.take(4 * ((size_t)d->n_lights + 1));
@@ -1141,6 +1215,22 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         } else if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
+    if (hasTextures) {
+        std::memcpy(H + oMatTex, matTex.data(), 16 * matTex.size());
+        std::memcpy(H + oTexProg, texProg.data(), 4 * texProg.size());
+        float4* tn = reinterpret_cast<float4*>(H + oTexNodes);
+        for (uint32_t t = 0; t < d->n_textures; ++t) {
+            const gb_texture& gt = d->textures[t];
+            float4* q = tn + (size_t)kTexNodeVec4 * t;
+            float tb;
+            std::memcpy(&tb, &gt.type, 4);
+            q[0] = make_float4(gt.value[0], gt.value[1], gt.value[2], tb);
+            int opts[4] = {gt.filter, gt.mapping, 0, 0};
+            std::memcpy(&q[1], opts, 16);
+            q[2] = make_float4(gt.map_scale[0], gt.map_scale[1], gt.map_offset[0], gt.map_offset[1]);
+            for (int r = 0; r < 3; ++r) q[3 + r] = make_float4(gt.to_tex[4 * r], gt.to_tex[4 * r + 1], gt.to_tex[4 * r + 2], gt.to_tex[4 * r + 3]);
+        }
+    }
     DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
     bool hasMeshLight = false;
     for (uint32_t l = 0; l < d->n_lights; ++l) {
@@ -1218,6 +1308,9 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.modelShade = reinterpret_cast<const int4*>(D + oModelShade);
     sc.triShade = reinterpret_cast<const float4*>(D + oTriShade);
     sc.materials = reinterpret_cast<const DeviceMaterial*>(D + oMaterials);
+    sc.matTex = hasTextures ? reinterpret_cast<const int4*>(D + oMatTex) : nullptr;
+    sc.texProg = hasTextures ? reinterpret_cast<const unsigned int*>(D + oTexProg) : nullptr;
+    sc.texNodes = hasTextures ? reinterpret_cast<const float4*>(D + oTexNodes) : nullptr;
     sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
     sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);
     sc.lightCdf = reinterpret_cast<const float*>(D + oLightCdf);
@@ -1428,8 +1521,12 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             int eo = last ? 1 : 0;
             {
                 KernelTick tick(ctx, GB_K_SHADE);
-#define GB_SHADE(MATV, MLV) k_shade<MATV, MLV><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
-                if (ctx->hasMeshLight) {
+#define GB_SHADE(MATV, MLV) k_shade<MATV, MLV, false><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
+#define GB_SHADE_TEX(MATV) k_shade<MATV, true, true><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
+                if (ctx->sc.matTex) { // a textured material slot: the variants with the texture evaluator
+                    GB_SHADE_TEX(GB_MAT_LAMBERT); GB_SHADE_TEX(GB_MAT_MIRROR); GB_SHADE_TEX(GB_MAT_TRANSPARENT);
+                    if (ctx->hasBlinn) GB_SHADE_TEX(GB_MAT_BLINN);
+                } else if (ctx->hasMeshLight) {
                     GB_SHADE(GB_MAT_LAMBERT, true); GB_SHADE(GB_MAT_MIRROR, true); GB_SHADE(GB_MAT_TRANSPARENT, true);
                     if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, true);
                 } else {
@@ -1437,6 +1534,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                     if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, false);
                 }
 #undef GB_SHADE
+#undef GB_SHADE_TEX
             }
             ctx->launches += ctx->hasBlinn ? 4 : 3;
             if (!last) {

@@ -62,6 +62,10 @@ struct DeviceScene {
     const int4* modelShade;     // per model: vert base, tri base (face order), has_normal | has_uv << 1, unused
     const float4* triShade;     // 4 per triangle slot (leaf order): the 3 vertex normals and 3 uvs, 64 bytes
     const DeviceMaterial* materials;
+    // procedural textures (texture.cuh); all three null when no material slot is textured
+    const int4* matTex;         // per material: program offset in texProg of kd, kt, exponent (0 = constant), 0
+    const unsigned int* texProg; // postfix programs: [length, node index ...]; entry 0 is unused
+    const float4* texNodes;     // 6 per texture: value | type, options, uv mapping, 3 rows world -> texture
     const DeviceLight* lights;
     const float* lightPower;    // CDF1D::mFunction
     const float* lightCdf;      // CDF1D::mCDF (nLights + 1)
