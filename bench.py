@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-stats", action="store_true", help="skip the counters child process (ncu runs: no roofline)")
+    ap.add_argument("--no-fast-tree", action="store_true", help="skip the extra --accel sah leg of the default run")
     ap.add_argument("--stats-only", default="", help=argparse.SUPPRESS)  # internal: "seed,spp_total,begin,end"
     ap.add_argument("--ref-budget", type=float, default=0.0,
                     help="seconds of CPU work per reference sample (default: 12 for the cpu_baseline of the CUDA arm, 4 per step of --impl reference)")
@@ -262,7 +264,7 @@ def main():
         print("STATS " + json.dumps(ctx.counters()), flush=True)
         return
     stats_pass = None
-    if rank == 0:
+    if rank == 0 and not args.no_stats:
         spp0 = scene.spp_squared(args.spp or None)
         if args.scaling == "strong":
             per0 = (spp0 + world - 1) // world
@@ -390,6 +392,37 @@ def main():
     e2e_value = samples_per_step_all / (e2e_ms / e2e_steps * 1e-3) * 1e-6 if e2e_steps else None
     assert np.isfinite(host_film).all()
 
+    # ---- the same workload on the non-parity fast tree, reported beside the headline
+    fast_tree = None
+    if world == 1 and args.accel == "equal_count" and not args.no_fast_tree and not args.no_e2e:
+        try:
+            t0 = time.perf_counter()
+            sah_scene = api.Scene(scene_json, accel="sah")
+            sah_load_s = time.perf_counter() - t0
+            ctx.upload_scene(sah_scene)
+            for i in range(3):
+                step(20000 + i)
+            ctx.synchronize()
+            fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fsteps = max(1, min(args.steps, 5))
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+                fa.record()
+            for i in range(fsteps):
+                step(20100 + i, flush_l2=False)
+            with torch.cuda.stream(stream):
+                fb.record()
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            fms = fa.elapsed_time(fb) / fsteps
+            fast_tree = {"accel": "sah", "value": samples_per_step_all / (fms * 1e-3) * 1e-6, "unit": "Msamples/s",
+                         "ms_per_step": fms, "steps": fsteps, "scene_load_s": sah_load_s,
+                         "note": "binned-SAH tree behind --accel sah: same kernels, same closest-hit distances, "
+                                 "not the reference's node order; the headline value is the parity tree"}
+            ctx.upload_scene(scene)
+        except Exception as e:  # an extra, never fatal
+            fast_tree = {"accel": "sah", "value": None, "note": f"failed: {e}"}
+
     if rank == 0 and st is None:
         st = {k: 0 for k in ("nodes_visited", "nodes_visited_any", "prims_tested", "prims_tested_any", "instances_entered",
                              "instances_entered_any", "rays_closest", "rays_any")}
@@ -446,6 +479,8 @@ def main():
                         "d2h_bytes_per_step": int(film_floats * 4), "steps": e2e_steps,
                         "what": "gb_upload_scene (host arrays) + gb_film_clear + gb_render + gb_film_download per step"},
                 "roofline": roofline}
+        if fast_tree is not None:
+            line["fast_tree"] = fast_tree
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_reference_sample(scene_json, budget_s=args.ref_budget or 12.0)
