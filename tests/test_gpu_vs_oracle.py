@@ -176,3 +176,45 @@ def test_bvh_depth_and_stack_limits(built):
     for k in ("nodes_visited", "prims_tested", "instances_entered"):
         assert g[k] == c[k], k
     ctx.close()
+
+
+def test_axis_aligned_rays_nan_in_the_slab_test(built):
+    """Rays with a zero direction component have an infinite reciprocal; when the origin also lies
+    exactly on a box plane the reference's slab test meets 0 * inf = NaN and its ordered
+    comparisons decide.  The kernels keep that comparison structure: hits, distances and node
+    counts still equal the oracle's.  (A min / max formulation of the slab test with 3-input
+    FMNMX3 and this case split off was measured: -6 ALU instructions per box, < 1 % faster.)"""
+    import os
+    d = util.gen_scene("grid", 160)
+    scene = api.Scene(os.path.join(d, "grid_pt.json"))
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    pos = scene.vert_pos().reshape(-1, 3)
+    rng = np.random.default_rng(21)
+    n = 60_000
+    o = pos[rng.integers(0, len(pos), n)].copy()          # coordinates that are box planes of the tree
+    axis = rng.integers(0, 3, n)
+    dirs = np.zeros((n, 3), np.float32)
+    dirs[np.arange(n), axis] = rng.choice([-1.0, 1.0], n)
+    two = rng.uniform(size=n) < 0.5                          # half of them: one zero component only
+    other = (axis + 1) % 3
+    dirs[np.arange(n)[two], other[two]] = rng.uniform(-1, 1, two.sum()).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    o -= dirs * rng.uniform(0.0, 3.0, (n, 1)).astype(np.float32) * (rng.uniform(size=(n, 1)) < 0.7)
+    # keep the on-plane coordinates exact where the direction component is zero
+    rays = np.concatenate([o, dirs, np.full((n, 1), 1e-3, np.float32), np.full((n, 1), np.inf, np.float32)], 1)
+    rays = rays.astype(np.float32)
+    # a mesh instance with identity-like placement keeps zero components zero in object space too
+    want, wc = op.trace_closest(scene, rays, counters=True)
+    ctx.enable_counters(True)
+    ctx.reset_counters()
+    got = ctx.trace_closest(rays)
+    gc = ctx.counters()
+    assert np.array_equal(got["inst"], want["inst"]) and np.array_equal(got["prim"], want["prim"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert gc["nodes_visited"] == wc["nodes_visited"] and gc["prims_tested"] == wc["prims_tested"]
+    ctx.enable_counters(False)
+    got2 = ctx.trace_closest(rays)
+    assert np.array_equal(got2["inst"], want["inst"]) and np.array_equal(got2["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert np.array_equal(ctx.trace_any(rays), op.trace_any(scene, rays))
+    assert (want["inst"] >= 0).mean() > 0.2
