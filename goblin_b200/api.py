@@ -55,7 +55,9 @@ class Light(C.Structure):
                 ("cos_falloff_start", C.c_float), ("geom_kind", C.c_int32), ("radius", C.c_float),
                 ("area", C.c_float), ("to_world", C.c_float * 12), ("to_object", C.c_float * 12),
                 ("instance", C.c_int32), ("model", C.c_int32), ("area_offset", C.c_uint32),
-                ("cdf_offset", C.c_uint32)]
+                ("cdf_offset", C.c_uint32), ("image_width", C.c_int32), ("image_height", C.c_int32),
+                ("image_offset", C.c_uint64), ("dist_width", C.c_int32), ("dist_height", C.c_int32),
+                ("dist_offset", C.c_uint64)]
 
 
 class Camera(C.Structure):
@@ -90,7 +92,9 @@ class SceneDesc(C.Structure):
                 ("light_tri_area", C.POINTER(C.c_float)), ("light_tri_cdf", C.POINTER(C.c_float)),
                 ("n_light_tri_area", C.c_uint32), ("n_light_tri_cdf", C.c_uint32),
                 ("world_bound", C.c_float * 6), ("camera", Camera), ("film", FilmDesc),
-                ("setting", RenderSetting), ("textures", C.POINTER(Texture)), ("n_textures", C.c_uint32)]
+                ("setting", RenderSetting), ("textures", C.POINTER(Texture)), ("n_textures", C.c_uint32),
+                ("image_texels", C.POINTER(C.c_float)), ("n_image_texels", C.c_uint64),
+                ("light_dist", C.POINTER(C.c_float)), ("n_light_dist", C.c_uint64)]
 
 
 class LoadOptions(C.Structure):

@@ -115,6 +115,11 @@ Quat quatMul(const Quat& a, const Quat& b) {
     return Quat(w, v.x, v.y, v.z);
 }
 
+Quat quatNormalize(const Quat& q) {
+    float inv = 1.0f / sqrt(q.w * q.w + (q.x * q.x + q.y * q.y + q.z * q.z));
+    return Quat(q.w * inv, q.x * inv, q.y * inv, q.z * inv);
+}
+
 Mat4 quatToMatrix(const Quat& q) {
     float x2 = 2.0f * q.x, y2 = 2.0f * q.y, z2 = 2.0f * q.z;
     float xx2 = x2 * q.x, xy2 = x2 * q.y, xz2 = x2 * q.z, xw2 = x2 * q.w;

@@ -96,6 +96,7 @@ struct Quat { // w + v, GoblinQuaternion.h
 Quat quatFromAxisAngle(const Vec3& axis, float angle);          // GoblinQuaternion.cpp:9-15
 Quat quatFromMatrix3(const float R[3][3]);                      // GoblinQuaternion.cpp:21-53
 Quat quatMul(const Quat& a, const Quat& b);                     // GoblinQuaternion.h operator*
+Quat quatNormalize(const Quat& q);                              // GoblinQuaternion.cpp:94-100
 Mat4 quatToMatrix(const Quat& q);                               // GoblinQuaternion.cpp:55-74
 Vec3 quatRotate(const Quat& q, const Vec3& p);                  // GoblinQuaternion.cpp:87-93
 Quat eulerToQuat(const Vec3& xyzDegrees, const std::string& order); // GoblinQuaternion.cpp:103-151

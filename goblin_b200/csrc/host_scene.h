@@ -23,6 +23,7 @@ struct gb_scene {
     std::vector<gb_light> lights;
     std::vector<float> lightPower, lightCdf;
     std::vector<float> lightTriArea, lightTriCdf; // mesh emitters: per-face areas and their CDF
+    std::vector<float> imageTexels, lightDist;    // image based lights: level-0 radiance, CDF2D tables
     float worldBound[6] = {0, 0, 0, 0, 0, 0};
     gb_camera camera{};
     gb_film_desc film{};

@@ -13,6 +13,7 @@
 #include <sstream>
 
 #include "bvh_builder.h"
+#include "image_map.h"
 #include "host_scene.h"
 #include "obj_loader.h"
 #include "param_set.h"
@@ -598,7 +599,7 @@ struct Loader {
         return true;
     }
 
-    struct PendingLight { gb_light l; Transform xf; int geometry = -1; int model = -1; };
+    struct PendingLight { gb_light l; Transform xf; int geometry = -1; int model = -1; Color3 averageRadiance; };
     std::vector<PendingLight> lights;
 
     static Vec3 lightAxis(const Vec3& dir, Transform* xf) { // Light::setOrientation + onVector(UnitZ)
@@ -621,9 +622,54 @@ struct Loader {
             std::memset(&l, 0, sizeof l);
             l.instance = -1;
             l.model = -1;
-            if (type == "ibl") {
-                err = "light '" + name + "': image based lights are outside the accelerated path";
-                return false;
+            if (type == "ibl") { // createImageBasedLight + ImageBasedLight ctor, src/GoblinLight.cpp:464-506,681-691
+                l.type = GB_LIGHT_IBL;
+                std::string filePath = resolvePath(p.getString("file"));
+                Vec3 filter = p.getVector3("filter");
+                // default orientation faces the centre of the map (spherical coordinates are z-up):
+                // rotateX(-PI/2), rotateY(-PI/2), then the light's own orientation in front
+                Quat q = quatNormalize(quatMul(quatFromAxisAngle(Vec3(1, 0, 0), -0.5f * kPi), Quat()));
+                q = quatNormalize(quatMul(quatFromAxisAngle(Vec3(0, 1, 0), -0.5f * kPi), q));
+                pl.xf.orientation = quatMul(getQuaternion(p), q);
+                pl.xf.update();
+                store3x4(pl.xf.matrix, l.to_world);
+                store3x4(pl.xf.inv, l.to_object);
+                int w = 0, h = 0;
+                std::vector<float> rgba;
+                std::string ierr;
+                if (!loadEXR(filePath, &w, &h, &rgba, &ierr)) {
+                    std::cerr << ierr << std::endl << "errror loading image " << filePath << std::endl;
+                    w = h = 1;
+                    rgba = {1.0f, 0.0f, 1.0f, 1.0f}; // Color::Magenta
+                }
+                for (size_t i = 0; i < (size_t)w * h; ++i) { // buffer[i] *= filter
+                    rgba[4 * i] *= filter.x; rgba[4 * i + 1] *= filter.y; rgba[4 * i + 2] *= filter.z;
+                }
+                std::vector<MipLevel> pyramid;
+                buildMipmap(std::move(rgba), w, h, &pyramid);
+                const int maxLevel = (int)pyramid.size() - 1;
+                float avg[4];
+                mipLookup(pyramid, maxLevel, 0.0f, 0.0f, avg); // mAverageRadiance
+                pl.averageRadiance = Color3{avg[0], avg[1], avg[2]};
+                const MipLevel& dl = pyramid[std::max(0, maxLevel - 8)];
+                std::vector<float> dist((size_t)dl.width * dl.height);
+                for (int i = 0; i < dl.height; ++i) {
+                    float sinTheta = (float)::sin((double)(((float)i + 0.5f) / (float)dl.height * kPi));
+                    for (int j = 0; j < dl.width; ++j) {
+                        const float* c = &dl.rgba[4 * ((size_t)i * dl.width + j)];
+                        dist[(size_t)i * dl.width + j] = (0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]) * sinTheta;
+                    }
+                }
+                std::vector<float> table;
+                buildDistribution2D(dist.data(), dl.width, dl.height, &table);
+                l.dist_width = dl.width;
+                l.dist_height = dl.height;
+                l.dist_offset = out->lightDist.size();
+                out->lightDist.insert(out->lightDist.end(), table.begin(), table.end());
+                l.image_width = pyramid[0].width;
+                l.image_height = pyramid[0].height;
+                l.image_offset = out->imageTexels.size() / 4;
+                out->imageTexels.insert(out->imageTexels.end(), pyramid[0].rgba.begin(), pyramid[0].rgba.end());
             } else if (type == "directional") {
                 l.type = GB_LIGHT_DIRECTIONAL;
                 Vec3 c = p.getVector3("radiance"), d = p.getVector3("direction");
@@ -760,6 +806,11 @@ struct Loader {
                 pr *= s; pg *= s; pb *= s;
                 break;
             }
+            case GB_LIGHT_IBL: { // mAverageRadiance * PI * (4.0f * PI * radius * radius)
+                float s = 4.0f * kPi * worldRadius * worldRadius;
+                pr = pl.averageRadiance.r * kPi * s; pg = pl.averageRadiance.g * kPi * s; pb = pl.averageRadiance.b * kPi * s;
+                break;
+            }
             default: { // area: mLe * PI * worldArea
                 const Vec3& sc = pl.xf.scale;
                 float worldArea = l.area * (sc.x * sc.y);
@@ -875,6 +926,10 @@ void gb_scene::fillDesc(gb_scene_desc* d) const {
     d->camera = camera;
     d->film = film;
     d->setting = setting;
+    d->image_texels = imageTexels.data();
+    d->n_image_texels = imageTexels.size() / 4;
+    d->light_dist = lightDist.data();
+    d->n_light_dist = lightDist.size();
     d->textures = textures.data();
     d->n_textures = (uint32_t)textures.size();
 }

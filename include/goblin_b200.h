@@ -68,7 +68,7 @@ typedef struct gb_hit {
 enum { GB_GEOM_MESH = 0, GB_GEOM_SPHERE = 1, GB_GEOM_DISK = 2 };
 enum { GB_MAT_LAMBERT = 0, GB_MAT_MIRROR = 1, GB_MAT_TRANSPARENT = 2, GB_MAT_BLINN = 3, GB_MAT_COUNT = 4 };
 enum { GB_FRESNEL_DIELECTRIC = 0, GB_FRESNEL_CONDUCTOR = 1 };
-enum { GB_LIGHT_POINT = 0, GB_LIGHT_DIRECTIONAL = 1, GB_LIGHT_SPOT = 2, GB_LIGHT_AREA = 3 };
+enum { GB_LIGHT_POINT = 0, GB_LIGHT_DIRECTIONAL = 1, GB_LIGHT_SPOT = 2, GB_LIGHT_AREA = 3, GB_LIGHT_IBL = 4 };
 enum { GB_METHOD_PATH_TRACING = 0, GB_METHOD_AO = 1 };
 /* BVH split methods.  EQUAL_COUNT is what every BVH of the reference is built
  * with (src/GoblinModel.cpp:24, src/GoblinScene.cpp:15) and the only parity
@@ -162,6 +162,17 @@ typedef struct gb_light {
     int32_t model;         /* the emitting mesh model, -1 otherwise            */
     uint32_t area_offset;  /* first per-face area in light_tri_area            */
     uint32_t cdf_offset;   /* first of tri_count + 1 entries in light_tri_cdf  */
+    /* image based light (src/GoblinLight.cpp:464-629): to_world / to_object hold
+     * its orientation; level 0 of the radiance MIPMap (already multiplied by the
+     * light's filter colour) and the CDF2D over luminance x sin(theta) */
+    int32_t image_width, image_height;
+    uint64_t image_offset; /* first RGBA texel (float4 units) in image_texels  */
+    int32_t dist_width, dist_height;
+    uint64_t dist_offset;  /* first float of this light's table in light_dist:
+                            * dist_height x dist_width function values, the rows'
+                            * dist_width + 1 CDF entries each, then the marginal:
+                            * dist_height row integrals, dist_height + 1 CDF
+                            * entries, 1 integral                               */
 } gb_light;
 
 typedef struct gb_camera {
@@ -229,6 +240,10 @@ typedef struct gb_scene_desc {
     gb_render_setting setting;
     const gb_texture* textures;     /* only entries materials reach are read  */
     uint32_t n_textures;
+    const float* image_texels;      /* image based lights: RGBA float texels  */
+    uint64_t n_image_texels;        /* in texels (4 floats each)              */
+    const float* light_dist;        /* image based lights: sampling tables    */
+    uint64_t n_light_dist;
 } gb_scene_desc;
 
 typedef struct gb_render_params {

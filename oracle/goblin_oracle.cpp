@@ -901,6 +901,59 @@ struct Oracle {
         pdf /= l.area;
         return pdf;
     }
+    // ---- ImageBasedLight, src/GoblinLight.cpp:464-629
+    // MIPMap::lookup(0, s, t) with repeat addressing, src/GoblinTexture.cpp:10-37,274-288
+    V3 iblLookup(const gb_light& l, float s, float t) const {
+        const float* img = d->image_texels + 4 * (size_t)l.image_offset;
+        const int w = l.image_width, h = l.image_height;
+        float sRes = s * w - 0.5f;
+        float tRes = t * h - 0.5f;
+        int s0 = (int)floor(sRes);
+        float ds = sRes - (float)s0;
+        int t0 = (int)floor(tRes);
+        float dt = tRes - (float)t0;
+        auto texel = [&](int ss, int tt) {
+            ss = ss % w;
+            tt = tt % h;
+            if (ss < 0) ss += w;
+            if (tt < 0) tt += h;
+            const float* c = img + 4 * ((size_t)tt * w + ss);
+            return V3(c[0], c[1], c[2]);
+        };
+        return (1.0f - ds) * (1.0f - dt) * texel(s0, t0) + (ds) * (1.0f - dt) * texel(s0 + 1, t0) +
+            (1.0f - ds) * (dt) * texel(s0, t0 + 1) + (ds) * (dt) * texel(s0 + 1, t0 + 1);
+    }
+    // Light::Le(ray): black for every light but the image based one (:511-518)
+    V3 lightLe(const gb_light& l, V3 dir) const {
+        if (l.type != GB_LIGHT_IBL) return V3();
+        V3 w = xfVector(l.to_object, dir); // mToWorld.invertVector
+        float theta = (float)acos(clampf(w.z, -1.0f, 1.0f));
+        float phi = (float)atan2(w.y, w.x);
+        phi = phi < 0.0f ? phi + TWO_PI : phi;
+        return iblLookup(l, phi * INV_TWOPI, theta * INV_PI);
+    }
+    // CDF1D::sampleContinuous, src/GoblinSampler.cpp:344-357
+    static float cdfSampleContinuous(const float* func, const float* cdf, int n, float integral, float u, float* pdf,
+        int* index) {
+        const float* lb = std::lower_bound(cdf, cdf + n + 1, u);
+        int offset = std::max(0, (int)(lb - cdf - 1));
+        float dd = (u - cdf[offset]) / (cdf[offset + 1] - cdf[offset]);
+        *pdf = func[offset] / integral;
+        if (index) *index = offset;
+        return ((float)offset + dd) / n;
+    }
+    struct Dist2D { const float *rowF, *rowC, *margF, *margC; float margI; int w, h; };
+    Dist2D dist2D(const gb_light& l) const {
+        Dist2D t;
+        t.w = l.dist_width; t.h = l.dist_height;
+        t.rowF = d->light_dist + l.dist_offset;
+        t.rowC = t.rowF + (size_t)t.w * t.h;
+        t.margF = t.rowC + (size_t)(t.w + 1) * t.h;
+        t.margC = t.margF + t.h;
+        t.margI = t.margC[t.h + 1];
+        return t;
+    }
+
     V3 sampleL(const gb_light& l, V3 p, float epsilon, float uComp, float u1, float u2, V3* wi, float* pdf,
         Ray* shadow) const {
         shadow->o = p;
@@ -908,6 +961,24 @@ struct Oracle {
         shadow->maxt = INF;
         *pdf = 1.0f;
         V3 color = rgb(l.color);
+        if (l.type == GB_LIGHT_IBL) { // ImageBasedLight::sampleL, :520-545; CDF2D::sampleContinuous
+            Dist2D t = dist2D(l);
+            float pdfRow, pdfCol;
+            int row;
+            float v = cdfSampleContinuous(t.margF, t.margC, t.h, t.margI, u2, &pdfRow, &row);
+            float uu = cdfSampleContinuous(t.rowF + (size_t)row * t.w, t.rowC + (size_t)row * (t.w + 1), t.w,
+                t.margF[row], u1, &pdfCol, nullptr);
+            float pdfST = pdfRow * pdfCol;
+            float theta = v * PI;
+            float phi = uu * TWO_PI;
+            float cosTheta = (float)cos(theta), sinTheta = (float)sin(theta);
+            float cosPhi = (float)cos(phi), sinPhi = (float)sin(phi);
+            V3 wLocal(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+            *wi = xfVector(l.to_world, wLocal);
+            *pdf = pdfST / (TWO_PI * PI * sinTheta); // the sinTheta == 0 guard above it is overwritten
+            shadow->d = *wi;
+            return iblLookup(l, uu, v);
+        }
         if (l.type == GB_LIGHT_POINT || l.type == GB_LIGHT_SPOT) {
             V3 dir = rgb(l.position) - p;
             *wi = normalize(dir);
@@ -983,6 +1054,21 @@ struct Oracle {
         return dot(ns, -*wi) > 0.0f ? color : V3(); // AreaLight::L
     }
     float lightPdf(const gb_light& l, V3 p, V3 wi) const { // Light::pdf / AreaLight::pdf
+        if (l.type == GB_LIGHT_IBL) { // ImageBasedLight::pdf, :618-629; CDF2D::pdf
+            V3 wiLocal = xfVector(l.to_object, wi);
+            float theta = (float)acos(clampf(wiLocal.z, -1.0f, 1.0f));
+            float sinTheta = (float)sin(theta);
+            if (sinTheta == 0.0f) return 0.0f;
+            float phi = (float)atan2(wiLocal.y, wiLocal.x);
+            phi = phi < 0.0f ? phi + TWO_PI : phi;
+            Dist2D t = dist2D(l);
+            float uu = phi * INV_TWOPI, v = theta * INV_PI;
+            int row = std::min(std::max((int)floor(t.h * v), 0), t.h - 1);
+            int col = std::min(std::max((int)floor(t.w * uu), 0), t.w - 1);
+            float integral = t.margI * t.margF[row];
+            float pdf2 = integral == 0.0f ? 0.0f : t.margF[row] * t.rowF[(size_t)row * t.w + col] / integral;
+            return pdf2 / (TWO_PI * PI * sinTheta);
+        }
         if (l.type != GB_LIGHT_AREA) return 0.0f;
         if (l.geom_kind == GB_GEOM_MESH) {
             const gb_model& m = d->models[l.model];
@@ -1008,7 +1094,10 @@ struct Oracle {
         float epsilon;
         Isect is;
         st.refIntersect++;
-        if (!intersect(ray, &epsilon, &is, st)) return Li;
+        if (!intersect(ray, &epsilon, &is, st)) { // Scene::evalEnvironmentLight, src/GoblinScene.cpp:89-95
+            for (uint32_t i = 0; i < d->n_lights; ++i) Li = Li + lightLe(d->lights[i], ray.d);
+            return Li;
+        }
         Li = Li + emitted(is, -ray.d);
         V3 throughput(1.0f, 1.0f, 1.0f);
         for (int bounces = 0; bounces < maxDepth - 1; ++bounces) {
@@ -1035,7 +1124,7 @@ struct Oracle {
                     st.refOccluded++;
                     if (!occluded(shadowRay, st)) {
                         st.refIntersect++; // evalAttenuation(shadowRay): one fruitless notOpaque walk
-                        if (light.type != GB_LIGHT_AREA) {
+                        if (light.type != GB_LIGHT_AREA && light.type != GB_LIGHT_IBL) { // light->isDelta()
                             Ld = Ld + f * L * absdot(n, wi) / lightPdfV;
                         } else {
                             bsdfPdfV = bsdfPdf(material, fragment, wo, wi);
@@ -1063,7 +1152,9 @@ struct Oracle {
                         V3 Le = emitted(next, -wi);
                         if (!isBlack(Le)) Ld = Ld + f * Le * absdot(wi, n) * fWeight / bsdfPdfV;
                     }
-                } // miss: light->Le(r) is black for every supported light (no IBL)
+                } else { // the radiance contribution from IBL (no cosine factor in the reference)
+                    Ld = Ld + f * lightLe(light, wi) * fWeight / bsdfPdfV;
+                }
             }
             Li = Li + throughput * Ld / pickLightPdf;
             if (isBlack(f) || bsdfPdfV == 0.0f) break;

@@ -37,6 +37,7 @@
 #include "GoblinRay.h"
 #include "GoblinThreadLocalStorage.h"
 #include "GoblinImageIO.h"
+#include "GoblinTexture.h"
 
 #include <atomic>
 #include <chrono>
@@ -290,6 +291,39 @@ static int cmdDump(SceneView& v, const char* outPath) {
     if (s->mPowerDistribution) {
         put_f32(f, "light.power", s->mPowerDistribution->mFunction);
         put_f32(f, "light.cdf", s->mPowerDistribution->mCDF);
+    }
+    // image based lights: radiance pyramid, orientation, sampling tables (include/goblin_b200.h layout)
+    for (size_t li = 0; li < s->getLights().size(); ++li) {
+        const ImageBasedLight* ibl = dynamic_cast<const ImageBasedLight*>(s->getLights()[li]);
+        if (!ibl) continue;
+        std::string pre = "ibl" + std::to_string(li) + ".";
+        const MIPMap<Color>* mm = ibl->mRadiance;
+        std::vector<int32_t> sizes;
+        for (int l = 0; l < mm->mLevelsNum; ++l) {
+            const ImageBuffer<Color>* b = mm->mPyramid[l];
+            sizes.push_back(b->width); sizes.push_back(b->height);
+            std::vector<float> px((size_t)b->width * b->height * 4);
+            memcpy(px.data(), b->image, px.size() * 4);
+            put_f32(f, pre + "level" + std::to_string(l), px);
+        }
+        put_i32(f, pre + "sizes", sizes);
+        put_f32(f, pre + "average", {ibl->mAverageRadiance.r, ibl->mAverageRadiance.g, ibl->mAverageRadiance.b});
+        const Matrix4& M = ibl->mToWorld.getMatrix();
+        const Matrix4& I = ibl->mToWorld.getInverse();
+        std::vector<float> fw, inv;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) { fw.push_back(M[r][c]); inv.push_back(I[r][c]); }
+        put_f32(f, pre + "to_world", fw);
+        put_f32(f, pre + "to_object", inv);
+        const CDF2D* d2 = ibl->mDistribution;
+        std::vector<float> table;
+        int h = (int)d2->mConditionalDist.size(), w = d2->mConditionalDist[0]->mCount;
+        for (int r = 0; r < h; ++r) table.insert(table.end(), d2->mConditionalDist[r]->mFunction.begin(), d2->mConditionalDist[r]->mFunction.end());
+        for (int r = 0; r < h; ++r) table.insert(table.end(), d2->mConditionalDist[r]->mCDF.begin(), d2->mConditionalDist[r]->mCDF.end());
+        table.insert(table.end(), d2->mMarginalDist->mFunction.begin(), d2->mMarginalDist->mFunction.end());
+        table.insert(table.end(), d2->mMarginalDist->mCDF.begin(), d2->mMarginalDist->mCDF.end());
+        table.push_back(d2->mMarginalDist->mIntegral);
+        put_f32(f, pre + "dist", table);
+        put_i32(f, pre + "dist_size", {w, h});
     }
     // --- camera / film / filter
     const CameraPtr cam = s->getCamera();
