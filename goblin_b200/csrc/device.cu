@@ -399,6 +399,10 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                         float3 w = div3(bs.f * absdot3(bs.wi, fr.n) * fWeight, bs.pdf);
                         float3 pw = div3(mul3(thr, w), pickPdf);
                         pendOut = make_float4(pw.x, pw.y, pw.z, __int_as_float(li));
+                    } else if (ML && ltype == GB_LIGHT_IBL) { // f * tr * light->Le(r) * fWeight / bsdfPdf: no cosine
+                        float3 w = div3(bs.f * fWeight, bs.pdf);
+                        float3 pw = div3(mul3(thr, w), pickPdf);
+                        pendOut = make_float4(pw.x, pw.y, pw.z, __int_as_float(li));
                     }
                 }
                 if (!(isBlack(bs.f) || bs.pdf == 0.0f)) {
@@ -433,6 +437,38 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 ps.shC[k] = make_float4(shC.x, shC.y, shC.z, __int_as_float((int)i));
             }
         }
+    }
+}
+
+// ------------------------------------------------------------- environment
+// Scenes with an image based light: what a ray that left the scene picks up.  Camera rays add
+// Scene::evalEnvironmentLight (GoblinScene.cpp:89-95: the sum of Le over all lights,
+// GoblinPathtracer.cpp:61-65); BSDF-sampled rays add the MIS-weighted term of the light that was
+// picked for their bounce (GoblinPathtracer.cpp:156-160), whose weight the shade kernel left in
+// `pend`.  One thread per path of the extend queue that has just been traced.
+__global__ void k_miss(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, const unsigned int* ctr,
+    int bounce) {
+    const unsigned int n = ctr[C_EXTEND];
+    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned int i = queue ? __ldg(queue + j) : j;
+        if (ps.hitId[i].x >= 0) continue;
+        const float4 rd = ps.rayD[i];
+        const float3 d = make3(rd.x, rd.y, rd.z);
+        float4 L = ps.L[i];
+        if (bounce == 0) {
+            for (unsigned int l = 0; l < sc.nLights; ++l) {
+                if (__float_as_int(__ldg(&sc.lights[l].colorType).w) != GB_LIGHT_IBL) continue;
+                const float3 le = iblLe(sc, sc.lights[l], d);
+                L.x += le.x; L.y += le.y; L.z += le.z;
+            }
+        } else {
+            const float4 pd = ps.pend[i];
+            const int li = __float_as_int(pd.w);
+            if (li < 0 || __float_as_int(__ldg(&sc.lights[li].colorType).w) != GB_LIGHT_IBL) continue;
+            const float3 le = iblLe(sc, sc.lights[li], d);
+            L.x += pd.x * le.x; L.y += pd.y * le.y; L.z += pd.z * le.z;
+        }
+        ps.L[i] = L;
     }
 }
 
@@ -1096,6 +1132,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oMatTex = ar.take(hasTextures ? 16 * (size_t)d->n_materials : 0);
     const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
     const size_t oTexNodes = ar.take(hasTextures ? 16 * (size_t)kTexNodeVec4 * d->n_textures : 0);
+    const size_t oImageTexels = ar.take(16 * (size_t)d->n_image_texels);
+    const size_t oLightDist = ar.take(4 * (size_t)d->n_light_dist);
     const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
     const size_t oLightPower = ar.take(4 * (size_t)d->n_lights);
     const size_t oLightCdf = ar.take(4 * ((size_t)d->n_lights + 1));
@@ -1231,8 +1269,10 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             for (int r = 0; r < 3; ++r) q[3 + r] = make_float4(gt.to_tex[4 * r], gt.to_tex[4 * r + 1], gt.to_tex[4 * r + 2], gt.to_tex[4 * r + 3]);
         }
     }
+    if (d->n_image_texels) std::memcpy(H + oImageTexels, d->image_texels, 16 * (size_t)d->n_image_texels);
+    if (d->n_light_dist) std::memcpy(H + oLightDist, d->light_dist, 4 * (size_t)d->n_light_dist);
     DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
-    bool hasMeshLight = false;
+    bool hasMeshLight = false, hasEnvLight = false;
     for (uint32_t l = 0; l < d->n_lights; ++l) {
         const gb_light& gl = d->lights[l];
         DeviceLight& dl = lights[l];
@@ -1269,6 +1309,21 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             uint32_t w[4] = {gl.area_offset, md.tri_count, md.has_normal ? 1u : 0u, gl.cdf_offset};
             std::memcpy(&dl.dirCos, w, 16);
             hasMeshLight = true;
+        }
+        if (gl.type == GB_LIGHT_IBL) {
+            const uint64_t texels = (uint64_t)gl.image_width * (uint64_t)gl.image_height;
+            const uint64_t dw = (uint64_t)gl.dist_width, dh = (uint64_t)gl.dist_height;
+            if (gl.image_width <= 0 || gl.image_height <= 0 || gl.dist_width <= 0 || gl.dist_height <= 0 ||
+                gl.image_offset + texels > d->n_image_texels || gl.image_offset > 0xffffffffull ||
+                gl.dist_offset + dw * dh + (dw + 1) * dh + 2 * dh + 2 > d->n_light_dist || gl.dist_offset > 0xffffffffull) {
+                return gb::failWith(GB_ERR_INVALID, "image based light ranges exceed image_texels / light_dist");
+            }
+            int dims[4] = {gl.image_width, gl.image_height, gl.dist_width, gl.dist_height};
+            uint32_t offs[4] = {(uint32_t)gl.image_offset, (uint32_t)gl.dist_offset, 0u, 0u};
+            std::memcpy(&dl.posRadius, dims, 16);
+            std::memcpy(&dl.dirCos, offs, 16);
+            hasMeshLight = true; // the shade-kernel variants that carry the rare light kinds
+            hasEnvLight = true;
         }
         dl.misc = make_float4(gl.cos_falloff_start, gl.area, kb, sb);
         for (int r = 0; r < 3; ++r) {
@@ -1323,6 +1378,9 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.nLights = d->n_lights;
     sc.lightIntegral = integral;
     sc.hasAreaLight = hasArea ? 1u : 0u;
+    sc.hasEnvLight = hasEnvLight ? 1u : 0u;
+    sc.imageTexels = reinterpret_cast<const float4*>(D + oImageTexels);
+    sc.lightDist = reinterpret_cast<const float*>(D + oLightDist);
     sc.camera = d->camera;
     sc.xres = f.xres; sc.yres = f.yres;
     sc.xstart = f.xstart; sc.xcount = f.xcount; sc.ystart = f.ystart; sc.ycount = f.ycount;
@@ -1513,8 +1571,13 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         for (int b = 0; b < depth; ++b) {
             // the last extend only feeds the BSDF-sampled emission term; skip it when no area light exists
             const bool last = b == depth - 1;
-            if (last && b > 0 && !ctx->sc.hasAreaLight) break;
+            if (last && b > 0 && !ctx->sc.hasAreaLight && !ctx->sc.hasEnvLight) break;
             if ((rc = extend(b, 0)) != GB_OK) return rc;
+            if (ctx->sc.hasEnvLight) { // rays that left the scene pick up the environment map
+                KernelTick tick(ctx, GB_K_SHADE);
+                k_miss<<<shadeGrid, 256, 0, st>>>(ctx->sc, ps, b == 0 ? nullptr : ps.qExtend[b & 1], ctx->ctr + b * kCtrStride, b);
+                ctx->launches++;
+            }
             unsigned int* c = ctx->ctr + b * kCtrStride;
             unsigned int* cn = ctx->ctr + (b + 1) * kCtrStride;
             unsigned int* qn = ps.qExtend[(b + 1) & 1];

@@ -71,9 +71,12 @@ struct DeviceScene {
     const float* lightCdf;      // CDF1D::mCDF (nLights + 1)
     const float4* lightTris;    // mesh emitters, 6 per face in FACE order: p0|area, p1, p2, n0, n1, n2
     const float* lightTriCdf;   // mesh emitters: area CDFs
+    const float4* imageTexels;  // image based lights: level 0 of the radiance maps, RGBA
+    const float* lightDist;     // image based lights: CDF2D tables (layout in goblin_b200.h)
     uint32_t nLights;
     float lightIntegral;        // CDF1D::mIntegral
     uint32_t hasAreaLight;
+    uint32_t hasEnvLight;       // some light is image based: missed rays pick up its radiance (k_miss)
     // ---- camera / film
     gb_camera camera;
     int xres, yres;

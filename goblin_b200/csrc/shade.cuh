@@ -535,6 +535,56 @@ __device__ __forceinline__ float shapePdf(int kind, float radius, float area, fl
     return sum;
 }
 
+// ---- ImageBasedLight (GoblinLight.cpp:464-629).  DeviceLight packing for GB_LIGHT_IBL: posRadius =
+// int bits (image width, image height, distribution width, distribution height), dirCos = uint bits
+// (first texel in sc.imageTexels, first float in sc.lightDist, 0, 0), toWorld / toObject = orientation.
+// MIPMap::lookup(0, s, t), repeat addressing (GoblinTexture.cpp:10-37,274-288)
+__device__ __noinline__ float3 iblLookup(const float4* __restrict__ img, int w, int h, float s, float t) {
+    const float sRes = s * w - 0.5f;
+    const float tRes = t * h - 0.5f;
+    const int s0 = (int)floorf(sRes);
+    const float ds = sRes - (float)s0;
+    const int t0 = (int)floorf(tRes);
+    const float dt = tRes - (float)t0;
+    int sa = s0 % w, sb = (s0 + 1) % w, ta = t0 % h, tb = (t0 + 1) % h;
+    if (sa < 0) sa += w;
+    if (sb < 0) sb += w;
+    if (ta < 0) ta += h;
+    if (tb < 0) tb += h;
+    const float4 a = __ldg(img + (size_t)ta * w + sa), b = __ldg(img + (size_t)ta * w + sb);
+    const float4 c = __ldg(img + (size_t)tb * w + sa), d = __ldg(img + (size_t)tb * w + sb);
+    const float wa = (1.0f - ds) * (1.0f - dt), wb = ds * (1.0f - dt), wc = (1.0f - ds) * dt, wd = ds * dt;
+    return make3(((a.x * wa + b.x * wb) + c.x * wc) + d.x * wd, ((a.y * wa + b.y * wb) + c.y * wc) + d.y * wd,
+        ((a.z * wa + b.z * wb) + c.z * wc) + d.z * wd);
+}
+// ImageBasedLight::Le(ray): the map looked up along a world direction
+__device__ __noinline__ float3 iblLe(const DeviceScene& sc, const DeviceLight& l, float3 dir) {
+    const float4 i0 = __ldg(&l.toObject[0]), i1 = __ldg(&l.toObject[1]), i2 = __ldg(&l.toObject[2]);
+    const float4 dims = __ldg(&l.posRadius), offs = __ldg(&l.dirCos);
+    const float3 w = xfVector(i0, i1, i2, dir); // mToWorld.invertVector
+    const float theta = acosf(fminf(fmaxf(w.z, -1.0f), 1.0f));
+    float phi = atan2f(w.y, w.x);
+    phi = phi < 0.0f ? phi + GB_TWO_PI : phi;
+    return iblLookup(sc.imageTexels + __float_as_uint(offs.x), __float_as_int(dims.x), __float_as_int(dims.y),
+        phi * GB_INV_TWOPI, theta * GB_INV_PI);
+}
+// std::lower_bound over a CDF of n + 1 entries, then CDF1D::sampleContinuous (GoblinSampler.cpp:344-357)
+__device__ __forceinline__ float cdfSampleContinuous(const float* __restrict__ func, const float* __restrict__ cdf, int n,
+    float integral, float u, float* pdf, int* index) {
+    int lo = 0, len = n + 1;
+    while (len > 0) { // first entry that is not < u
+        const int half = len >> 1;
+        if (__ldg(cdf + lo + half) < u) { lo += half + 1; len -= half + 1; }
+        else len = half;
+    }
+    const int offset = max(0, lo - 1);
+    const float c0 = __ldg(cdf + offset), c1 = __ldg(cdf + offset + 1);
+    const float d = (u - c0) / (c1 - c0);
+    *pdf = __ldg(func + offset) / integral;
+    *index = offset;
+    return ((float)offset + d) / (float)n;
+}
+
 struct LightSampleResult {
     float3 L;
     float3 wi;
@@ -555,9 +605,31 @@ __device__ __forceinline__ LightSampleResult sampleLight(const DeviceScene& sc, 
     float4 ct = __ldg(&l.colorType);
     int type = __float_as_int(ct.w);
     float3 color = make3(ct.x, ct.y, ct.z);
-    r.delta = type != GB_LIGHT_AREA;
+    r.delta = type != GB_LIGHT_AREA && type != GB_LIGHT_IBL;
     r.pdf = 1.0f;
     r.maxt = INFINITY;
+    if (ML && type == GB_LIGHT_IBL) { // ImageBasedLight::sampleL + CDF2D::sampleContinuous
+        const float4 dims = __ldg(&l.posRadius), offs = __ldg(&l.dirCos);
+        const int dw = __float_as_int(dims.z), dh = __float_as_int(dims.w);
+        const float* rowF = sc.lightDist + __float_as_uint(offs.y);
+        const float* rowC = rowF + (size_t)dw * dh;
+        const float* margF = rowC + (size_t)(dw + 1) * dh;
+        const float* margC = margF + dh;
+        float pdfRow, pdfCol;
+        int row, col;
+        const float v = cdfSampleContinuous(margF, margC, dh, __ldg(margC + dh + 1), u2, &pdfRow, &row);
+        const float uu = cdfSampleContinuous(rowF + (size_t)row * dw, rowC + (size_t)row * (dw + 1), dw, __ldg(margF + row), u1,
+            &pdfCol, &col);
+        const float pdfST = pdfRow * pdfCol;
+        float sinTheta, cosTheta, sinPhi, cosPhi;
+        sincosf(v * GB_PI, &sinTheta, &cosTheta);
+        sincosf(uu * GB_TWO_PI, &sinPhi, &cosPhi);
+        const float4 w0 = __ldg(&l.toWorld[0]), w1 = __ldg(&l.toWorld[1]), w2 = __ldg(&l.toWorld[2]);
+        r.wi = xfVector(w0, w1, w2, make3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));
+        r.pdf = pdfST / (GB_TWO_PI * GB_PI * sinTheta);
+        r.L = iblLookup(sc.imageTexels + __float_as_uint(offs.x), __float_as_int(dims.x), __float_as_int(dims.y), uu, v);
+        return r;
+    }
     if (type == GB_LIGHT_POINT || type == GB_LIGHT_SPOT) {
         float4 pr = __ldg(&l.posRadius);
         float3 dir = make3(pr.x, pr.y, pr.z) - p;
@@ -647,6 +719,26 @@ template <bool ML>
 __device__ __forceinline__ float lightPdf(const DeviceScene& sc, int li, float3 p, float3 wi) {
     const DeviceLight& l = sc.lights[li];
     int type = __float_as_int(__ldg(&l.colorType).w);
+    if (ML && type == GB_LIGHT_IBL) { // ImageBasedLight::pdf + CDF2D::pdf
+        const float4 j0 = __ldg(&l.toObject[0]), j1 = __ldg(&l.toObject[1]), j2 = __ldg(&l.toObject[2]);
+        const float3 wl = xfVector(j0, j1, j2, wi);
+        const float theta = acosf(fminf(fmaxf(wl.z, -1.0f), 1.0f));
+        const float sinTheta = sinf(theta);
+        if (sinTheta == 0.0f) return 0.0f;
+        float phi = atan2f(wl.y, wl.x);
+        phi = phi < 0.0f ? phi + GB_TWO_PI : phi;
+        const float4 dims = __ldg(&l.posRadius), offs = __ldg(&l.dirCos);
+        const int dw = __float_as_int(dims.z), dh = __float_as_int(dims.w);
+        const float* rowF = sc.lightDist + __float_as_uint(offs.y);
+        const float* margF = rowF + (size_t)dw * dh + (size_t)(dw + 1) * dh;
+        const float margI = __ldg(margF + dh + dh + 1);
+        const int row = min(max((int)floorf(dh * (theta * GB_INV_PI)), 0), dh - 1);
+        const int col = min(max((int)floorf(dw * (phi * GB_INV_TWOPI)), 0), dw - 1);
+        const float mf = __ldg(margF + row);
+        const float integral = margI * mf;
+        const float pdf2 = integral == 0.0f ? 0.0f : mf * __ldg(rowF + (size_t)row * dw + col) / integral;
+        return pdf2 / (GB_TWO_PI * GB_PI * sinTheta);
+    }
     if (type != GB_LIGHT_AREA) return 0.0f;
     float4 pr = __ldg(&l.posRadius);
     float4 misc = __ldg(&l.misc);

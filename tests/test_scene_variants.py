@@ -46,6 +46,20 @@ def _variant(name):
         sc["render_setting"]["ao_sample_num"] = 10
     elif name == "delta_only":
         sc["lights"] = [l for l in sc["lights"] if l["type"] != "area"]
+    elif name.startswith("ibl"):
+        # image based light (src/GoblinLight.cpp:464-629): a 40 x 24 map (resized to 64 x 32 by the
+        # MIPMap) beside a point light, or a 32 x 16 one alone
+        sky = {"name": "sky", "type": "ibl", "file": "_env_40x24.exr", "filter": [0.8, 0.9, 1.0], "euler": [10.0, 40.0, 0.0]}
+        if name == "ibl":
+            sc["lights"] = [l for l in sc["lights"] if l["type"] == "point"] + [sky]
+        elif name == "ibl_only":
+            sky["file"] = "_env_32x16.exr"
+            sky["filter"] = [1.0, 1.0, 1.0]
+            del sky["euler"]
+            sc["lights"] = [sky]
+        else:  # every light kind at once, the map missing: the reference falls back to 1 x 1 magenta
+            sky["file"] = "_env_missing.exr"
+            sc["lights"] = sc["lights"] + [sky]
     elif name.startswith("tex_"):
         # procedural textures (src/GoblinTexture.cpp:292-427) on every material slot that takes one
         tex = sc["textures"]
@@ -83,7 +97,7 @@ def _variant(name):
 
 
 VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
-            "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof"]
+            "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof", "ibl", "ibl_only", "ibl_missing"]
 
 
 @pytest.fixture(scope="module")
@@ -91,12 +105,21 @@ def variant_files(tmp_path_factory, built):
     """JSON files next to the tiny scene's models (mesh paths are relative to the scene file)."""
     out = {}
     d = os.path.dirname(util.TINY_PT)
+    rng = np.random.default_rng(5)
+    env = []
+    for w, h in ((40, 24), (32, 16)):  # HDR maps with a small very bright region, written by the product's EXR writer
+        img = rng.uniform(0.05, 1.0, (h, w, 3)).astype(np.float32)
+        img[h // 6:h // 6 + 3, w // 4:w // 4 + 4] *= 40.0
+        env.append(os.path.join(d, f"_env_{w}x{h}.exr"))
+        api.write_rgb(env[-1], img)
     for v in VARIANTS:
         path = os.path.join(d, f"_variant_{v}.json")
         with open(path, "w") as f:
             json.dump(_variant(v), f)
         out[v] = path
     yield out
+    for p in env:
+        os.remove(p)
     for p in out.values():
         for q in (p, p[:-5] + ".exr"):
             if os.path.exists(q):
@@ -132,6 +155,21 @@ def test_loader_and_oracle_match_reference(variant_files, v):
         assert np.array_equal(scene.top_order(), dump["top.order"])
         if scene.desc.n_lights:
             assert np.array_equal(scene.light_cdf().view(np.uint32), dump["light.cdf"].view(np.uint32))
+        for li in range(scene.desc.n_lights):  # image based lights: map, orientation, sampling tables
+            L = scene.desc.lights[li]
+            if L.type != 4:
+                continue
+            pre = f"ibl{li}."
+            tex = np.ctypeslib.as_array(scene.desc.image_texels, (scene.desc.n_image_texels * 4,))
+            tex = tex[4 * L.image_offset:4 * (L.image_offset + L.image_width * L.image_height)]
+            assert [L.image_width, L.image_height] == list(dump[pre + "sizes"][:2])
+            assert np.array_equal(tex.view(np.uint32), dump[pre + "level0"].view(np.uint32))
+            n_dist = len(dump[pre + "dist"])
+            dist = np.ctypeslib.as_array(scene.desc.light_dist, (scene.desc.n_light_dist,))[L.dist_offset:L.dist_offset + n_dist]
+            assert [L.dist_width, L.dist_height] == list(dump[pre + "dist_size"])
+            assert np.array_equal(dist.view(np.uint32), dump[pre + "dist"].view(np.uint32))
+            assert np.array_equal(np.array(L.to_world[:], np.float32).view(np.uint32), dump[pre + "to_world"].view(np.uint32))
+            assert np.array_equal(np.array(L.to_object[:], np.float32).view(np.uint32), dump[pre + "to_object"].view(np.uint32))
         # Li and camera rays on fresh samples
         rng = np.random.default_rng(zlib.crc32(v.encode()))
         rows = rng.uniform(0, 1, (1500, _row_floats(scene))).astype(np.float32)
@@ -188,3 +226,101 @@ def test_gpu_matches_oracle(variant_files, v):
     if v == "nolights":
         assert (g[..., :3] == 0).all() and (g[..., 3] > 0).any()
     ctx.close()
+
+
+# ---- the OpenEXR reader behind image based lights against the reference's (tinyexr's LoadEXR)
+
+def _write_exr(path, img, compression, pixel_type, line_order_decreasing=False, channels="BGR"):
+    """A small OpenEXR scanline writer for tests: compression 0 none, 1 RLE, 2 ZIPS, 3 ZIP;
+    pixel_type 1 HALF, 2 FLOAT."""
+    import struct
+    h, w, _ = img.shape
+    idx = {"R": 0, "G": 1, "B": 2}
+
+    def attr(name, typ, val):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(val)) + val
+
+    names = sorted(channels)
+    ch = b"".join(n.encode() + b"\0" + struct.pack("<iBxxxii", pixel_type, 0, 1, 1) for n in names) + b"\0"
+    win = struct.pack("<4i", 0, 0, w - 1, h - 1)
+    hd = struct.pack("<II", 20000630, 2)
+    hd += attr("channels", "chlist", ch) + attr("compression", "compression", bytes([compression]))
+    hd += attr("dataWindow", "box2i", win) + attr("displayWindow", "box2i", win)
+    hd += attr("lineOrder", "lineOrder", bytes([1 if line_order_decreasing else 0]))
+    hd += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+    hd += attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+    hd += b"\0"
+    lines = 16 if compression == 3 else 1
+    dt = np.float16 if pixel_type == 1 else np.float32
+
+    def shuffle(raw):
+        b = np.frombuffer(raw, np.uint8)
+        t = np.concatenate([b[0::2], b[1::2]]).astype(np.int32)
+        d = t.copy()
+        d[1:] = (t[1:] - t[:-1] + 128 + 256) % 256
+        return d.astype(np.uint8).tobytes()
+
+    def rle(data):
+        out = bytearray()
+        i = 0
+        while i < len(data):
+            j = i
+            while j + 1 < len(data) and data[j + 1] == data[i] and j - i < 126:
+                j += 1
+            if j - i >= 2:
+                out += struct.pack("b", j - i) + data[i:i + 1]
+                i = j + 1
+            else:
+                k = i
+                while k < len(data) and k - i < 127 and not (k + 2 < len(data) and data[k] == data[k + 1] == data[k + 2]):
+                    k += 1
+                out += struct.pack("b", -(k - i)) + data[i:k]
+                i = k
+        return bytes(out)
+
+    blocks = []
+    for y0 in range(0, h, lines):
+        raw = b"".join(img[y, :, idx[n]].astype(dt).tobytes() for y in range(y0, min(h, y0 + lines)) for n in names)
+        if compression in (2, 3):
+            z = zlib.compress(shuffle(raw))
+            data = z if len(z) < len(raw) else raw
+        elif compression == 1:
+            z = rle(shuffle(raw))
+            data = z if len(z) < len(raw) else raw
+        else:
+            data = raw
+        blocks.append((y0, data))
+    if line_order_decreasing:
+        blocks = blocks[::-1]
+    off = len(hd) + 8 * len(blocks)
+    table, body = {}, b""
+    for y0, data in blocks:
+        table[y0] = off + len(body)
+        body += struct.pack("<ii", y0, len(data)) + data
+    tab = b"".join(struct.pack("<Q", table[y0]) for y0 in sorted(table))
+    open(path, "wb").write(hd + tab + body)
+
+
+@pytest.mark.skipif(not util.have_ref_tool(), reason="oracle/_ref/ref_tool not built")
+@pytest.mark.parametrize("compression,pixel_type,decreasing", [(0, 2, False), (1, 1, False), (2, 2, False), (3, 1, False),
+                                                                (3, 2, False)])  # increasing-y files only: the pinned case
+def test_exr_reader_matches_the_reference_loader(built, tmp_path, compression, pixel_type, decreasing):
+    rng = np.random.default_rng(compression * 7 + pixel_type)
+    img = rng.uniform(0.0, 3.0, (40, 64, 3)).astype(np.float32)
+    img[10:30, 5:40] = 0.25  # runs for RLE / ZIP to chew on
+    sc = json.load(open(util.TINY_PT))
+    sc["lights"] = [{"name": "sky", "type": "ibl", "file": "env.exr", "filter": [1.0, 1.0, 1.0]}]
+    d = tmp_path / "scene"
+    os.makedirs(d / "models")
+    for f in os.listdir(os.path.join(os.path.dirname(util.TINY_PT), "models")):
+        os.symlink(os.path.join(os.path.dirname(util.TINY_PT), "models", f), d / "models" / f)
+    json.dump(sc, open(d / "s.json", "w"))
+    _write_exr(str(d / "env.exr"), img, compression, pixel_type, decreasing)
+    _ref("dump", str(d / "s.json"), str(d / "d.gbar"))
+    dump = gbar.load(str(d / "d.gbar"))
+    scene = api.Scene(str(d / "s.json"))
+    L = scene.desc.lights[0]
+    assert (L.image_width, L.image_height) == (64, 64)  # 64 x 40 resized up to powers of two
+    tex = np.ctypeslib.as_array(scene.desc.image_texels, (scene.desc.n_image_texels * 4,))
+    assert np.array_equal(tex.view(np.uint32), dump["ibl0.level0"].view(np.uint32))
+    assert dump["ibl0.level0"].reshape(-1, 4)[:, :3].max() > 1.0  # really the image, not the magenta fallback
