@@ -46,7 +46,13 @@ class Material(C.Structure):
 class Texture(C.Structure):
     _fields_ = [("type", C.c_int32), ("is_float", C.c_int32), ("value", C.c_float * 3),
                 ("child", C.c_int32 * 2), ("filter", C.c_int32), ("mapping", C.c_int32),
-                ("map_scale", C.c_float * 2), ("map_offset", C.c_float * 2), ("to_tex", C.c_float * 12)]
+                ("map_scale", C.c_float * 2), ("map_offset", C.c_float * 2), ("to_tex", C.c_float * 12),
+                ("image_filter", C.c_int32), ("address_mode", C.c_int32), ("max_anisotropy", C.c_float),
+                ("first_level", C.c_int32), ("n_levels", C.c_int32)]
+
+
+class ImageLevel(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("texel_offset", C.c_uint64)]
 
 
 class Light(C.Structure):
@@ -93,6 +99,7 @@ class SceneDesc(C.Structure):
                 ("n_light_tri_area", C.c_uint32), ("n_light_tri_cdf", C.c_uint32),
                 ("world_bound", C.c_float * 6), ("camera", Camera), ("film", FilmDesc),
                 ("setting", RenderSetting), ("textures", C.POINTER(Texture)), ("n_textures", C.c_uint32),
+                ("image_levels", C.POINTER(ImageLevel)), ("n_image_levels", C.c_uint32),
                 ("image_texels", C.POINTER(C.c_float)), ("n_image_texels", C.c_uint64),
                 ("light_dist", C.POINTER(C.c_float)), ("n_light_dist", C.c_uint64)]
 

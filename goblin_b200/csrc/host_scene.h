@@ -24,6 +24,7 @@ struct gb_scene {
     std::vector<float> lightPower, lightCdf;
     std::vector<float> lightTriArea, lightTriCdf; // mesh emitters: per-face areas and their CDF
     std::vector<float> imageTexels, lightDist;    // image based lights: level-0 radiance, CDF2D tables
+    std::vector<gb_image_level> imageLevels;      // image textures: MIPMap pyramids in imageTexels
     float worldBound[6] = {0, 0, 0, 0, 0, 0};
     gb_camera camera{};
     gb_film_desc film{};

@@ -470,6 +470,55 @@ struct Loader {
         }
     }
 
+    // ImageTexture<T>::getMIPMap + convertTexel (src/GoblinTexture.cpp:454-503): one pyramid per
+    // (format, file, gamma, channel); max_anisotropy only matters to the lookup.
+    std::map<std::string, std::pair<int, int>> imagePyramids; // key -> (first level, level count)
+    void loadImagePyramid(const std::string& filePath, bool isFloat, float gamma, int channel, gb_texture* t) {
+        std::string key = (isFloat ? "f|" : "c|") + filePath + "|" + std::to_string(channel) + "|";
+        key.append(reinterpret_cast<const char*>(&gamma), 4);
+        auto it = imagePyramids.find(key);
+        if (it == imagePyramids.end()) {
+            int w = 0, h = 0;
+            std::vector<float> rgba;
+            std::string ierr;
+            if (!loadEXR(filePath, &w, &h, &rgba, &ierr)) {
+                std::cerr << ierr << std::endl << "error loading image file " << filePath << std::endl;
+                w = h = 1;
+                rgba = {1.0f, 0.0f, 1.0f, 1.0f}; // Color::Magenta
+            }
+            auto powG = [&](float v) { return (float)::pow((double)v, (double)gamma); }; // pow(float, float) binds to the double overload there
+            for (size_t i = 0; i < (size_t)w * h; ++i) {
+                float* c = &rgba[4 * i];
+                if (isFloat) { // ImageTexture<float>::convertTexel: always through pow
+                    float v = channel == 4 ? 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2] : c[channel];
+                    v = powG(v);
+                    c[0] = c[1] = c[2] = v;
+                    c[3] = 1.0f;
+                } else { // ImageTexture<Color>::convertTexel
+                    float r = c[0], g = c[1], b = c[2], a = c[3];
+                    if (channel != 4) { r = g = b = c[channel]; a = 1.0f; } // Color(float): alpha 1
+                    c[0] = gamma == 1.0f ? r : powG(r);
+                    c[1] = gamma == 1.0f ? g : powG(g);
+                    c[2] = gamma == 1.0f ? b : powG(b);
+                    c[3] = a;
+                }
+            }
+            std::vector<MipLevel> pyramid;
+            buildMipmap(std::move(rgba), w, h, &pyramid);
+            const int first = (int)out->imageLevels.size();
+            for (const MipLevel& l : pyramid) {
+                gb_image_level gl{};
+                gl.width = l.width; gl.height = l.height;
+                gl.texel_offset = out->imageTexels.size() / 4;
+                out->imageLevels.push_back(gl);
+                out->imageTexels.insert(out->imageTexels.end(), l.rgba.begin(), l.rgba.end());
+            }
+            it = imagePyramids.emplace(key, std::make_pair(first, (int)pyramid.size())).first;
+        }
+        t->first_level = it->second.first;
+        t->n_levels = it->second.second;
+    }
+
     // createTextures, src/GoblinContextLoader.cpp:246-303: file order, children resolved by name at
     // creation (so only earlier textures are visible), first definition of a name wins
     bool createTextures(const JsonValue& root) {
@@ -484,13 +533,36 @@ struct Loader {
                 continue;
             }
             const bool isFloat = format == "float";
-            if (type == "image") {
-                err = "texture '" + name + "' of type 'image' is outside the accelerated path "
-                    "(constant, checkerboard and scale textures only)";
-                return false;
-            }
             gb_texture t{};
-            if (type == "checkerboard") { // createFloat/ColorCheckerboardTexture
+            if (type == "image") { // createFloat/ColorImageTexture + ImageTexture::getMIPMap
+                t.type = GB_TEX_IMAGE;
+                t.is_float = isFloat ? 1 : 0;
+                t.child[0] = t.child[1] = -1;
+                readMapping(p, &t);
+                std::string filePath = resolvePath(p.getString("file"));
+                std::string filterStr = p.getString("filter", "nearest");
+                if (filterStr == "nearest") t.image_filter = GB_FILTER_NEAREST;
+                else if (filterStr == "bilinear") t.image_filter = GB_FILTER_BILINEAR;
+                else if (filterStr == "trilinear") t.image_filter = GB_FILTER_TRILINEAR;
+                else if (filterStr == "EWA") t.image_filter = GB_FILTER_EWA;
+                else { std::cerr << "unrecognize filter: " << filterStr << std::endl; t.image_filter = GB_FILTER_NEAREST; }
+                std::string addressStr = p.getString("address", "repeat");
+                if (addressStr == "repeat") t.address_mode = GB_ADDRESS_REPEAT;
+                else if (addressStr == "clamp") t.address_mode = GB_ADDRESS_CLAMP;
+                else if (addressStr == "border") t.address_mode = GB_ADDRESS_BORDER;
+                else { std::cerr << "unrecognize address mode: " << addressStr << std::endl; t.address_mode = GB_ADDRESS_REPEAT; }
+                float gamma = p.getFloat("gamma", 1.0f);
+                std::string channelStr = p.getString("channel", "All");
+                int channel = 4; // ChannelAll
+                if (channelStr == "R") channel = 0;
+                else if (channelStr == "G") channel = 1;
+                else if (channelStr == "B") channel = 2;
+                else if (channelStr == "A") channel = 3;
+                else if (channelStr != "All") std::cerr << "unrecognize channel: " << channelStr << std::endl;
+                // the colour variant never forwards max_anisotropy (src/GoblinTexture.cpp:739-744): default 10
+                t.max_anisotropy = isFloat ? p.getFloat("max_anisotropy", 10.0f) : 10.0f;
+                loadImagePyramid(filePath, isFloat, gamma, channel, &t);
+            } else if (type == "checkerboard") { // createFloat/ColorCheckerboardTexture
                 t.type = GB_TEX_CHECKERBOARD;
                 t.is_float = isFloat ? 1 : 0;
                 readMapping(p, &t);
@@ -926,6 +998,8 @@ void gb_scene::fillDesc(gb_scene_desc* d) const {
     d->camera = camera;
     d->film = film;
     d->setting = setting;
+    d->image_levels = imageLevels.data();
+    d->n_image_levels = (uint32_t)imageLevels.size();
     d->image_texels = imageTexels.data();
     d->n_image_texels = imageTexels.size() / 4;
     d->light_dist = lightDist.data();

@@ -130,9 +130,19 @@ typedef struct gb_material {
  * ray's uv differentials), scale = float texture x texture.  Children are
  * indices of EARLIER entries of the table (textures are created in file
  * order and look their children up by name at creation,
- * src/GoblinContextLoader.cpp:246-303).  Image textures are not supported. */
-enum { GB_TEX_CONSTANT = 0, GB_TEX_CHECKERBOARD = 1, GB_TEX_SCALE = 2 };
+ * src/GoblinContextLoader.cpp:246-303).  Image textures (:431-503) read an
+ * OpenEXR file into a MIPMap pyramid. */
+enum { GB_TEX_CONSTANT = 0, GB_TEX_CHECKERBOARD = 1, GB_TEX_SCALE = 2, GB_TEX_IMAGE = 3 };
 enum { GB_MAPPING_UV = 0, GB_MAPPING_SPHERICAL = 1 };
+/* image textures (src/GoblinTexture.h:12-31): "filter" nearest / bilinear / trilinear / EWA,
+ * "address" repeat / clamp / border */
+enum { GB_FILTER_NEAREST = 0, GB_FILTER_BILINEAR = 1, GB_FILTER_TRILINEAR = 2, GB_FILTER_EWA = 3 };
+enum { GB_ADDRESS_REPEAT = 0, GB_ADDRESS_CLAMP = 1, GB_ADDRESS_BORDER = 2 };
+/* One level of a MIPMap pyramid (src/GoblinTexture.cpp:39-71) in image_texels. */
+typedef struct gb_image_level {
+    int32_t width, height;
+    uint64_t texel_offset; /* first RGBA texel (float4 units) in image_texels */
+} gb_image_level;
 typedef struct gb_texture {
     int32_t type;          /* GB_TEX_*                                         */
     int32_t is_float;      /* float texture: value[0] only                     */
@@ -143,6 +153,13 @@ typedef struct gb_texture {
     float map_scale[2];    /* UVMapping                                        */
     float map_offset[2];
     float to_tex[12];      /* SphericalMapping: world -> texture space, 3x4    */
+    /* image texture: the pyramid of its (file, gamma, channel) after convertTexel;
+     * float images keep their value in every colour channel */
+    int32_t image_filter;  /* GB_FILTER_*                                      */
+    int32_t address_mode;  /* GB_ADDRESS_*                                     */
+    float max_anisotropy;  /* EWA                                              */
+    int32_t first_level;   /* index of level 0 in gb_scene_desc.image_levels   */
+    int32_t n_levels;
 } gb_texture;
 
 typedef struct gb_light {
@@ -240,7 +257,9 @@ typedef struct gb_scene_desc {
     gb_render_setting setting;
     const gb_texture* textures;     /* only entries materials reach are read  */
     uint32_t n_textures;
-    const float* image_texels;      /* image based lights: RGBA float texels  */
+    const gb_image_level* image_levels; /* image textures: pyramid levels     */
+    uint32_t n_image_levels;
+    const float* image_texels;      /* image based lights / textures: RGBA float texels */
     uint64_t n_image_texels;        /* in texels (4 floats each)              */
     const float* light_dist;        /* image based lights: sampling tables    */
     uint64_t n_light_dist;

@@ -608,9 +608,132 @@ struct Oracle {
         float xHalf = 0.5f * x;
         return (float)floor(xHalf) + 2.0f * std::max(xHalf - (float)floor(xHalf) - 0.5f, 0.0f);
     }
+    // ---- image textures: MIPMap<T> lookups, src/GoblinTexture.cpp:10-37,82-288
+    V3 imgTexel(const gb_texture& t, int level, int s, int tt) const { // ImageBuffer::texel
+        const gb_image_level& im = d->image_levels[t.first_level + level];
+        if (t.address_mode == GB_ADDRESS_CLAMP) {
+            s = std::min(std::max(s, 0), im.width - 1);
+            tt = std::min(std::max(s, 0), im.height - 1); // sic: the reference clamps s into t
+        } else if (t.address_mode == GB_ADDRESS_BORDER) {
+            if (s < 0 || tt < 0 || s >= im.width || tt >= im.height) return V3();
+        } else {
+            s = s % im.width;
+            tt = tt % im.height;
+            if (s < 0) s += im.width;
+            if (tt < 0) tt += im.height;
+        }
+        const float* c = d->image_texels + 4 * ((size_t)im.texel_offset + (size_t)tt * im.width + s);
+        return V3(c[0], c[1], c[2]);
+    }
+    V3 imgBilinear(const gb_texture& t, int level, float s, float tt) const { // MIPMap::lookup(level, s, t, m)
+        // the reference clamps to [0, mLevelsNum] and then indexes one past the pyramid at the top;
+        // product and oracle clamp to the last level
+        level = std::min(std::max(level, 0), t.n_levels - 1);
+        const gb_image_level& im = d->image_levels[t.first_level + level];
+        float sRes = s * im.width - 0.5f;
+        float tRes = tt * im.height - 0.5f;
+        int s0 = floorInt(sRes);
+        float ds = sRes - (float)s0;
+        int t0 = floorInt(tRes);
+        float dt = tRes - (float)t0;
+        return (1.0f - ds) * (1.0f - dt) * imgTexel(t, level, s0, t0) + (ds) * (1.0f - dt) * imgTexel(t, level, s0 + 1, t0) +
+            (1.0f - ds) * (dt) * imgTexel(t, level, s0, t0 + 1) + (ds) * (dt) * imgTexel(t, level, s0 + 1, t0 + 1);
+    }
+    // log2 of a float binds to the float overload in the reference's translation units (sqrt, pow,
+    // sin, acos, atan2, exp and floor bind to the double ones)
+    V3 imgTrilinear(const gb_texture& t, float s, float tt, float width) const {
+        float level = t.n_levels - 1 + log2f(std::max(width, 1e-8f));
+        int iLevel = floorInt(level);
+        if (iLevel < 0) return imgBilinear(t, 0, s, tt);
+        if (iLevel >= t.n_levels - 1) return imgBilinear(t, t.n_levels - 1, s, tt);
+        float delta = level - (float)iLevel;
+        return (1.0f - delta) * imgBilinear(t, iLevel, s, tt) + (delta) * imgBilinear(t, iLevel + 1, s, tt);
+    }
+    V3 imgEWA(const gb_texture& t, int level, float s, float tt, float A, float B, float C) const { // MIPMap::EWA
+        const gb_image_level& im = d->image_levels[t.first_level + level];
+        float sRes = (float)im.width;
+        float tRes = (float)im.height;
+        s = s * im.width - 0.5f;
+        tt = tt * im.height - 0.5f;
+        A = A / (sRes * sRes);
+        B = B / (sRes * tRes);
+        C = C / (tRes * tRes);
+        float invDet = 1.0f / (-B * B + 4.0f * A * C);
+        float offsetS = 2.0f * (float)sqrt(C * invDet);
+        float offsetT = 2.0f * (float)sqrt(A * invDet);
+        int s0 = (int)ceil(s - offsetS);
+        int s1 = floorInt(s + offsetS);
+        int t0 = (int)ceil(tt - offsetT);
+        int t1 = floorInt(tt + offsetT);
+        float weightSum = 0.0f;
+        V3 result;
+        for (int is = s0; is <= s1; ++is) {
+            for (int it = t0; it <= t1; ++it) {
+                float ss = is - s;
+                float tt2 = it - tt;
+                float r2 = A * ss * ss + B * ss * tt2 + C * tt2 * tt2;
+                if (r2 <= 1.0f) {
+                    size_t lutIndex = (size_t)floorInt(r2 * 128);
+                    size_t li = std::min(lutIndex, (size_t)127);
+                    float r2l = float(li) / float(127); // initEWALut: expf(-2 r2) - expf(-2)
+                    float weight = expf(-2.0f * r2l) - expf(-2.0f);
+                    result = result + imgTexel(t, level, is, it) * weight;
+                    weightSum += weight;
+                }
+            }
+        }
+        if (weightSum > 0.0f) {
+            // Color::operator/=(float) multiplies by the reciprocal; MIPMap<float> divides
+            result = t.is_float ? V3(result.x / weightSum, result.y / weightSum, result.z / weightSum) : result / weightSum;
+        } else {
+            result = imgTexel(t, level, (int)s, (int)tt);
+        }
+        return result;
+    }
+    V3 imgLookup(const gb_texture& t, const TexCoord& tc) const { // MIPMap::lookup(tc, filter, address)
+        float s = tc.s, tt = tc.t;
+        if (t.image_filter == GB_FILTER_BILINEAR || t.image_filter == GB_FILTER_TRILINEAR) {
+            float width = std::max(std::max(fabsf(tc.dsdx), fabsf(tc.dtdx)), std::max(fabsf(tc.dsdy), fabsf(tc.dtdy)));
+            if (t.image_filter == GB_FILTER_TRILINEAR) return imgTrilinear(t, s, tt, width);
+            float level = t.n_levels - 1 + log2f(std::max(width, 1e-8f));
+            return imgBilinear(t, floorInt(level + 0.5f), s, tt); // roundInt
+        }
+        if (t.image_filter != GB_FILTER_EWA) return imgBilinear(t, 0, s, tt); // lookupNearest
+        float ds0 = tc.dsdx, dt0 = tc.dtdx, ds1 = tc.dsdy, dt1 = tc.dtdy; // lookupEWA
+        float majorLength = (float)sqrt(ds0 * ds0 + dt0 * dt0);
+        float minorLength = (float)sqrt(ds1 * ds1 + dt1 * dt1);
+        if (majorLength < minorLength) {
+            std::swap(ds0, ds1);
+            std::swap(dt0, dt1);
+            std::swap(majorLength, minorLength);
+        }
+        if (minorLength * t.max_anisotropy < majorLength && minorLength > 0.0f) {
+            float scale = majorLength / (minorLength * t.max_anisotropy);
+            minorLength *= scale;
+            ds1 *= scale;
+            dt1 *= scale;
+        }
+        float A = dt0 * dt0 + dt1 * dt1;
+        float B = -2.0f * (ds0 * dt0 + ds1 * dt1);
+        float C = ds0 * ds0 + ds1 * ds1;
+        float F = A * C - 0.25f * B * B;
+        if (minorLength == 0.0f || F <= 0.0f) return imgTrilinear(t, s, tt, minorLength);
+        float invF = 1.0f / F;
+        A *= invF;
+        B *= invF;
+        C *= invF;
+        float level = t.n_levels - 1 + log2f(minorLength);
+        int iLevel = floorInt(level);
+        if (iLevel < 0) return imgBilinear(t, 0, s, tt);
+        if (iLevel >= t.n_levels - 1) return imgBilinear(t, t.n_levels - 1, s, tt);
+        float delta = level - (float)iLevel;
+        return (1.0f - delta) * imgEWA(t, iLevel, s, tt, A, B, C) + (delta) * imgEWA(t, iLevel + 1, s, tt, A, B, C);
+    }
+
     // Texture<T>::lookup; float textures live in .x
     V3 texLookup(int index, const Frag& f) const {
         const gb_texture& t = d->textures[index];
+        if (t.type == GB_TEX_IMAGE) return imgLookup(t, mapTexture(t, f)); // ImageTexture::lookup
         if (t.type == GB_TEX_SCALE) { // mScale->lookup(f) * mTexture->lookup(f)
             float sc = texLookup(t.child[1], f).x;
             return texLookup(t.child[0], f) * sc;

