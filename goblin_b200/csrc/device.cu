@@ -1015,7 +1015,18 @@ bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, s
                 if (!ok) return;
                 if (g.type == GB_TEX_CHECKERBOARD && g.mapping != GB_MAPPING_UV && g.mapping != GB_MAPPING_SPHERICAL) { ok = false; return; }
                 --depth; // two values in, one out
-            } else if (g.type == GB_TEX_CONSTANT) {
+            } else if (g.type == GB_TEX_CONSTANT || g.type == GB_TEX_IMAGE) {
+                if (g.type == GB_TEX_IMAGE) {
+                    if (g.n_levels < 1 || g.first_level < 0 || (uint64_t)g.first_level + (uint64_t)g.n_levels > d->n_image_levels ||
+                        g.image_filter < GB_FILTER_NEAREST || g.image_filter > GB_FILTER_EWA ||
+                        g.address_mode < GB_ADDRESS_REPEAT || g.address_mode > GB_ADDRESS_BORDER ||
+                        (g.mapping != GB_MAPPING_UV && g.mapping != GB_MAPPING_SPHERICAL)) { ok = false; return; }
+                    for (int l = 0; l < g.n_levels; ++l) {
+                        const gb_image_level& il = d->image_levels[g.first_level + l];
+                        if (il.width < 1 || il.height < 1 || il.texel_offset > 0xffffffffull ||
+                            il.texel_offset + (uint64_t)il.width * (uint64_t)il.height > d->n_image_texels) { ok = false; return; }
+                    }
+                }
                 ++depth;
                 maxDepth = std::max(maxDepth, depth);
             } else {
@@ -1132,6 +1143,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oMatTex = ar.take(hasTextures ? 16 * (size_t)d->n_materials : 0);
     const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
     const size_t oTexNodes = ar.take(hasTextures ? 16 * (size_t)kTexNodeVec4 * d->n_textures : 0);
+    const size_t oTexLevels = ar.take(hasTextures ? 16 * (size_t)d->n_image_levels : 0);
     const size_t oImageTexels = ar.take(16 * (size_t)d->n_image_texels);
     const size_t oLightDist = ar.take(4 * (size_t)d->n_light_dist);
     const size_t oLights = ar.take(sizeof(DeviceLight) * (size_t)d->n_lights);
@@ -1262,15 +1274,24 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             float4* q = tn + (size_t)kTexNodeVec4 * t;
             float tb;
             std::memcpy(&tb, &gt.type, 4);
-            q[0] = make_float4(gt.value[0], gt.value[1], gt.value[2], tb);
-            int opts[4] = {gt.filter, gt.mapping, 0, 0};
+            q[0] = make_float4(gt.type == GB_TEX_IMAGE ? gt.max_anisotropy : gt.value[0], gt.value[1], gt.value[2], tb);
+            int opts[4] = {gt.type == GB_TEX_IMAGE ? gt.image_filter : gt.filter, gt.mapping, gt.address_mode, gt.first_level};
             std::memcpy(&q[1], opts, 16);
+            int img[4] = {gt.n_levels, gt.is_float, 0, 0};
+            std::memcpy(&q[6], img, 16);
             q[2] = make_float4(gt.map_scale[0], gt.map_scale[1], gt.map_offset[0], gt.map_offset[1]);
             for (int r = 0; r < 3; ++r) q[3 + r] = make_float4(gt.to_tex[4 * r], gt.to_tex[4 * r + 1], gt.to_tex[4 * r + 2], gt.to_tex[4 * r + 3]);
         }
     }
     if (d->n_image_texels) std::memcpy(H + oImageTexels, d->image_texels, 16 * (size_t)d->n_image_texels);
     if (d->n_light_dist) std::memcpy(H + oLightDist, d->light_dist, 4 * (size_t)d->n_light_dist);
+    if (hasTextures) {
+        int4* tl = reinterpret_cast<int4*>(H + oTexLevels);
+        for (uint32_t l = 0; l < d->n_image_levels; ++l) {
+            const gb_image_level& il = d->image_levels[l];
+            tl[l] = make_int4(il.width, il.height, (int)(uint32_t)il.texel_offset, 0);
+        }
+    }
     DeviceLight* lights = reinterpret_cast<DeviceLight*>(H + oLights);
     bool hasMeshLight = false, hasEnvLight = false;
     for (uint32_t l = 0; l < d->n_lights; ++l) {
@@ -1366,6 +1387,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.matTex = hasTextures ? reinterpret_cast<const int4*>(D + oMatTex) : nullptr;
     sc.texProg = hasTextures ? reinterpret_cast<const unsigned int*>(D + oTexProg) : nullptr;
     sc.texNodes = hasTextures ? reinterpret_cast<const float4*>(D + oTexNodes) : nullptr;
+    sc.texLevels = hasTextures ? reinterpret_cast<const int4*>(D + oTexLevels) : nullptr;
     sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
     sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);
     sc.lightCdf = reinterpret_cast<const float*>(D + oLightCdf);

@@ -65,7 +65,8 @@ struct DeviceScene {
     // procedural textures (texture.cuh); all three null when no material slot is textured
     const int4* matTex;         // per material: program offset in texProg of kd, kt, exponent (0 = constant), 0
     const unsigned int* texProg; // postfix programs: [length, node index ...]; entry 0 is unused
-    const float4* texNodes;     // 6 per texture: value | type, options, uv mapping, 3 rows world -> texture
+    const float4* texNodes;     // 7 per texture: value | type, options, uv mapping, 3 rows world -> texture, image info
+    const int4* texLevels;      // image textures: (width, height, first texel in imageTexels, 0) per pyramid level
     const DeviceLight* lights;
     const float* lightPower;    // CDF1D::mFunction
     const float* lightCdf;      // CDF1D::mCDF (nLights + 1)

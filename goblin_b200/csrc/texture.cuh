@@ -12,7 +12,7 @@
 namespace gb {
 
 constexpr int kTexStack = 8;     // value stack of the postfix evaluation (checked at upload)
-constexpr int kTexNodeVec4 = 6;  // float4 per texture node
+constexpr int kTexNodeVec4 = 7;  // float4 per texture node
 
 // What the textures read of the Fragment beyond buildFragment's p / n / dpdu.
 struct TexFrag {
@@ -168,9 +168,134 @@ __device__ __forceinline__ void pointToST(float4 r0, float4 r1, float4 r2, float
     *t = theta * GB_INV_PI;
 }
 
+// ---- image textures: MIPMap<T> lookups (GoblinTexture.cpp:10-37,82-288).  Node record of an image
+// texture: [0] = (max anisotropy, -, -, type), [1] int bits = (filter, mapping, address mode, first level),
+// [2] = uv scale / offset, [3..5] = spherical rows with int bits (level count, is_float) in [5].w ... kept in
+// TexImage below.  Level table: int4 (width, height, first texel, 0) per level.
+struct TexImage {
+    const int4* levels;     // this texture's level 0
+    const float4* texels;
+    int nLevels, address;
+    bool isFloat;
+};
+__device__ __forceinline__ float3 imgTexel(const TexImage& im, int level, int s, int t) { // ImageBuffer::texel
+    const int4 l = __ldg(im.levels + level);
+    if (im.address == GB_ADDRESS_CLAMP) {
+        s = min(max(s, 0), l.x - 1);
+        t = min(max(s, 0), l.y - 1); // sic: the reference clamps s into t
+    } else if (im.address == GB_ADDRESS_BORDER) {
+        if (s < 0 || t < 0 || s >= l.x || t >= l.y) return make3(0.0f, 0.0f, 0.0f);
+    } else {
+        s = s % l.x;
+        t = t % l.y;
+        if (s < 0) s += l.x;
+        if (t < 0) t += l.y;
+    }
+    const float4 c = __ldg(im.texels + (size_t)(unsigned int)l.z + (size_t)t * l.x + s);
+    return make3(c.x, c.y, c.z);
+}
+__device__ __noinline__ float3 imgBilinear(const TexImage& im, int level, float s, float t) { // MIPMap::lookup(level, s, t, m)
+    level = min(max(level, 0), im.nLevels - 1); // the reference indexes one past the pyramid at the top
+    const int4 l = __ldg(im.levels + level);
+    const float sRes = s * l.x - 0.5f;
+    const float tRes = t * l.y - 0.5f;
+    const int s0 = floorInt(sRes);
+    const float ds = sRes - (float)s0;
+    const int t0 = floorInt(tRes);
+    const float dt = tRes - (float)t0;
+    return (1.0f - ds) * (1.0f - dt) * imgTexel(im, level, s0, t0) + (ds) * (1.0f - dt) * imgTexel(im, level, s0 + 1, t0) +
+        (1.0f - ds) * (dt) * imgTexel(im, level, s0, t0 + 1) + (ds) * (dt) * imgTexel(im, level, s0 + 1, t0 + 1);
+}
+__device__ __forceinline__ float3 imgTrilinear(const TexImage& im, float s, float t, float width) {
+    const float level = im.nLevels - 1 + log2f(fmaxf(width, 1e-8f));
+    const int iLevel = floorInt(level);
+    if (iLevel < 0) return imgBilinear(im, 0, s, t);
+    if (iLevel >= im.nLevels - 1) return imgBilinear(im, im.nLevels - 1, s, t);
+    const float delta = level - (float)iLevel;
+    return (1.0f - delta) * imgBilinear(im, iLevel, s, t) + (delta) * imgBilinear(im, iLevel + 1, s, t);
+}
+__device__ __noinline__ float3 imgEWA(const TexImage& im, int level, float s, float t, float A, float B, float C) {
+    const int4 l = __ldg(im.levels + level);
+    const float sRes = (float)l.x, tRes = (float)l.y;
+    s = s * l.x - 0.5f;
+    t = t * l.y - 0.5f;
+    A = A / (sRes * sRes);
+    B = B / (sRes * tRes);
+    C = C / (tRes * tRes);
+    const float invDet = 1.0f / (-B * B + 4.0f * A * C);
+    const float offsetS = 2.0f * sqrtf(C * invDet);
+    const float offsetT = 2.0f * sqrtf(A * invDet);
+    const int s0 = (int)ceilf(s - offsetS), s1 = floorInt(s + offsetS);
+    const int t0 = (int)ceilf(t - offsetT), t1 = floorInt(t + offsetT);
+    float weightSum = 0.0f;
+    float3 result = make3(0.0f, 0.0f, 0.0f);
+    for (int is = s0; is <= s1; ++is) {
+        for (int it = t0; it <= t1; ++it) {
+            const float ss = is - s, tt = it - t;
+            const float r2 = A * ss * ss + B * ss * tt + C * tt * tt;
+            if (r2 <= 1.0f) {
+                const int lutIndex = min(floorInt(r2 * 128.0f), 127);
+                // MIPMap::initEWALut: expf(-2 r2') - expf(-2) on 128 entries
+                const float weight = expf(-2.0f * ((float)lutIndex / 127.0f)) - expf(-2.0f);
+                result = result + imgTexel(im, level, is, it) * weight;
+                weightSum += weight;
+            }
+        }
+    }
+    if (weightSum > 0.0f) {
+        // Color::operator/=(float) multiplies by the reciprocal; MIPMap<float> divides
+        if (im.isFloat) result = make3(result.x / weightSum, result.y / weightSum, result.z / weightSum);
+        else result = result * (1.0f / weightSum);
+    } else {
+        result = imgTexel(im, level, (int)s, (int)t);
+    }
+    return result;
+}
+// MIPMap::lookup(tc, filter, address)
+__device__ __noinline__ float3 imgLookup(const TexImage& im, int filter, float maxAniso, float s, float t, float dsdx,
+    float dtdx, float dsdy, float dtdy) {
+    if (filter == GB_FILTER_BILINEAR || filter == GB_FILTER_TRILINEAR) {
+        const float width = fmaxf(fmaxf(fabsf(dsdx), fabsf(dtdx)), fmaxf(fabsf(dsdy), fabsf(dtdy)));
+        if (filter == GB_FILTER_TRILINEAR) return imgTrilinear(im, s, t, width);
+        const float level = im.nLevels - 1 + log2f(fmaxf(width, 1e-8f));
+        return imgBilinear(im, floorInt(level + 0.5f), s, t);
+    }
+    if (filter != GB_FILTER_EWA) return imgBilinear(im, 0, s, t); // lookupNearest
+    float ds0 = dsdx, dt0 = dtdx, ds1 = dsdy, dt1 = dtdy; // lookupEWA
+    float majorLength = sqrtf(ds0 * ds0 + dt0 * dt0);
+    float minorLength = sqrtf(ds1 * ds1 + dt1 * dt1);
+    if (majorLength < minorLength) {
+        float x = ds0; ds0 = ds1; ds1 = x;
+        x = dt0; dt0 = dt1; dt1 = x;
+        x = majorLength; majorLength = minorLength; minorLength = x;
+    }
+    if (minorLength * maxAniso < majorLength && minorLength > 0.0f) {
+        const float scale = majorLength / (minorLength * maxAniso);
+        minorLength *= scale;
+        ds1 *= scale;
+        dt1 *= scale;
+    }
+    float A = dt0 * dt0 + dt1 * dt1;
+    float B = -2.0f * (ds0 * dt0 + ds1 * dt1);
+    float C = ds0 * ds0 + ds1 * ds1;
+    const float F = A * C - 0.25f * B * B;
+    if (minorLength == 0.0f || F <= 0.0f) return imgTrilinear(im, s, t, minorLength);
+    const float invF = 1.0f / F;
+    A *= invF;
+    B *= invF;
+    C *= invF;
+    const float level = im.nLevels - 1 + log2f(minorLength);
+    const int iLevel = floorInt(level);
+    if (iLevel < 0) return imgBilinear(im, 0, s, t);
+    if (iLevel >= im.nLevels - 1) return imgBilinear(im, im.nLevels - 1, s, t);
+    const float delta = level - (float)iLevel;
+    return (1.0f - delta) * imgEWA(im, iLevel, s, t, A, B, C) + (delta) * imgEWA(im, iLevel + 1, s, t, A, B, C);
+}
+
 // Texture<T>::lookup of the texture a program ends in.  prog: [length, node, node, ...] in postfix
-// order; node record: [0] value rgb | type, [1] int bits: filter, mapping, -, -,
-// [2] uv scale.xy, offset.xy, [3..5] spherical world -> texture rows.  Float textures use .x.
+// order; node record: [0] value rgb (image: max anisotropy) | type, [1] int bits: filter, mapping, image
+// address mode, image first level, [2] uv scale.xy, offset.xy, [3..5] spherical world -> texture rows,
+// [6] int bits: image level count, is_float.  Float textures use .x.
 __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int progOffset, const TexFrag& f) {
     float3 stack[kTexStack];
     int sp = 0;
@@ -185,9 +310,7 @@ __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int p
         } else if (type == GB_TEX_SCALE) { // mScale->lookup(f) * mTexture->lookup(f): children = texture, scale
             const float scale = stack[--sp].x;
             stack[sp - 1] = stack[sp - 1] * scale;
-        } else { // CheckboardTexture<T>::lookup, GoblinTexture.cpp:377-416: children = texture1, texture2
-            const float3 T2 = stack[--sp];
-            const float3 T1 = stack[sp - 1];
+        } else { // checkerboard (two children on the stack) or image: both start from the texture mapping
             const int4 opt = __ldg(reinterpret_cast<const int4*>(node + 1));
             float s, t, dsdx, dtdx, dsdy, dtdy;
             if (opt.y == GB_MAPPING_SPHERICAL) { // SphericalMapping::map
@@ -209,6 +332,15 @@ __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int p
                 dsdx = m.x * f.dudx; dtdx = m.y * f.dvdx;
                 dsdy = m.x * f.dudy; dtdy = m.y * f.dvdy;
             }
+            if (type == GB_TEX_IMAGE) { // ImageTexture<T>::lookup, GoblinTexture.cpp:447-452
+                const int4 img = __ldg(reinterpret_cast<const int4*>(node + 6)); // level count, is_float, -, -
+                TexImage im{sc.texLevels + opt.w, sc.imageTexels, img.x, opt.z, img.y != 0};
+                stack[sp++] = imgLookup(im, opt.x, head.x, s, t, dsdx, dtdx, dsdy, dtdy);
+                continue;
+            }
+            // CheckboardTexture<T>::lookup, GoblinTexture.cpp:377-416: children = texture1, texture2
+            const float3 T2 = stack[--sp];
+            const float3 T1 = stack[sp - 1];
             const bool even = (floorInt(s) + floorInt(t)) % 2 == 0;
             float3 r = even ? T1 : T2;
             if (opt.x) {
