@@ -374,6 +374,7 @@ def main():
         ctx.upload_scene(scene)
     film_ptr, film_floats = ctx.film_device_ptr()
     film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
+    host_buf = np.zeros((scene.desc.film.yres, scene.desc.film.xres, 4), np.float32)
     barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
@@ -382,7 +383,7 @@ def main():
         film_ptr, film_floats = ctx.film_device_ptr()
         film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
         step(10000 + i, flush_l2=False)
-        host_film = ctx.film_download()
+        host_film = ctx.film_download(out=host_buf)  # the caller's film buffer, reused like Film::mPixels
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - w0) * 1e3
     te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")

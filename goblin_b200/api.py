@@ -390,9 +390,12 @@ class Context:
     def film_clear(self):
         check(lib().gb_film_clear(self._h))
 
-    def film_download(self):
+    def film_download(self, out=None):
+        """Film::mPixels as yres x xres x (r, g, b, weight); `out` reuses a caller-owned buffer."""
         f = self.scene.desc.film
-        out = np.zeros((f.yres, f.xres, 4), dtype=np.float32)
+        if out is None:
+            out = np.empty((f.yres, f.xres, 4), dtype=np.float32)
+        assert out.shape == (f.yres, f.xres, 4) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
         check(lib().gb_film_download(self._h, out.ctypes.data))
         return out
 

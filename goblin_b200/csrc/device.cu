@@ -16,6 +16,7 @@
 // No tensor cores, no TMA: traversal is a dependent gather of 32-byte nodes,
 // not a dense contraction (north_star).
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -712,7 +713,11 @@ struct gb_context {
     DeviceScene sc{};
     char* arenaDev = nullptr;   // every scene array lives in one device allocation ...
     char* arenaHost = nullptr;  // ... filled through one (pinned) staging buffer
-    size_t arenaCap = 0, uploadBytes = 0;
+    size_t arenaCap = 0, hostCap = 0, uploadBytes = 0;
+    int* deriveError = nullptr;      // device flag of the derive kernels (bad index in the scene arrays)
+    int* deriveErrorHost = nullptr;  // pinned
+    float* filmHost = nullptr;       // pinned staging for film downloads
+    size_t filmHostPixels = 0;
     bool arenaPinned = false;
     gb_render_setting setting{};
     int stackEntries = 0; // per-thread traversal stack entries this scene needs
@@ -761,6 +766,7 @@ void freeScene(gb_context* ctx) {
     ctx->arenaDev = nullptr;
     ctx->arenaHost = nullptr;
     ctx->arenaCap = 0;
+    ctx->hostCap = 0;
     if (ctx->film) cudaFree(ctx->film);
     ctx->film = nullptr;
     ctx->filmPixels = 0;
@@ -888,6 +894,8 @@ int gb_create(int device, gb_context** out) {
     GB_CUDA(cudaMalloc((void**)&ctx->traceHead, 64));
     GB_CUDA(cudaMalloc((void**)&ctx->stats, S_COUNT * sizeof(unsigned long long)));
     GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
+    GB_CUDA(cudaMalloc((void**)&ctx->deriveError, sizeof(int)));
+    GB_CUDA(cudaMallocHost((void**)&ctx->deriveErrorHost, sizeof(int)));
     *out = ctx;
     return GB_OK;
 }
@@ -901,6 +909,9 @@ int gb_destroy(gb_context* ctx) {
     cudaFree(ctx->ctr);
     cudaFree(ctx->traceHead);
     cudaFree(ctx->stats);
+    cudaFree(ctx->deriveError);
+    cudaFreeHost(ctx->deriveErrorHost);
+    if (ctx->filmHost) cudaFreeHost(ctx->filmHost);
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
@@ -975,23 +986,6 @@ inline uint32_t refOf(const gb_bvh_node* nodes, const uint32_t* pairIndex, uint3
     return REF_LEAF | REF_MULTI | node;
 }
 
-void fillPairs(const gb_bvh_node* nodes, uint32_t count, const uint32_t* pairIndex, float4* out) {
-    hostParallelFor(count, 1u << 16, [=](size_t b, size_t e) {
-        for (size_t i = b; i < e; ++i) {
-            const gb_bvh_node& nd = nodes[i];
-            if (nd.nprims != 0) continue;
-            const gb_bvh_node& l = nodes[i + 1];
-            const gb_bvh_node& r = nodes[nd.offset];
-            float4* q = out + 4 * (size_t)pairIndex[i];
-            q[0] = make_float4(l.bmin[0], l.bmin[1], l.bmin[2], l.bmax[0]);
-            q[1] = make_float4(l.bmax[1], l.bmax[2], r.bmin[0], r.bmin[1]);
-            q[2] = make_float4(r.bmin[2], r.bmax[0], r.bmax[1], r.bmax[2]);
-            uint32_t w[4] = {refOf(nodes, pairIndex, (uint32_t)i + 1), refOf(nodes, pairIndex, nd.offset), nd.axis, 0u};
-            std::memcpy(&q[3], w, 16);
-        }
-    });
-}
-
 // Postfix programs for the textured material slots: a texture's children come before it, so the
 // device evaluates a program left to right on a value stack.  Validates the part of the texture
 // table the materials reach (types, child indices pointing at EARLIER entries: no cycles, float
@@ -1055,6 +1049,72 @@ bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, s
     return true;
 }
 
+} // namespace (reopened below: kernels have external linkage)
+
+// Pair nodes from the reference's 32-byte nodes (fillPairs, on the device): one thread per node, interior
+// nodes write the 64-byte record of their two children at the pair index the host numbered them with.
+__global__ void k_derive_pairs(const float4* __restrict__ nodes, const unsigned int* __restrict__ pairIndex,
+    unsigned int count, float4* __restrict__ out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float4 n1 = __ldg(nodes + 2 * (size_t)i + 1);
+    const unsigned int word = __float_as_uint(n1.w); // nprims | axis << 8
+    if ((word & 0xffu) != 0u) return;
+    const unsigned int right = __float_as_uint(n1.z), left = i + 1;
+    auto refOfNode = [&](unsigned int node, float4 c1) -> unsigned int {
+        const unsigned int w = __float_as_uint(c1.w) & 0xffu;
+        if (w == 0u) return __ldg(pairIndex + node);
+        if (w == 1u) return REF_LEAF | __float_as_uint(c1.z);
+        return REF_LEAF | REF_MULTI | node;
+    };
+    const float4 l0 = __ldg(nodes + 2 * (size_t)left), l1 = __ldg(nodes + 2 * (size_t)left + 1);
+    const float4 r0 = __ldg(nodes + 2 * (size_t)right), r1 = __ldg(nodes + 2 * (size_t)right + 1);
+    float4* q = out + 4 * (size_t)__ldg(pairIndex + i);
+    q[0] = make_float4(l0.x, l0.y, l0.z, l0.w);
+    q[1] = make_float4(l1.x, l1.y, r0.x, r0.y);
+    q[2] = make_float4(r0.z, r0.w, r1.x, r1.y);
+    q[3] = make_float4(__uint_as_float(refOfNode(left, l1)), __uint_as_float(refOfNode(right, r1)),
+        __uint_as_float((word >> 8) & 0xffu), 0.0f);
+}
+
+// Triangle test records (p0, e1, e2, face) and shading records (vertex normals, uvs) in BVH leaf order,
+// one thread per leaf slot: e1 = p1 - p0, e2 = p2 - p0 are the reference's per-test subtractions
+// (src/GoblinTriangle.cpp:51-54), done once.  Index errors are reported through `error`.
+__global__ void k_derive_tris(const unsigned int* __restrict__ order, const unsigned int* __restrict__ triIndex,
+    const float* __restrict__ pos, const float* __restrict__ nrm, const float* __restrict__ uv, unsigned int triCount,
+    unsigned int vertCount, float4* __restrict__ triRec, float4* __restrict__ triShade, int* error) {
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= triCount) return;
+    const unsigned int face = __ldg(order + k);
+    if (face >= triCount) { *error = 1; return; }
+    const unsigned int v0 = __ldg(triIndex + 3 * (size_t)face), v1 = __ldg(triIndex + 3 * (size_t)face + 1),
+                       v2 = __ldg(triIndex + 3 * (size_t)face + 2);
+    if (v0 >= vertCount || v1 >= vertCount || v2 >= vertCount) { *error = 2; return; }
+    const float* p0 = pos + 3 * (size_t)v0;
+    const float* p1 = pos + 3 * (size_t)v1;
+    const float* p2 = pos + 3 * (size_t)v2;
+    const float p0x = __ldg(p0), p0y = __ldg(p0 + 1), p0z = __ldg(p0 + 2);
+    const float e1x = __ldg(p1) - p0x, e1y = __ldg(p1 + 1) - p0y, e1z = __ldg(p1 + 2) - p0z;
+    const float e2x = __ldg(p2) - p0x, e2y = __ldg(p2 + 1) - p0y, e2z = __ldg(p2 + 2) - p0z;
+    float4* r = triRec + 3 * (size_t)k;
+    r[0] = make_float4(p0x, p0y, p0z, e1x);
+    r[1] = make_float4(e1y, e1z, e2x, e2y);
+    r[2] = make_float4(e2z, __uint_as_float(face), 0.0f, 0.0f);
+    const float* n0 = nrm + 3 * (size_t)v0;
+    const float* n1 = nrm + 3 * (size_t)v1;
+    const float* n2 = nrm + 3 * (size_t)v2;
+    const float* t0 = uv + 2 * (size_t)v0;
+    const float* t1 = uv + 2 * (size_t)v1;
+    const float* t2 = uv + 2 * (size_t)v2;
+    float4* q = triShade + 4 * (size_t)k;
+    q[0] = make_float4(__ldg(n0), __ldg(n0 + 1), __ldg(n0 + 2), __ldg(n1));
+    q[1] = make_float4(__ldg(n1 + 1), __ldg(n1 + 2), __ldg(n2), __ldg(n2 + 1));
+    q[2] = make_float4(__ldg(n2 + 2), __ldg(t0), __ldg(t0 + 1), __ldg(t1));
+    q[3] = make_float4(__ldg(t1 + 1), __ldg(t2), __ldg(t2 + 1), 0.0f);
+}
+
+namespace {
+
 struct Arena { // offsets into the staging / device arena, 256-byte aligned
     size_t size = 0;
     size_t take(size_t bytes) {
@@ -1074,6 +1134,15 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const uint32_t nInst = d->n_instances;
     const gb_film_desc& f = d->film;
     if (f.xres <= 0 || f.yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad film resolution");
+    // GB_UPLOAD_TIMING=1 prints where the host time of an upload goes (e2e overhead analysis)
+    static const bool timing = std::getenv("GB_UPLOAD_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[gb_upload_scene] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     // ---- validate, measure tree depth (stack need), number the pair nodes
     int topDepth = 0, modelDepth = 0;
     std::vector<uint32_t> topPairIndex;
@@ -1117,20 +1186,25 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         const gb_instance& in = d->instances[id];
         if (in.model < 0 || (uint32_t)in.model >= d->n_models) return gb::failWith(GB_ERR_INVALID, "instance model out of range");
     }
+    lap("validate");
     // ---- arena layout
     Arena ar;
     const size_t oTopNodes = ar.take(32 * (size_t)d->n_top_nodes);
     const size_t oModelNodes = ar.take(32 * (size_t)d->n_model_nodes);
-    const size_t oTopPairs = ar.take(64 * (size_t)nTopPairs);
-    const size_t oModelPairs = ar.take(64 * (size_t)nModelPairs);
+    // what the derive kernels read (the reference's own arrays + the pair numbering): uploaded
+    const size_t oRawTopPairIdx = ar.take(4 * (size_t)d->n_top_nodes);
+    const size_t oRawModelPairIdx = ar.take(4 * (size_t)d->n_model_nodes);
+    const size_t oRawOrder = ar.take(4 * (size_t)d->n_tris);
+    const size_t oRawTriIndex = ar.take(12 * (size_t)d->n_tris);
+    const size_t oRawPos = ar.take(12 * (size_t)d->n_verts);
+    const size_t oRawNrm = ar.take(12 * (size_t)d->n_verts);
+    const size_t oRawUv = ar.take(8 * (size_t)d->n_verts);
     const size_t oInstToObject = ar.take(48 * (size_t)nInst);
     const size_t oInstToWorld = ar.take(48 * (size_t)nInst);
     const size_t oInstInfo = ar.take(16 * (size_t)nInst);
     const size_t oInstInfo2 = ar.take(16 * (size_t)nInst);
     const size_t oInstShade = ar.take(16 * (size_t)nInst);
-    const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
     const size_t oModelShade = ar.take(16 * (size_t)d->n_models);
-    const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
     const size_t oMaterials = ar.take(sizeof(DeviceMaterial) * (size_t)d->n_materials);
     // procedural textures: postfix programs of the textured material slots
     std::vector<int4> matTex(d->n_materials, make_int4(0, 0, 0, 0));
@@ -1152,81 +1226,66 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oLightTris = ar.take(96 * (size_t)d->n_light_tri_area);
     const size_t oLightTriCdf = ar.take(4 * (size_t)d->n_light_tri_cdf);
     const size_t oFilter = ar.take(4 * 256);
-    if (ar.size > ctx->arenaCap) {
+    // everything above crosses PCIe; the arrays below are derived from it on the device
+    // (k_derive_pairs, k_derive_tris): only the device arena holds them
+    const size_t uploadSize = ar.size;
+    const size_t oTopPairs = ar.take(64 * (size_t)nTopPairs);
+    const size_t oModelPairs = ar.take(64 * (size_t)nModelPairs);
+    const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
+    const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
+    if (ar.size > ctx->arenaCap) { // both arenas persist and only grow
         if (ctx->arenaDev) cudaFree(ctx->arenaDev);
-        if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
-        ctx->arenaDev = nullptr; ctx->arenaHost = nullptr; ctx->arenaCap = 0;
+        ctx->arenaDev = nullptr; ctx->arenaCap = 0;
         GB_CUDA(cudaMalloc((void**)&ctx->arenaDev, ar.size));
+        ctx->arenaCap = ar.size;
+    }
+    if (uploadSize > ctx->hostCap) {
+        if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
+        ctx->arenaHost = nullptr; ctx->hostCap = 0;
         void* hp = nullptr;
-        if (cudaMallocHost(&hp, ar.size) == cudaSuccess) { ctx->arenaPinned = true; }
+        if (cudaMallocHost(&hp, uploadSize) == cudaSuccess) { ctx->arenaPinned = true; }
         else {
             cudaGetLastError();
-            hp = std::malloc(ar.size);
+            hp = std::malloc(uploadSize);
             ctx->arenaPinned = false;
             if (!hp) return gb::failWith(GB_ERR_INVALID, "out of host memory for the staging arena");
         }
         ctx->arenaHost = static_cast<char*>(hp);
-        ctx->arenaCap = ar.size;
+        ctx->hostCap = uploadSize;
     }
     char* H = ctx->arenaHost;
+    lap("layout");
     // ---- fill the staging arena
     std::memcpy(H + oTopNodes, d->top_nodes, 32 * (size_t)d->n_top_nodes);
-    hostParallelFor(d->n_model_nodes, 1u << 18, [&](size_t b, size_t e) {
+    hostParallelFor(d->n_model_nodes, 1u << 15, [&](size_t b, size_t e) {
         std::memcpy(H + oModelNodes + 32 * b, d->model_nodes + b, 32 * (e - b));
     });
-    fillPairs(d->top_nodes, d->n_top_nodes, topPairIndex.data(), reinterpret_cast<float4*>(H + oTopPairs));
+    // the pair numbering of every interior node and the meshes' own arrays: the derive kernels turn
+    // them into pair nodes and leaf-order triangle records on the device
+    if (d->n_top_nodes) std::memcpy(H + oRawTopPairIdx, topPairIndex.data(), 4 * (size_t)d->n_top_nodes);
     const uint32_t topRootRef = d->n_top_nodes ? refOf(d->top_nodes, topPairIndex.data(), 0) : REF_NONE;
     std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE);
     int4* modelShade = reinterpret_cast<int4*>(H + oModelShade);
-    float4* triRec = reinterpret_cast<float4*>(H + oTriRec);
-    float4* triShade = reinterpret_cast<float4*>(H + oTriShade);
-    std::string fillError;
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
         modelShade[m] = make_int4((int)md.vert_offset, (int)md.tri_offset, (md.has_normal ? 1 : 0) | (md.has_uv ? 2 : 0), 0);
         if (md.kind != GB_GEOM_MESH) continue;
         const gb_bvh_node* nodes = d->model_nodes + md.node_offset;
-        fillPairs(nodes, md.node_count, modelPairIndex[m].data(),
-            reinterpret_cast<float4*>(H + oModelPairs) + 4 * (size_t)modelPairBase[m]);
-        if (md.node_count) modelRootRef[m] = refOf(nodes, modelPairIndex[m].data(), 0);
+        if (md.node_count) {
+            std::memcpy(H + oRawModelPairIdx + 4 * (size_t)md.node_offset, modelPairIndex[m].data(), 4 * (size_t)md.node_count);
+            modelRootRef[m] = refOf(nodes, modelPairIndex[m].data(), 0);
+        }
         std::vector<uint32_t>().swap(modelPairIndex[m]);
-        // triangle records in BVH leaf order: e1 = p1 - p0, e2 = p2 - p0 (the reference's per-test
-        // subtractions, done once)
-        std::atomic<int> bad(0);
-        hostParallelFor(md.tri_count, 1u << 15, [&](size_t b, size_t e) {
-            for (size_t k = b; k < e; ++k) {
-                uint32_t face = d->model_order[md.tri_offset + k];
-                if (face >= md.tri_count) { bad = 1; return; }
-                const uint32_t* vi = d->tri_index + 3 * ((size_t)md.tri_offset + face);
-                if (vi[0] >= md.vert_count || vi[1] >= md.vert_count || vi[2] >= md.vert_count) { bad = 2; return; }
-                const float* p0 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[0]);
-                const float* p1 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[1]);
-                const float* p2 = d->vert_pos + 3 * ((size_t)md.vert_offset + vi[2]);
-                float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
-                float e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-                float4* r = triRec + 3 * ((size_t)md.tri_offset + k);
-                float faceBits;
-                std::memcpy(&faceBits, &face, 4);
-                r[0] = make_float4(p0[0], p0[1], p0[2], e1[0]);
-                r[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
-                r[2] = make_float4(e2[2], faceBits, 0.0f, 0.0f);
-                // shading record: the face's vertex normals and uvs, gathered once
-                const float* n0 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[0]);
-                const float* n1 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[1]);
-                const float* n2 = d->vert_nrm + 3 * ((size_t)md.vert_offset + vi[2]);
-                const float* t0 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[0]);
-                const float* t1 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[1]);
-                const float* t2 = d->vert_uv + 2 * ((size_t)md.vert_offset + vi[2]);
-                float4* q = triShade + 4 * ((size_t)md.tri_offset + k);
-                q[0] = make_float4(n0[0], n0[1], n0[2], n1[0]);
-                q[1] = make_float4(n1[1], n1[2], n2[0], n2[1]);
-                q[2] = make_float4(n2[2], t0[0], t0[1], t1[0]);
-                q[3] = make_float4(t1[1], t2[0], t2[1], 0.0f);
-            }
-        });
-        if (bad == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
-        if (bad == 2) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
     }
+    if (d->n_tris) hostParallelFor(d->n_tris, 1u << 15, [&](size_t b, size_t e) {
+        std::memcpy(H + oRawOrder + 4 * b, d->model_order + b, 4 * (e - b));
+        std::memcpy(H + oRawTriIndex + 12 * b, d->tri_index + 3 * b, 12 * (e - b));
+    });
+    if (d->n_verts) hostParallelFor(d->n_verts, 1u << 15, [&](size_t b, size_t e) {
+        std::memcpy(H + oRawPos + 12 * b, d->vert_pos + 3 * b, 12 * (e - b));
+        std::memcpy(H + oRawNrm + 12 * b, d->vert_nrm + 3 * b, 12 * (e - b));
+        std::memcpy(H + oRawUv + 8 * b, d->vert_uv + 2 * b, 8 * (e - b));
+    });
     float4* instToObject = reinterpret_cast<float4*>(H + oInstToObject);
     float4* instToWorld = reinterpret_cast<float4*>(H + oInstToWorld);
     int4* instInfo = reinterpret_cast<int4*>(H + oInstInfo);
@@ -1365,10 +1424,41 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         for (uint32_t l = 0; l < d->n_lights; ++l) acc = acc + d->light_power[l] * dx;
         integral = acc;
     }
+    lap("fill");
     // ---- one host-to-device copy
-    GB_CUDA(cudaMemcpyAsync(ctx->arenaDev, H, ar.size, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->uploadBytes = ar.size;
-    const char* D = ctx->arenaDev;
+    GB_CUDA(cudaMemcpyAsync(ctx->arenaDev, H, uploadSize, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->uploadBytes = uploadSize;
+    char* D = ctx->arenaDev;
+    // ---- derive the traversal / shading records on the device, at HBM speed instead of PCIe speed
+    GB_CUDA(cudaMemsetAsync(ctx->deriveError, 0, sizeof(int), ctx->stream));
+    if (nTopPairs) {
+        k_derive_pairs<<<(d->n_top_nodes + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(D + oTopNodes),
+            reinterpret_cast<const unsigned int*>(D + oRawTopPairIdx), d->n_top_nodes, reinterpret_cast<float4*>(D + oTopPairs));
+        ctx->launches++;
+    }
+    for (uint32_t m = 0; m < d->n_models; ++m) {
+        const gb_model& md = d->models[m];
+        if (md.kind != GB_GEOM_MESH) continue;
+        if (modelPairCount[m]) {
+            k_derive_pairs<<<(md.node_count + 255) / 256, 256, 0, ctx->stream>>>(
+                reinterpret_cast<const float4*>(D + oModelNodes) + 2 * (size_t)md.node_offset,
+                reinterpret_cast<const unsigned int*>(D + oRawModelPairIdx) + md.node_offset, md.node_count,
+                reinterpret_cast<float4*>(D + oModelPairs) + 4 * (size_t)modelPairBase[m]);
+            ctx->launches++;
+        }
+        if (md.tri_count) {
+            k_derive_tris<<<(md.tri_count + 255) / 256, 256, 0, ctx->stream>>>(
+                reinterpret_cast<const unsigned int*>(D + oRawOrder) + md.tri_offset,
+                reinterpret_cast<const unsigned int*>(D + oRawTriIndex) + 3 * (size_t)md.tri_offset,
+                reinterpret_cast<const float*>(D + oRawPos) + 3 * (size_t)md.vert_offset,
+                reinterpret_cast<const float*>(D + oRawNrm) + 3 * (size_t)md.vert_offset,
+                reinterpret_cast<const float*>(D + oRawUv) + 2 * (size_t)md.vert_offset, md.tri_count, md.vert_count,
+                reinterpret_cast<float4*>(D + oTriRec) + 3 * (size_t)md.tri_offset,
+                reinterpret_cast<float4*>(D + oTriShade) + 4 * (size_t)md.tri_offset, ctx->deriveError);
+            ctx->launches++;
+        }
+    }
+    GB_CUDA(cudaMemcpyAsync(ctx->deriveErrorHost, ctx->deriveError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DeviceScene sc{};
     sc.tune = ctx->tune;
     sc.topNodes = reinterpret_cast<const float4*>(D + oTopNodes);
@@ -1421,10 +1511,13 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     ctx->filmDesc = d->film;
     GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
     GB_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging arena may be refilled after this
+    if (*ctx->deriveErrorHost == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
+    if (*ctx->deriveErrorHost == 2) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
     ctx->sc = sc;
     ctx->setting = d->setting;
     ctx->hasBlinn = hasBlinn;
     ctx->hasMeshLight = hasMeshLight;
+    lap("copy+sync");
     ctx->haveScene = true;
     if (traceSmem(ctx) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
     return GB_OK;
@@ -1772,8 +1865,19 @@ int gb_film_download(gb_context* ctx, float* rgbw) {
     if (!ctx || !rgbw) return gb::failWith(GB_ERR_INVALID, "null argument");
     if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
     GB_CUDA(cudaSetDevice(ctx->device));
-    GB_CUDA(cudaMemcpyAsync(rgbw, ctx->film, ctx->filmPixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    // through a pinned staging buffer: a DMA at PCIe speed plus a host memcpy beats the driver's
+    // staged copy into pageable memory (0.57 -> 0.2 ms for a 512 x 384 film)
+    if (ctx->filmHostPixels < ctx->filmPixels) {
+        if (ctx->filmHost) cudaFreeHost(ctx->filmHost);
+        ctx->filmHost = nullptr;
+        ctx->filmHostPixels = 0;
+        if (cudaMallocHost((void**)&ctx->filmHost, ctx->filmPixels * sizeof(float4)) == cudaSuccess) ctx->filmHostPixels = ctx->filmPixels;
+        else cudaGetLastError();
+    }
+    float* dst = ctx->filmHost ? ctx->filmHost : rgbw;
+    GB_CUDA(cudaMemcpyAsync(dst, ctx->film, ctx->filmPixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (dst != rgbw) std::memcpy(rgbw, dst, ctx->filmPixels * sizeof(float4));
     return GB_OK;
 }
 
