@@ -336,17 +336,23 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
             float3 o = make3(ro.x, ro.y, ro.z), d = make3(rd.x, rd.y, rd.z);
             Frag fr = buildFragment(sc, h, o, d);
             float3 wo = -d;
-            float4 Lacc = ps.L[i];
-            // emitted radiance seen through this segment
+            // emitted radiance seen through this segment: the only thing that touches L here, so the
+            // 32 bytes of its read-modify-write are spent on emitter hits alone
             if (fr.areaLight >= 0) {
                 float4 lc = __ldg(&sc.lights[fr.areaLight].colorType);
                 bool facing = dot3(fr.n, wo) > 0.0f; // AreaLight::L
                 if (bounce == 0) { // Li += intersection.Le(-ray.d), GoblinPathtracer.cpp:67
-                    if (facing) { Lacc.x += lc.x; Lacc.y += lc.y; Lacc.z += lc.z; }
+                    if (facing) {
+                        float4 Lacc = ps.L[i];
+                        Lacc.x += lc.x; Lacc.y += lc.y; Lacc.z += lc.z;
+                        ps.L[i] = Lacc;
+                    }
                 } else {
                     float4 pd = ps.pend[i]; // BSDF-sampled MIS term, GoblinPathtracer.cpp:148-155
                     if (__float_as_int(pd.w) == fr.areaLight && facing) {
+                        float4 Lacc = ps.L[i];
                         Lacc.x += pd.x * lc.x; Lacc.y += pd.y * lc.y; Lacc.z += pd.z * lc.z;
+                        ps.L[i] = Lacc;
                     }
                 }
             }
@@ -410,13 +416,12 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                     float3 w = div3(bs.f * absdot3(bs.wi, fr.n), bs.pdf);
                     thr = mul3(thr, w);
                     ps.thr[i] = make_float4(thr.x, thr.y, thr.z, 0.0f);
-                    ps.pend[i] = pendOut;
+                    if (sc.hasAreaLight | sc.hasEnvLight) ps.pend[i] = pendOut; // nobody reads it otherwise
                     ps.rayO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, eps);
                     ps.rayD[i] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.0f);
                     alive = true;
                 }
             }
-            ps.L[i] = Lacc;
         }
         // warp-aggregated appends: next extend queue, shadow queue
         unsigned int mask = __ballot_sync(0xffffffffu, alive);
