@@ -463,7 +463,9 @@ def main():
                     "kernel_share_of_step": kms[0] / total_ms,
                     "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]}}
         if stats_failed:
-            roofline.update({"achieved": None, "frac": None, "note": "the counters pass failed; no algorithmic bytes"})
+            roofline.update({"achieved": None, "frac": None,
+                             "note": "no algorithmic bytes: the counters pass was skipped (--no-stats)" if args.no_stats
+                             else "the counters pass failed; no algorithmic bytes"})
         line = {"metric": METRIC.get(args.scene, "path-traced Msamples/s (%s)" % args.scene), "value": value, "unit": "Msamples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
