@@ -40,7 +40,9 @@ class Instance(C.Structure):
 class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float),
                 ("k", C.c_float), ("exponent", C.c_float), ("fresnel", C.c_int32),
-                ("kd_tex", C.c_int32), ("kt_tex", C.c_int32), ("exponent_tex", C.c_int32)]
+                ("kd_tex", C.c_int32), ("kt_tex", C.c_int32), ("exponent_tex", C.c_int32),
+                ("mask", C.c_int32), ("alpha", C.c_float), ("transparent_color", C.c_float * 3),
+                ("alpha_tex", C.c_int32), ("transparent_tex", C.c_int32)]
 
 
 class Texture(C.Structure):

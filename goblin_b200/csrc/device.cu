@@ -1182,6 +1182,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         if (d->materials[m].type < 0 || d->materials[m].type >= GB_MAT_COUNT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
+        if (d->materials[m].mask) return gb::failWith(GB_ERR_INVALID, "mask materials are not rendered by this build");
     }
     std::vector<int> slotOf(nInst, -1); // original instance index -> leaf slot
     for (uint32_t s = 0; s < nInst; ++s) {

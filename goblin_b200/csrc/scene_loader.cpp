@@ -609,9 +609,25 @@ struct Loader {
                 m.eta = p.getFloat("index", 1.5f);
                 m.k = p.getFloat("k", -1.0f);
                 m.fresnel = m.k > 0.0f ? GB_FRESNEL_CONDUCTOR : GB_FRESNEL_DIELECTRIC;
-            } else if (type == "subsurface" || type == "mask") {
+            } else if (type == "subsurface") {
                 err = "material '" + name + "' of type '" + type + "' is outside the accelerated path";
                 return false;
+            } else if (type == "mask") { // createMaskMaterial, src/GoblinMaterial.cpp:929-950
+                FloatSlot alpha;
+                alpha.v = 1.0f;
+                if (p.hasString("alpha")) alpha = getFloatTexture(p.getString("alpha"));
+                else std::cout << "no feed in alpha" << std::endl;
+                ColorSlot tc;
+                tc.c = Color3{1.0f, 1.0f, 1.0f};
+                if (p.hasString("transparent_color")) tc = getColorTexture(p.getString("transparent_color"));
+                else std::cout << "no feed in tr color" << std::endl;
+                m = out->materials[getMaterial(p.getString("material"))]; // the masked material's record
+                if (m.mask) { err = "material '" + name + "': a mask around a mask is outside the accelerated path"; return false; }
+                m.mask = 1;
+                m.alpha = alpha.v;
+                m.alpha_tex = alpha.tex;
+                m.transparent_color[0] = tc.c.r; m.transparent_color[1] = tc.c.g; m.transparent_color[2] = tc.c.b;
+                m.transparent_tex = tc.tex;
             } else if (type == "transparent") {
                 m.type = GB_MAT_TRANSPARENT;
                 ColorSlot kr = getColorTexture(p.getString("Kr")), kt = getColorTexture(p.getString("Kt"));

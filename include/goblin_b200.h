@@ -123,6 +123,14 @@ typedef struct gb_material {
     int32_t kd_tex;
     int32_t kt_tex;
     int32_t exponent_tex;
+    /* Mask material (src/GoblinMaterial.cpp:747-811): the fields above are the MASKED material's;
+     * alpha blends it with an index-matched pass-through of colour transparent_color.  A mask makes
+     * its primitives "not opaque" for the path tracer's filtered traces (src/GoblinPathtracer.cpp:5-48). */
+    int32_t mask;              /* 1 = this record is a Mask around the material described above */
+    float alpha;
+    float transparent_color[3];
+    int32_t alpha_tex;         /* 1 + texture index (a float texture), 0 = the constant alpha    */
+    int32_t transparent_tex;   /* 1 + texture index, 0 = the constant transparent_color          */
 } gb_material;
 
 /* Procedural textures (src/GoblinTexture.cpp:292-427): constant, checkerboard

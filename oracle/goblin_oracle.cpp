@@ -418,12 +418,21 @@ struct Oracle {
 
     // Scene::intersect -> BVH -> InstancedPrimitive::intersect -> Model::intersect
     // (src/GoblinScene.cpp:75-83, src/GoblinPrimitive.cpp:103-112, src/GoblinModel.cpp:39-52)
-    bool intersect(Ray& ray, float* epsilon, Isect* isect, Stats& st) const {
+    // filter: the IntersectFilter of src/GoblinPathtracer.cpp:5-11 (0 = none, 1 = isOpaque, 2 = notOpaque).
+    // The reference applies it per refined Model, after walking a mesh's BVH (src/GoblinModel.cpp:44);
+    // the material belongs to the model, so skipping the whole instance gives the same hits.
+    bool filteredOut(const gb_model& m, int filter) const {
+        if (!filter) return false;
+        const bool opaque = !d->materials[m.material].mask;
+        return (filter == 1) != opaque;
+    }
+    bool intersect(Ray& ray, float* epsilon, Isect* isect, Stats& st, int filter = 0) const {
         st.closest++;
         return walk<false>(d->top_nodes, d->n_top_nodes, ray, st, [&](uint32_t slot) {
             uint32_t ii = d->top_order[slot];
             const gb_instance& in = d->instances[ii];
             const gb_model& m = d->models[in.model];
+            if (filteredOut(m, filter)) return false;
             st.insts++;
             Ray r{xfPoint(in.to_object, ray.o), xfVector(in.to_object, ray.d), ray.mint, ray.maxt}; // invertRay
             bool hit = false;
@@ -457,19 +466,20 @@ struct Oracle {
     }
 
     // Scene::occluded (src/GoblinScene.cpp:85-87)
-    bool occluded(const Ray& ray, Stats& st) const {
+    bool occluded(const Ray& ray, Stats& st, int filter = 0) const {
         st.any++;
         const uint64_t n0 = st.nodes, p0 = st.prims, i0 = st.insts;
-        bool occ = occludedWalk(ray, st);
+        bool occ = occludedWalk(ray, st, filter);
         st.nodesAny += st.nodes - n0;
         st.primsAny += st.prims - p0;
         st.instsAny += st.insts - i0;
         return occ;
     }
-    bool occludedWalk(const Ray& ray, Stats& st) const {
+    bool occludedWalk(const Ray& ray, Stats& st, int filter) const {
         return walk<true>(d->top_nodes, d->n_top_nodes, ray, st, [&](uint32_t slot) {
             const gb_instance& in = d->instances[d->top_order[slot]];
             const gb_model& m = d->models[in.model];
+            if (filteredOut(m, filter)) return false;
             st.insts++;
             Ray r{xfPoint(in.to_object, ray.o), xfVector(in.to_object, ray.d), ray.mint, ray.maxt};
             if (m.kind == GB_GEOM_MESH) {
@@ -1295,6 +1305,143 @@ struct Oracle {
         return Li;
     }
 
+    // ---- MaskMaterial (src/GoblinMaterial.cpp:747-811) around the masked material's record
+    struct MaskEval { float alpha; V3 tc; };
+    MaskEval maskEval(const gb_material& m, const Frag& f) const {
+        MaskEval e;
+        e.alpha = m.alpha_tex ? texLookup(m.alpha_tex - 1, f).x : m.alpha;
+        e.tc = m.transparent_tex ? texLookup(m.transparent_tex - 1, f) : rgb(m.transparent_color);
+        return e;
+    }
+    bool sceneHasMask() const {
+        for (uint32_t i = 0; i < d->n_materials; ++i) if (d->materials[i].mask) return true;
+        return false;
+    }
+    // PathTracer::evalAttenuation, src/GoblinPathtracer.cpp:21-48: the product of the index-matched
+    // transmittances of the not-opaque surfaces along a segment
+    V3 evalAttenuation(const Ray& ray, Stats& st) const {
+        V3 throughput(1.0f, 1.0f, 1.0f);
+        float maxt = ray.maxt;
+        Ray currentRay = ray;
+        float epsilon;
+        Isect is;
+        while (true) {
+            st.refIntersect++;
+            if (!intersect(currentRay, &epsilon, &is, st, 2)) break;
+            Frag fr = is.frag;
+            computeUVDifferential(fr, RayDiff()); // a fresh Fragment: no differentials
+            const gb_material& m = d->materials[d->models[d->instances[is.inst].model].material];
+            MaskEval e = maskEval(m, fr);
+            throughput = throughput * ((1.0f - e.alpha) * e.tc); // sampleBSDF(..., BSDFnullptr)
+            if (throughput.x == 0.0f && throughput.y == 0.0f && throughput.z == 0.0f) break;
+            currentRay.mint = currentRay.maxt + epsilon;
+            currentRay.maxt = maxt;
+        }
+        return throughput;
+    }
+    // PathTracer::Li for scenes with a Mask material: every filtered trace and attenuation walk of the
+    // reference is executed as written (src/GoblinPathtracer.cpp:50-179)
+    template <typename U>
+    V3 liPathMask(Ray ray, RayDiff rayDiff, int maxDepth, U u, Stats& st) const {
+        if (d->n_lights == 0) return V3();
+        V3 Li;
+        float epsilon;
+        Isect is;
+        auto envLight = [&](V3 dir) { V3 e; for (uint32_t i = 0; i < d->n_lights; ++i) e = e + lightLe(d->lights[i], dir); return e; };
+        st.refIntersect++;
+        if (!intersect(ray, &epsilon, &is, st)) return envLight(ray.d);
+        Li = Li + emitted(is, -ray.d);
+        V3 throughput(1.0f, 1.0f, 1.0f);
+        bool firstBounce = true;
+        for (int bounces = 0; bounces < maxDepth - 1; ++bounces) {
+            float ub[7];
+            u(bounces, ub);
+            float pickLightPdf;
+            int li = pickLight(ub[6], &pickLightPdf);
+            const gb_light& light = d->lights[li];
+            V3 Ld;
+            computeUVDifferential(is.frag, rayDiff);
+            const Frag& fragment = is.frag;
+            const gb_material& raw = d->materials[d->models[d->instances[is.inst].model].material];
+            const gb_material material = resolveMaterial(raw, fragment);
+            const bool mask = raw.mask != 0;
+            MaskEval me{1.0f, V3()};
+            if (mask) me = maskEval(raw, fragment);
+            V3 wo = -ray.d;
+            V3 wi;
+            V3 p = fragment.p;
+            V3 n = fragment.n;
+            float lightPdfV, bsdfPdfV;
+            Ray shadowRay;
+            V3 L = sampleL(light, p, epsilon, ub[0], ub[1], ub[2], &wi, &lightPdfV, &shadowRay);
+            if (!isBlack(L) && lightPdfV > 0.0f) {
+                V3 f = bsdf(material, fragment, wo, wi);
+                if (mask) f = f * me.alpha; // alpha * mMaskedMaterial->bsdf
+                if (!isBlack(f) && (st.refOccluded++, !occluded(shadowRay, st, 1))) {
+                    V3 tr = evalAttenuation(shadowRay, st);
+                    if (light.type != GB_LIGHT_AREA && light.type != GB_LIGHT_IBL) {
+                        Ld = Ld + f * tr * L * absdot(n, wi) / lightPdfV;
+                    } else {
+                        bsdfPdfV = bsdfPdf(material, fragment, wo, wi);
+                        if (mask) bsdfPdfV = me.alpha * bsdfPdfV; // MaskMaterial::pdf, both parts requested
+                        float lWeight = powerHeuristic(lightPdfV, bsdfPdfV);
+                        Ld = Ld + f * tr * L * absdot(n, wi) * lWeight / lightPdfV;
+                    }
+                }
+            }
+            bool specular = false, nullSampled = false;
+            V3 f;
+            if (mask && !(ub[3] < me.alpha)) { // the index-matched pass-through
+                f = (1.0f - me.alpha) * me.tc;
+                wi = -normalize(wo);
+                bsdfPdfV = 1.0f - me.alpha;
+                nullSampled = true;
+            } else {
+                f = sampleBSDF(material, fragment, wo, ub[3], ub[4], ub[5], &wi, &bsdfPdfV, &specular);
+                if (mask) { f = f * me.alpha; bsdfPdfV *= me.alpha; }
+            }
+            if (!isBlack(f) && bsdfPdfV > 0.0f) {
+                if (nullSampled) {
+                    throughput = throughput * (f / bsdfPdfV);
+                    ray = Ray{p, wi, epsilon, INF};
+                    rayDiff.has = false;
+                    st.refIntersect++;
+                    if (!intersect(ray, &epsilon, &is, st)) {
+                        if (firstBounce) Li = Li + throughput * envLight(ray.d);
+                        break;
+                    }
+                    continue;
+                }
+                float fWeight = 1.0f;
+                if (!specular) fWeight = powerHeuristic(bsdfPdfV, lightPdf(light, p, wi));
+                Isect lightIs;
+                float lightEps;
+                Ray r{p, wi, epsilon, INF};
+                st.refIntersect++;
+                if (intersect(r, &lightEps, &lightIs, st, 1)) {
+                    V3 tr = evalAttenuation(r, st); // r.maxt has shrunk to the opaque hit
+                    int al = d->models[d->instances[lightIs.inst].model].area_light;
+                    if (al == li && light.type == GB_LIGHT_AREA) {
+                        V3 Le = emitted(lightIs, -wi);
+                        if (!isBlack(Le)) Ld = Ld + f * tr * Le * absdot(wi, n) * fWeight / bsdfPdfV;
+                    }
+                } else {
+                    V3 tr = evalAttenuation(r, st);
+                    Ld = Ld + f * tr * lightLe(light, wi) * fWeight / bsdfPdfV;
+                }
+            }
+            Li = Li + throughput * Ld / pickLightPdf;
+            if (isBlack(f) || bsdfPdfV == 0.0f) break;
+            throughput = throughput * f * absdot(wi, n) / bsdfPdfV;
+            ray = Ray{p, wi, epsilon, INF};
+            rayDiff.has = false;
+            st.refIntersect++;
+            if (!intersect(ray, &epsilon, &is, st)) break;
+            firstBounce = false;
+        }
+        return Li;
+    }
+
     // ---- AORenderer::Li, src/GoblinAO.cpp:12-37.  u(a, out[2])
     template <typename U>
     V3 liAO(Ray ray, int aoSamples, U u, Stats& st) const {
@@ -1471,6 +1618,7 @@ int go_li(const gb_scene_desc* d, const float* samples, size_t n, size_t row, fl
     const int method = d->setting.method;
     const int depth = std::max(1, d->setting.max_ray_depth);
     const int ao = std::max(1, d->setting.ao_sample_num);
+    const bool hasMask = o.sceneHasMask();
     size_t need = 4 + (method == GB_METHOD_AO ? 2 * (size_t)ao : 7 * (size_t)depth);
     if (row < need) return 1;
     std::vector<Stats> per(threadCount(threads));
@@ -1484,8 +1632,9 @@ int go_li(const gb_scene_desc* d, const float* samples, size_t n, size_t row, fl
             if (method == GB_METHOD_AO) {
                 L = o.liAO(ray, ao, [&](int a, float* uv) { uv[0] = s[4 + 2 * a]; uv[1] = s[4 + 2 * a + 1]; }, st);
             } else {
-                L = o.liPath(ray, o.cameraRayDiff(s[0], s[1], s[2], s[3]), depth,
-                    [&](int bn, float* ub) { std::memcpy(ub, s + 4 + 7 * bn, 7 * sizeof(float)); }, st);
+                auto ubs = [&](int bn, float* ub) { std::memcpy(ub, s + 4 + 7 * bn, 7 * sizeof(float)); };
+                L = hasMask ? o.liPathMask(ray, o.cameraRayDiff(s[0], s[1], s[2], s[3]), depth, ubs, st)
+                            : o.liPath(ray, o.cameraRayDiff(s[0], s[1], s[2], s[3]), depth, ubs, st);
             }
             out_rgb[3 * i] = L.x; out_rgb[3 * i + 1] = L.y; out_rgb[3 * i + 2] = L.z;
             if (ref_calls) {
@@ -1506,6 +1655,7 @@ int go_li(const gb_scene_desc* d, const float* samples, size_t n, size_t row, fl
 int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, int threads, int pixel_stride,
     gb_counters* counters, uint64_t* ref_calls) {
     Oracle o(d);
+    const bool hasMask = o.sceneHasMask();
     const gb_film_desc& f = d->film;
     int method = p->method >= 0 ? p->method : d->setting.method;
     int depth = p->max_ray_depth > 0 ? p->max_ray_depth : d->setting.max_ray_depth;
@@ -1553,13 +1703,15 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                         uv[1] = ((float)(a / aoRoot) + uy) * asub;
                     }, st);
                 } else {
-                    L = o.liPath(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, [&](int bn, float* ub) {
+                    auto ubs = [&](int bn, float* ub) {
                         float a4[4], b4[4];
                         block(p->seed, id, 1u + 2u * (uint32_t)bn, a4);
                         block(p->seed, id, 2u + 2u * (uint32_t)bn, b4);
                         ub[0] = a4[0]; ub[1] = a4[1]; ub[2] = a4[2]; ub[3] = a4[3];
                         ub[4] = b4[0]; ub[5] = b4[1]; ub[6] = b4[2];
-                    }, st);
+                    };
+                    L = hasMask ? o.liPathMask(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, ubs, st)
+                                : o.liPath(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, ubs, st);
                 }
                 samplesDone[t]++;
                 // ImageTile::addSample, src/GoblinFilm.cpp:61-90

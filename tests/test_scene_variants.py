@@ -60,6 +60,32 @@ def _variant(name):
         else:  # every light kind at once, the map missing: the reference falls back to 1 x 1 magenta
             sky["file"] = "_env_missing.exr"
             sc["lights"] = sc["lights"] + [sky]
+    elif name.startswith("mask"):
+        # Mask materials (src/GoblinMaterial.cpp:747-811): constant and checkerboard alpha, tinted
+        # pass-through, around Lambert / Blinn / glass; they bring back the path tracer's isOpaque filter
+        # and evalAttenuation (src/GoblinPathtracer.cpp:5-48) for real
+        tex = sc["textures"]
+        tex += [
+            {"format": "float", "name": "half", "type": "constant", "float": 0.5},
+            {"format": "float", "name": "zero", "type": "constant", "float": 0.0},
+            {"format": "float", "name": "one", "type": "constant", "float": 1.0},
+            {"format": "float", "name": "cutout", "type": "checkerboard", "texture1": "zero", "texture2": "one",
+             "mapping": "uv", "scale": [6.0, 6.0]},
+            {"format": "color", "name": "amber", "type": "constant", "color": [1.0, 0.8, 0.5]},
+        ]
+        sc["materials"] += [
+            {"name": "veil", "type": "mask", "material": "green", "alpha": "half", "transparent_color": "amber"},
+            {"name": "lace", "type": "mask", "material": "gloss", "alpha": "cutout"},
+            {"name": "ghost_glass", "type": "mask", "material": "glass", "alpha": "half"},
+            {"name": "plain", "type": "mask", "material": "red"},
+        ]
+        for pr in sc["primitives"]:
+            if pr["type"] != "model":
+                continue
+            pr["material"] = {"box": "veil", "plate": "lace", "blob": "ghost_glass", "ico": "plain"}.get(pr["name"], pr["material"])
+        if name == "mask_ibl":
+            sc["lights"] = [l for l in sc["lights"] if l["type"] in ("point", "area")][:2] + [
+                {"name": "sky", "type": "ibl", "file": "_env_32x16.exr", "filter": [0.6, 0.7, 0.9]}]
     elif name.startswith("img_"):
         # image textures (src/GoblinTexture.cpp:82-288,431-503): every filter and address mode, both
         # mappings, colour and float formats, gamma and channel selection
@@ -135,7 +161,7 @@ def _variant(name):
 
 VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
             "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof", "ibl", "ibl_only", "ibl_missing",
-            "img_nearest", "img_bilinear", "img_trilinear", "img_ewa"]
+            "img_nearest", "img_bilinear", "img_trilinear", "img_ewa", "mask", "mask_ibl"]
 
 
 @pytest.fixture(scope="module")
