@@ -35,6 +35,7 @@
 #include "traverse.cuh"
 #include "shade.cuh"
 #include "texture.cuh"
+#include "mask.cuh"
 
 namespace gb {
 
@@ -208,7 +209,7 @@ __global__ void k_raygen(DeviceScene sc, PathState ps, WaveParams wp, SampleSour
     cameraRay(sc, imageX, imageY, u.z, u.w, &o, &d);
     ps.rayO[i] = make_float4(o.x, o.y, o.z, 1e-3f); // ray->mint = 1e-3f
     ps.rayD[i] = make_float4(d.x, d.y, d.z, 0.0f);
-    ps.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    ps.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f); // w: no real bounce yet (firstBounce)
     ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     ps.pend[i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
     if (ps.aoCount) ps.aoCount[i] = 0u;
@@ -347,7 +348,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                         Lacc.x += lc.x; Lacc.y += lc.y; Lacc.z += lc.z;
                         ps.L[i] = Lacc;
                     }
-                } else {
+                } else if (!(TEX && sc.matMask)) { // with masks the MIS ray is traced on its own (k_mis_mask)
                     float4 pd = ps.pend[i]; // BSDF-sampled MIS term, GoblinPathtracer.cpp:148-155
                     if (__float_as_int(pd.w) == fr.areaLight && facing) {
                         float4 Lacc = ps.L[i];
@@ -379,14 +380,25 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                     }
                     applyTextures(sc, fr.material, MAT, h, o, d, fr, bounce == 0, imageX, imageY, u0.z, u0.w, &m);
                 }
+                // Mask around this material (MaskMaterial, GoblinMaterial.cpp:747-811): alpha scales the
+                // masked BSDF, 1 - alpha goes straight through
+                bool masked = false;
+                MaskEval me;
+                me.alpha = 1.0f; me.tc = make3(0.0f, 0.0f, 0.0f);
+                if (TEX && sc.matMask && __ldg(sc.matMask + 2 * (size_t)fr.material).x) {
+                    masked = true;
+                    me = maskAt(sc, fr.material, h, o, d, fr, nullptr);
+                }
                 if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
                     LightSampleResult ls = sampleLight<ML>(sc, li, fr.p, eps, uA.x, uA.y, uA.z);
                     if (!isBlack(ls.L) && ls.pdf > 0.0f) {
                         float3 f = MAT == GB_MAT_LAMBERT ? lambertEval(m, fr.n, wo, ls.wi) : blinnEval(m, fr.n, wo, ls.wi);
+                        if (TEX && masked) f = f * me.alpha;
                         if (!isBlack(f)) {
                             float3 c = mul3(f, ls.L) * absdot3(fr.n, ls.wi);
                             if (!ls.delta) {
                                 float bsdfPdf = MAT == GB_MAT_LAMBERT ? lambertPdf(fr.n, wo, ls.wi) : blinnPdf(m, fr.n, wo, ls.wi);
+                                if (TEX && masked) bsdfPdf = me.alpha * bsdfPdf;
                                 c = c * powerHeuristic(ls.pdf, bsdfPdf);
                             }
                             c = div3(c, ls.pdf);
@@ -396,9 +408,21 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                         }
                     }
                 }
-                BsdfSample bs = sampleBsdf(m, MAT, fr, wo, uA.w, uB.x, uB.y);
+                BsdfSample bs;
+                bool nullSampled = false;
+                if (TEX && masked && !(uA.w < me.alpha)) { // the index-matched pass-through (BSDFnullptr)
+                    bs.f = (1.0f - me.alpha) * me.tc;
+                    bs.wi = -normalize3(wo);
+                    bs.pdf = 1.0f - me.alpha;
+                    bs.specular = false;
+                    nullSampled = true;
+                    shadow = false; // the reference `continue`s: this bounce's direct light is dropped
+                } else {
+                    bs = sampleBsdf(m, MAT, fr, wo, uA.w, uB.x, uB.y);
+                    if (TEX && masked) { bs.f = bs.f * me.alpha; bs.pdf *= me.alpha; }
+                }
                 float4 pendOut = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-                if (!isBlack(bs.f) && bs.pdf > 0.0f) {
+                if (!nullSampled && !isBlack(bs.f) && bs.pdf > 0.0f) {
                     float fWeight = 1.0f;
                     if (!bs.specular) fWeight = powerHeuristic(bs.pdf, lightPdf<ML>(sc, li, fr.p, bs.wi));
                     int ltype = __float_as_int(__ldg(&sc.lights[li].colorType).w);
@@ -413,9 +437,16 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                     }
                 }
                 if (!(isBlack(bs.f) || bs.pdf == 0.0f)) {
-                    float3 w = div3(bs.f * absdot3(bs.wi, fr.n), bs.pdf);
-                    thr = mul3(thr, w);
-                    ps.thr[i] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+                    // thr.w: the path has only punched through masks so far (the reference's firstBounce)
+                    float first = 0.0f;
+                    if (TEX && nullSampled) {
+                        thr = mul3(thr, div3(bs.f, bs.pdf)); // throughput *= f / bsdfPdf, no cosine
+                        first = tv.w;
+                    } else {
+                        float3 w = div3(bs.f * absdot3(bs.wi, fr.n), bs.pdf);
+                        thr = mul3(thr, w);
+                    }
+                    ps.thr[i] = make_float4(thr.x, thr.y, thr.z, first);
                     if (sc.hasAreaLight | sc.hasEnvLight) ps.pend[i] = pendOut; // nobody reads it otherwise
                     ps.rayO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, eps);
                     ps.rayD[i] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, 0.0f);
@@ -467,6 +498,16 @@ __global__ void k_miss(DeviceScene sc, PathState ps, const unsigned int* __restr
                 const float3 le = iblLe(sc, sc.lights[l], d);
                 L.x += le.x; L.y += le.y; L.z += le.z;
             }
+        } else if (sc.matMask) {
+            // masks: the MIS term was settled by k_mis_mask; a path that only punched through masks
+            // since the camera still sees the environment (firstBounce, GoblinPathtracer.cpp:124-128)
+            const float4 tv = ps.thr[i];
+            if (tv.w == 0.0f) continue;
+            for (unsigned int l = 0; l < sc.nLights; ++l) {
+                if (__float_as_int(__ldg(&sc.lights[l].colorType).w) != GB_LIGHT_IBL) continue;
+                const float3 le = iblLe(sc, sc.lights[l], d);
+                L.x += tv.x * le.x; L.y += tv.y * le.y; L.z += tv.z * le.z;
+            }
         } else {
             const float4 pd = ps.pend[i];
             const int li = __float_as_int(pd.w);
@@ -474,6 +515,59 @@ __global__ void k_miss(DeviceScene sc, PathState ps, const unsigned int* __restr
             const float3 le = iblLe(sc, sc.lights[li], d);
             L.x += pd.x * le.x; L.y += pd.y * le.y; L.z += pd.z * le.z;
         }
+        ps.L[i] = L;
+    }
+}
+
+// --------------------------------------------------------------------- masks
+// Scenes with a Mask material (mask.cuh).  Shadow segments: occluded by OPAQUE primitives only, then
+// attenuated by the not-opaque ones (GoblinPathtracer.cpp:96-99).
+__global__ void k_shadow_mask(DeviceScene sc, PathState ps, const unsigned int* ctr, unsigned long long* stats) {
+    const unsigned int n = ctr[C_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + S_RAYS_ANY, (unsigned long long)n);
+    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const float4 a = ps.shO[j], b = ps.shD[j];
+        const float3 o = make3(a.x, a.y, a.z), d = make3(b.x, b.y, b.z);
+        if (simpleAny(sc, o, d, a.w, b.w, FILTER_OPAQUE)) continue;
+        const float3 tr = evalAttenuation(sc, o, d, a.w, b.w);
+        const float4 c = ps.shC[j];
+        const unsigned int i = (unsigned int)__float_as_int(c.w);
+        float4 L = ps.L[i];
+        L.x += c.x * tr.x; L.y += c.y * tr.y; L.z += c.z * tr.z;
+        ps.L[i] = L;
+    }
+}
+// The MIS ray of a bounce (GoblinPathtracer.cpp:142-161): closest OPAQUE hit, attenuation up to it, then
+// the picked light's emission there -- or the environment map when nothing opaque is hit.  One thread per
+// path that continues; `pend` holds the weight the shade kernel prepared.
+__global__ void k_mis_mask(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, const unsigned int* ctrNext,
+    unsigned long long* stats) {
+    const unsigned int n = ctrNext[C_EXTEND];
+    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned int i = __ldg(queue + j);
+        const float4 pd = ps.pend[i];
+        const int li = __float_as_int(pd.w);
+        if (li < 0) continue;
+        const float4 ro = ps.rayO[i], rd = ps.rayD[i];
+        const float3 o = make3(ro.x, ro.y, ro.z), d = make3(rd.x, rd.y, rd.z);
+        atomicAdd(stats + S_RAYS_CLOSEST, 1ull);
+        HitRec h;
+        const bool found = simpleClosest(sc, o, d, ro.w, INFINITY, FILTER_OPAQUE, &h);
+        const int ltype = __float_as_int(__ldg(&sc.lights[li].colorType).w);
+        float3 le = make3(0.0f, 0.0f, 0.0f);
+        if (found) {
+            const Frag fr = buildFragment(sc, h, o, d);
+            if (fr.areaLight == li && ltype == GB_LIGHT_AREA && dot3(fr.n, -d) > 0.0f) {
+                const float4 lc = __ldg(&sc.lights[li].colorType);
+                le = make3(lc.x, lc.y, lc.z);
+            }
+        } else if (ltype == GB_LIGHT_IBL) {
+            le = iblLe(sc, sc.lights[li], d);
+        }
+        if (le.x == 0.0f && le.y == 0.0f && le.z == 0.0f) continue;
+        const float3 tr = evalAttenuation(sc, o, d, ro.w, found ? h.t : INFINITY);
+        float4 L = ps.L[i];
+        L.x += pd.x * le.x * tr.x; L.y += pd.y * le.y * tr.y; L.z += pd.z * le.z * tr.z;
         ps.L[i] = L;
     }
 }
@@ -995,8 +1089,8 @@ inline uint32_t refOf(const gb_bvh_node* nodes, const uint32_t* pairIndex, uint3
 // device evaluates a program left to right on a value stack.  Validates the part of the texture
 // table the materials reach (types, child indices pointing at EARLIER entries: no cycles, float
 // children where a float is read) and the stack / length bounds of the evaluator.
-bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, std::vector<unsigned int>* prog,
-    std::string* err) {
+bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, std::vector<int4>* matMask,
+    std::vector<unsigned int>* prog, std::string* err) {
     auto emit = [&](int root, bool wantFloat, int* offset) -> bool {
         std::vector<unsigned int> out;
         int depth = 0, maxDepth = 0;
@@ -1050,6 +1144,17 @@ bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, s
         if (mm.kt_tex && mm.type == GB_MAT_TRANSPARENT && !emit(mm.kt_tex - 1, false, &slots.y)) return false;
         if (mm.exponent_tex && mm.type == GB_MAT_BLINN && !emit(mm.exponent_tex - 1, true, &slots.z)) return false;
         (*matTex)[m] = slots;
+        if (mm.mask) { // MaskMaterial: alpha (float) and transparent colour, constants or programs
+            int4 info = make_int4(1, 0, 0, 0);
+            if (mm.alpha_tex && !emit(mm.alpha_tex - 1, true, &info.y)) return false;
+            if (mm.transparent_tex && !emit(mm.transparent_tex - 1, false, &info.z)) return false;
+            float v[4] = {mm.alpha, mm.transparent_color[0], mm.transparent_color[1], mm.transparent_color[2]};
+            int4 bits;
+            std::memcpy(&bits, v, 16);
+            (*matMask)[2 * (size_t)m] = info;
+            (*matMask)[2 * (size_t)m + 1] = bits;
+            if (prog->empty()) prog->push_back(0u); // mask scenes run the texture-capable shade kernels
+        }
     }
     return true;
 }
@@ -1182,7 +1287,6 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     }
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         if (d->materials[m].type < 0 || d->materials[m].type >= GB_MAT_COUNT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
-        if (d->materials[m].mask) return gb::failWith(GB_ERR_INVALID, "mask materials are not rendered by this build");
     }
     std::vector<int> slotOf(nInst, -1); // original instance index -> leaf slot
     for (uint32_t s = 0; s < nInst; ++s) {
@@ -1215,11 +1319,15 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     // procedural textures: postfix programs of the textured material slots
     std::vector<int4> matTex(d->n_materials, make_int4(0, 0, 0, 0));
     std::vector<unsigned int> texProg;
+    std::vector<int4> matMask(2 * (size_t)d->n_materials, make_int4(0, 0, 0, 0));
+    bool hasMask = false;
+    for (uint32_t m = 0; m < d->n_materials; ++m) hasMask = hasMask || d->materials[m].mask != 0;
     {
         std::string terr;
-        if (!compileTexturePrograms(d, &matTex, &texProg, &terr)) return gb::failWith(GB_ERR_INVALID, terr);
+        if (!compileTexturePrograms(d, &matTex, &matMask, &texProg, &terr)) return gb::failWith(GB_ERR_INVALID, terr);
     }
     const bool hasTextures = !texProg.empty();
+    const size_t oMatMask = ar.take(hasMask ? 32 * (size_t)d->n_materials : 0);
     const size_t oMatTex = ar.take(hasTextures ? 16 * (size_t)d->n_materials : 0);
     const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
     const size_t oTexNodes = ar.take(hasTextures ? 16 * (size_t)kTexNodeVec4 * d->n_textures : 0);
@@ -1330,6 +1438,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         } else if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
+    if (hasMask) std::memcpy(H + oMatMask, matMask.data(), 16 * matMask.size());
     if (hasTextures) {
         std::memcpy(H + oMatTex, matTex.data(), 16 * matTex.size());
         std::memcpy(H + oTexProg, texProg.data(), 4 * texProg.size());
@@ -1484,6 +1593,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.texProg = hasTextures ? reinterpret_cast<const unsigned int*>(D + oTexProg) : nullptr;
     sc.texNodes = hasTextures ? reinterpret_cast<const float4*>(D + oTexNodes) : nullptr;
     sc.texLevels = hasTextures ? reinterpret_cast<const int4*>(D + oTexLevels) : nullptr;
+    sc.matMask = hasMask ? reinterpret_cast<const int4*>(D + oMatMask) : nullptr;
     sc.lights = reinterpret_cast<const DeviceLight*>(D + oLights);
     sc.lightPower = reinterpret_cast<const float*>(D + oLightPower);
     sc.lightCdf = reinterpret_cast<const float*>(D + oLightCdf);
@@ -1721,7 +1831,12 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
 #undef GB_SHADE_TEX
             }
             ctx->launches += ctx->hasBlinn ? 4 : 3;
-            if (!last) {
+            if (!last && ctx->sc.matMask) { // masks: filtered shadow / MIS traces with attenuation (mask.cuh)
+                KernelTick tick(ctx, GB_K_SHADOW);
+                k_shadow_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, c, ctx->stats);
+                if (ctx->sc.hasAreaLight | ctx->sc.hasEnvLight) k_mis_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, qn, cn, ctx->stats);
+                ctx->launches += 2;
+            } else if (!last) {
                 KernelTick tick(ctx, GB_K_SHADOW);
                 if (ctx->statsOn) {
                     if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;

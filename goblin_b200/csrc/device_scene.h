@@ -66,6 +66,8 @@ struct DeviceScene {
     const int4* matTex;         // per material: program offset in texProg of kd, kt, exponent (0 = constant), 0
     const unsigned int* texProg; // postfix programs: [length, node index ...]; entry 0 is unused
     const float4* texNodes;     // 7 per texture: value | type, options, uv mapping, 3 rows world -> texture, image info
+    const int4* matMask;        // Mask materials (mask.cuh), 2 per material: (is mask, alpha program, colour program, 0),
+                                // float bits (alpha, transparent colour rgb); null when the scene has none
     const int4* texLevels;      // image textures: (width, height, first texel in imageTexels, 0) per pyramid level
     const DeviceLight* lights;
     const float* lightPower;    // CDF1D::mFunction
