@@ -70,7 +70,8 @@ class Light(C.Structure):
 
 class Camera(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("orientation", C.c_float * 4), ("proj00", C.c_float),
-                ("proj11", C.c_float), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
+                ("proj11", C.c_float), ("lens_radius", C.c_float), ("focal_distance", C.c_float),
+                ("orthographic", C.c_int32), ("film_width", C.c_float), ("film_height", C.c_float)]
 
 
 class FilmDesc(C.Structure):

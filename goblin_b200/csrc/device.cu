@@ -207,7 +207,7 @@ __global__ void k_raygen(DeviceScene sc, PathState ps, WaveParams wp, SampleSour
     imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
     float3 o, d;
     cameraRay(sc, imageX, imageY, u.z, u.w, &o, &d);
-    ps.rayO[i] = make_float4(o.x, o.y, o.z, 1e-3f); // ray->mint = 1e-3f
+    ps.rayO[i] = make_float4(o.x, o.y, o.z, cameraMint(sc)); // ray->mint
     ps.rayD[i] = make_float4(d.x, d.y, d.z, 0.0f);
     ps.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 1.0f); // w: no real bounce yet (firstBounce)
     ps.L[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -791,7 +791,7 @@ __global__ void k_camera_rays(DeviceScene sc, const float* samples, unsigned int
     gb_ray r;
     r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
     r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
-    r.mint = 1e-3f;
+    r.mint = cameraMint(sc);
     r.maxt = INFINITY;
     rays[i] = r;
 }

@@ -371,10 +371,6 @@ struct Loader {
         if (!cc) cc = &empty;
         cp.parse(*cc);
         std::string type = cp.getString("type");
-        if (type == "orthographic") {
-            err = "orthographic camera is outside the accelerated path";
-            return false;
-        }
         float lensRadius = cp.getFloat("lens_radius");
         if (lensRadius != 0.0f) {
             // the lens disk is an intersectable black-Lambert instance, first
@@ -431,6 +427,15 @@ struct Loader {
         cam.proj11 = yScale;
         cam.lens_radius = lensRadius;
         cam.focal_distance = cp.getFloat("focal_distance", 1.0f);
+        if (type == "orthographic") { // createOrthographicCamera + ctor, src/GoblinCamera.cpp:290-299,390-398
+            cam.orthographic = 1;
+            cam.lens_radius = 0.0f; // the orthographic camera has no lens model (a lens_radius still adds the lens disk)
+            cam.focal_distance = 0.0f;
+            cam.film_width = cp.getFloat("film_width", 35.0f);
+            cam.film_height = cam.film_width / aspect;
+            cam.proj00 = 2.0f / cam.film_width; // matrixOrthoLHD3D
+            cam.proj11 = 2.0f / cam.film_height;
+        }
         return true;
     }
 

@@ -156,6 +156,12 @@ __device__ __forceinline__ void cameraRay(const DeviceScene& sc, float imageX, f
     float yView = yNDC / cam.proj11;
     float3 viewDir = make3(xView, yView, 1.0f);
     float3 pos = make3(cam.position[0], cam.position[1], cam.position[2]);
+    if (cam.orthographic) { // OrthographicCamera::generateRay, GoblinCamera.cpp:301-329
+        float3 pView = make3(0.5f * cam.film_width * xNDC, 0.5f * cam.film_height * yNDC, 0.0f);
+        *o = pos + quatRotate(cam.orientation, pView);
+        *d = quatRotate(cam.orientation, make3(0.0f, 0.0f, 1.0f));
+        return;
+    }
     if (cam.lens_radius == 0.0f) {
         *o = pos;
         *d = quatRotate(cam.orientation, normalize3(viewDir));
@@ -168,6 +174,9 @@ __device__ __forceinline__ void cameraRay(const DeviceScene& sc, float imageX, f
         *d = quatRotate(cam.orientation, normalize3(pFocus - viewOrigin));
     }
 }
+
+// ray->mint of a camera ray: 1e-3 (perspective, GoblinCamera.cpp:143), 0 (orthographic, :324)
+__device__ __forceinline__ float cameraMint(const DeviceScene& sc) { return sc.camera.orthographic ? 0.0f : 1e-3f; }
 
 // ------------------------------------------------------------ hit fragment
 struct Frag {

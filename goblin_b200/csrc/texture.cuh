@@ -121,8 +121,12 @@ __device__ __noinline__ void texDifferentials(const DeviceScene& sc, float image
     const float3 dxViewDir = make3(dxNDC / cam.proj00, yView, 1.0f);
     const float3 dyViewDir = make3(xView, dyNDC / cam.proj11, 1.0f);
     const float3 pos = make3(cam.position[0], cam.position[1], cam.position[2]);
-    float3 oAux, dxD, dyD;
-    if (cam.lens_radius == 0.0f) {
+    float3 oAux, oAuxY, dxD, dyD;
+    if (cam.orthographic) { // OrthographicCamera::generateRay: shifted origins, one direction
+        oAux = pos + quatRotate(cam.orientation, make3(0.5f * cam.film_width * dxNDC, 0.5f * cam.film_height * yNDC, 0.0f));
+        oAuxY = pos + quatRotate(cam.orientation, make3(0.5f * cam.film_width * xNDC, 0.5f * cam.film_height * dyNDC, 0.0f));
+        dxD = dyD = quatRotate(cam.orientation, make3(0.0f, 0.0f, 1.0f));
+    } else if (cam.lens_radius == 0.0f) {
         oAux = pos;
         dxD = quatRotate(cam.orientation, normalize3(dxViewDir));
         dyD = quatRotate(cam.orientation, normalize3(dyViewDir));
@@ -134,13 +138,14 @@ __device__ __noinline__ void texDifferentials(const DeviceScene& sc, float image
         dxD = quatRotate(cam.orientation, normalize3(dxViewDir * ft - viewOrigin));
         dyD = quatRotate(cam.orientation, normalize3(dyViewDir * ft - viewOrigin));
     }
+    if (!cam.orthographic) oAuxY = oAux; // perspective: both auxiliary rays start at the ray origin
     const float3 p = tf->p, n = tf->n;
     const float minusD = dot3(p, n);
     const float tdx = (minusD - dot3(oAux, n)) / dot3(dxD, n);
-    const float tdy = (minusD - dot3(oAux, n)) / dot3(dyD, n);
+    const float tdy = (minusD - dot3(oAuxY, n)) / dot3(dyD, n);
     if (isnan(tdx) || isnan(tdy)) return;
     const float3 dpdx = (oAux + tdx * dxD) - p;
-    const float3 dpdy = (oAux + tdy * dyD) - p;
+    const float3 dpdy = (oAuxY + tdy * dyD) - p;
     tf->dpdx = dpdx;
     tf->dpdy = dpdy;
     int a0, a1;

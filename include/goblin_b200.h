@@ -207,6 +207,11 @@ typedef struct gb_camera {
     float proj11;
     float lens_radius;
     float focal_distance;
+    /* OrthographicCamera (src/GoblinCamera.cpp:290-329): parallel rays from a film_width x
+     * film_height window, mint 0; proj00 / proj11 then hold matrixOrthoLHD3D's 2 / w, 2 / h */
+    int32_t orthographic;
+    float film_width;
+    float film_height;
 } gb_camera;
 
 typedef struct gb_film_desc {

@@ -519,6 +519,12 @@ struct Oracle {
         V3 pos(c.position[0], c.position[1], c.position[2]);
         RayDiff rd;
         rd.has = true;
+        if (c.orthographic) { // OrthographicCamera::generateRay, src/GoblinCamera.cpp:301-329
+            rd.dxO = pos + quatRotate(c.orientation, V3(0.5f * c.film_width * dxNDC, 0.5f * c.film_height * yNDC, 0.0f));
+            rd.dyO = pos + quatRotate(c.orientation, V3(0.5f * c.film_width * xNDC, 0.5f * c.film_height * dyNDC, 0.0f));
+            rd.dxD = rd.dyD = quatRotate(c.orientation, V3(0.0f, 0.0f, 1.0f));
+            return rd;
+        }
         if (c.lens_radius == 0.0f) {
             rd.dxO = rd.dyO = pos;
             rd.dxD = quatRotate(c.orientation, normalize(dxViewDir));
@@ -786,6 +792,13 @@ struct Oracle {
         V3 viewDir(xView, yView, 1.0f);
         V3 pos(c.position[0], c.position[1], c.position[2]);
         Ray ray;
+        if (c.orthographic) { // OrthographicCamera::generateRay: mint 0
+            ray.o = pos + quatRotate(c.orientation, V3(0.5f * c.film_width * xNDC, 0.5f * c.film_height * yNDC, 0.0f));
+            ray.d = quatRotate(c.orientation, V3(0.0f, 0.0f, 1.0f));
+            ray.mint = 0.0f;
+            ray.maxt = INF;
+            return ray;
+        }
         if (c.lens_radius == 0.0f) {
             ray.o = pos;
             ray.d = quatRotate(c.orientation, normalize(viewDir));

@@ -60,6 +60,14 @@ def _variant(name):
         else:  # every light kind at once, the map missing: the reference falls back to 1 x 1 magenta
             sky["file"] = "_env_missing.exr"
             sc["lights"] = sc["lights"] + [sky]
+    elif name == "ortho":  # OrthographicCamera (src/GoblinCamera.cpp:290-329) with a filtered checkerboard floor
+        sc["camera"]["type"] = "orthographic"
+        sc["camera"]["film_width"] = 9.0
+        sc["textures"] += [{"format": "color", "name": "check", "type": "checkerboard", "texture1": "red", "texture2": "white",
+                            "mapping": "uv", "scale": [9.0, 9.0], "filter": True}]
+        for m in sc["materials"]:
+            if m["name"] == "grey":
+                m["Kd"] = "check"
     elif name.startswith("mask"):
         # Mask materials (src/GoblinMaterial.cpp:747-811): constant and checkerboard alpha, tinted
         # pass-through, around Lambert / Blinn / glass; they bring back the path tracer's isOpaque filter
@@ -161,7 +169,7 @@ def _variant(name):
 
 VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp50", "nolights", "delta_only", "depth1",
             "depth2", "ao10", "tex_point", "tex_filtered", "tex_dof", "ibl", "ibl_only", "ibl_missing",
-            "img_nearest", "img_bilinear", "img_trilinear", "img_ewa", "mask", "mask_ibl"]
+            "img_nearest", "img_bilinear", "img_trilinear", "img_ewa", "mask", "mask_ibl", "ortho"]
 
 
 @pytest.fixture(scope="module")
