@@ -42,7 +42,8 @@ class Material(C.Structure):
                 ("k", C.c_float), ("exponent", C.c_float), ("fresnel", C.c_int32),
                 ("kd_tex", C.c_int32), ("kt_tex", C.c_int32), ("exponent_tex", C.c_int32),
                 ("mask", C.c_int32), ("alpha", C.c_float), ("transparent_color", C.c_float * 3),
-                ("alpha_tex", C.c_int32), ("transparent_tex", C.c_int32)]
+                ("alpha_tex", C.c_int32), ("transparent_tex", C.c_int32), ("bump_tex", C.c_int32),
+                ("normal_tex", C.c_int32)]
 
 
 class Texture(C.Structure):

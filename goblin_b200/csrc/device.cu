@@ -378,7 +378,11 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                         u0 = src.block(id, i, 0);
                         imagePosition(wp, px, py, s, u0, src.table != nullptr, &imageX, &imageY);
                     }
-                    applyTextures(sc, fr.material, MAT, h, o, d, fr, bounce == 0, imageX, imageY, u0.z, u0.w, &m);
+                    // bump / normal maps rewrite the frame: it comes back by value
+                    float3 nOut = fr.n, dpduOut = fr.dpdu;
+                    applyTextures(sc, fr.material, MAT, h, o, d, fr, bounce == 0, imageX, imageY, u0.z, u0.w, &m, &nOut, &dpduOut);
+                    fr.n = nOut;
+                    fr.dpdu = dpduOut;
                 }
                 // Mask around this material (MaskMaterial, GoblinMaterial.cpp:747-811): alpha scales the
                 // masked BSDF, 1 - alpha goes straight through
@@ -576,6 +580,7 @@ __global__ void k_mis_mask(DeviceScene sc, PathState ps, const unsigned int* __r
 // AORenderer::Li (GoblinAO.cpp:12-37): work item = (hit path, occlusion ray).
 // The hit frame of every AO path, once (instead of once per occlusion ray): position + epsilon,
 // tangent, bitangent, normal go to path-state arrays the AO integrator does not otherwise use.
+template <bool TEX> // TEX: the scene has textured materials, i.e. possibly bump / normal maps
 __global__ void k_ao_frames(DeviceScene sc, PathState ps, const unsigned int* ctr) {
     const unsigned int n = ctr[C_MAT0];
     for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
@@ -585,6 +590,12 @@ __global__ void k_ao_frames(DeviceScene sc, PathState ps, const unsigned int* ct
         HitRec h;
         h.t = hv.x; h.b1 = hv.y; h.b2 = hv.z; h.inst = hid.x; h.prim = hid.y;
         Frag fr = buildFragment(sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z));
+        if (TEX) { // bump / normal maps
+            float3 nOut = fr.n, dpduOut = fr.dpdu;
+            perturbOnly(sc, h, make3(ro.x, ro.y, ro.z), make3(rd.x, rd.y, rd.z), fr, &nOut, &dpduOut);
+            fr.n = nOut;
+            fr.dpdu = dpduOut;
+        }
         ShadeFrame sf = makeFrame(fr);
         ps.shO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, 1e-3f * h.t); // Ray(fragment.getPosition(), dir, epsilon)
         ps.thr[i] = make_float4(sf.t.x, sf.t.y, sf.t.z, 0.0f);
@@ -1143,7 +1154,11 @@ bool compileTexturePrograms(const gb_scene_desc* d, std::vector<int4>* matTex, s
         if (mm.kd_tex && !emit(mm.kd_tex - 1, false, &slots.x)) return false;
         if (mm.kt_tex && mm.type == GB_MAT_TRANSPARENT && !emit(mm.kt_tex - 1, false, &slots.y)) return false;
         if (mm.exponent_tex && mm.type == GB_MAT_BLINN && !emit(mm.exponent_tex - 1, true, &slots.z)) return false;
-        (*matTex)[m] = slots;
+        int4 slots2 = make_int4(0, 0, 0, 0);
+        if (mm.bump_tex && !emit(mm.bump_tex - 1, true, &slots.w)) return false;
+        if (mm.normal_tex && !emit(mm.normal_tex - 1, false, &slots2.x)) return false;
+        (*matTex)[2 * (size_t)m] = slots;
+        (*matTex)[2 * (size_t)m + 1] = slots2;
         if (mm.mask) { // MaskMaterial: alpha (float) and transparent colour, constants or programs
             int4 info = make_int4(1, 0, 0, 0);
             if (mm.alpha_tex && !emit(mm.alpha_tex - 1, true, &info.y)) return false;
@@ -1317,7 +1332,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oModelShade = ar.take(16 * (size_t)d->n_models);
     const size_t oMaterials = ar.take(sizeof(DeviceMaterial) * (size_t)d->n_materials);
     // procedural textures: postfix programs of the textured material slots
-    std::vector<int4> matTex(d->n_materials, make_int4(0, 0, 0, 0));
+    std::vector<int4> matTex(2 * (size_t)d->n_materials, make_int4(0, 0, 0, 0));
     std::vector<unsigned int> texProg;
     std::vector<int4> matMask(2 * (size_t)d->n_materials, make_int4(0, 0, 0, 0));
     bool hasMask = false;
@@ -1328,7 +1343,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     }
     const bool hasTextures = !texProg.empty();
     const size_t oMatMask = ar.take(hasMask ? 32 * (size_t)d->n_materials : 0);
-    const size_t oMatTex = ar.take(hasTextures ? 16 * (size_t)d->n_materials : 0);
+    const size_t oMatTex = ar.take(hasTextures ? 32 * (size_t)d->n_materials : 0);
     const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
     const size_t oTexNodes = ar.take(hasTextures ? 16 * (size_t)kTexNodeVec4 * d->n_textures : 0);
     const size_t oTexLevels = ar.take(hasTextures ? 16 * (size_t)d->n_image_levels : 0);
@@ -1779,7 +1794,8 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         if ((rc = extend(0, 1)) != GB_OK) return rc;
         {
             KernelTick tick(ctx, GB_K_OTHER);
-            k_ao_frames<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
+            if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
+            else k_ao_frames<false><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
             ctx->launches++;
         }
         {

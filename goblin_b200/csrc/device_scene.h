@@ -63,7 +63,7 @@ struct DeviceScene {
     const float4* triShade;     // 4 per triangle slot (leaf order): the 3 vertex normals and 3 uvs, 64 bytes
     const DeviceMaterial* materials;
     // procedural textures (texture.cuh); all three null when no material slot is textured
-    const int4* matTex;         // per material: program offset in texProg of kd, kt, exponent (0 = constant), 0
+    const int4* matTex;         // 2 per material: program offsets in texProg of (kd, kt, exponent, bump map), (normal map, -, -, -); 0 = none
     const unsigned int* texProg; // postfix programs: [length, node index ...]; entry 0 is unused
     const float4* texNodes;     // 7 per texture: value | type, options, uv mapping, 3 rows world -> texture, image info
     const int4* matMask;        // Mask materials (mask.cuh), 2 per material: (is mask, alpha program, colour program, 0),

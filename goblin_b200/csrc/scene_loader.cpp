@@ -598,10 +598,6 @@ struct Loader {
         for (const JsonValue& mj : list->arr) {
             ParamSet p(mj);
             std::string type = p.getString("type"), name = p.getString("name");
-            if (p.hasString("bumpmap") || p.hasString("normalmap")) {
-                err = "material '" + name + "': bump / normal maps are outside the accelerated path";
-                return false;
-            }
             gb_material m{};
             if (type == "blinn") { // createBlinnMaterial, src/GoblinMaterial.cpp:834-854
                 m.type = GB_MAT_BLINN;
@@ -652,6 +648,10 @@ struct Loader {
                 ColorSlot kd = getColorTexture(p.getString("Kd"));
                 m = lambert(kd.c);
                 m.kd_tex = kd.tex;
+            }
+            if (type != "mask") { // getBumpShaders, src/GoblinMaterial.cpp:813-824 (a mask defers to the masked material)
+                if (p.hasString("bumpmap")) m.bump_tex = floatTextureIndex(p.getString("bumpmap")) + 1;
+                if (p.hasString("normalmap")) m.normal_tex = colorTextureIndex(p.getString("normalmap")) + 1;
             }
             addMaterial(name, m);
         }

@@ -301,7 +301,9 @@ __device__ __noinline__ float3 imgLookup(const TexImage& im, int filter, float m
 // order; node record: [0] value rgb (image: max anisotropy) | type, [1] int bits: filter, mapping, image
 // address mode, image first level, [2] uv scale.xy, offset.xy, [3..5] spherical world -> texture rows,
 // [6] int bits: image level count, is_float.  Float textures use .x.
-__device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int progOffset, const TexFrag& f) {
+// fu, fv, fp: the uv and position the mappings read (the fragment's own, or the bump map's offset probes)
+__device__ __noinline__ float3 evalTextureAt(const DeviceScene& sc, unsigned int progOffset, const TexFrag& f, float fu,
+    float fv, float3 fp) {
     float3 stack[kTexStack];
     int sp = 0;
     const unsigned int* prog = sc.texProg + progOffset;
@@ -320,10 +322,10 @@ __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int p
             float s, t, dsdx, dtdx, dsdy, dtdy;
             if (opt.y == GB_MAPPING_SPHERICAL) { // SphericalMapping::map
                 const float4 r0 = __ldg(node + 3), r1 = __ldg(node + 4), r2 = __ldg(node + 5);
-                pointToST(r0, r1, r2, f.p, &s, &t);
+                pointToST(r0, r1, r2, fp, &s, &t);
                 float sdx, tdx, sdy, tdy;
-                pointToST(r0, r1, r2, f.p + f.dpdx, &sdx, &tdx);
-                pointToST(r0, r1, r2, f.p + f.dpdy, &sdy, &tdy);
+                pointToST(r0, r1, r2, fp + f.dpdx, &sdx, &tdx);
+                pointToST(r0, r1, r2, fp + f.dpdy, &sdy, &tdy);
                 dsdx = sdx - s;
                 if (dsdx > 0.5f) dsdx -= 1.0f; else if (dsdx < -0.5f) dsdx += 1.0f;
                 dsdy = sdy - s;
@@ -332,8 +334,8 @@ __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int p
                 dtdy = tdy - t;
             } else { // UVMapping::map
                 const float4 m = __ldg(node + 2);
-                s = m.x * f.u + m.z;
-                t = m.y * f.v + m.w;
+                s = m.x * fu + m.z;
+                t = m.y * fv + m.w;
                 dsdx = m.x * f.dudx; dtdx = m.y * f.dvdx;
                 dsdy = m.x * f.dudy; dtdy = m.y * f.dvdy;
             }
@@ -365,16 +367,58 @@ __device__ __noinline__ float3 evalTexture(const DeviceScene& sc, unsigned int p
     }
     return stack[0];
 }
+__device__ __forceinline__ float3 evalTexture(const DeviceScene& sc, unsigned int progOffset, const TexFrag& f) {
+    return evalTextureAt(sc, progOffset, f, f.u, f.v, f.p);
+}
+
+// Material::perturb -> BumpShaders::evaluate (GoblinMaterial.cpp:221-281): height-field bump mapping by
+// forward differences of the bump texture along dpdu / dpdv, then a tangent-space normal map.  Rewrites the
+// fragment's normal and tangents; the lookups see a fresh Fragment (no differentials).
+__device__ __noinline__ void perturbFragment(const DeviceScene& sc, unsigned int bumpProg, unsigned int normalProg, TexFrag* tf) {
+    if (bumpProg) {
+        const float3 p = tf->p, n = tf->n;
+        const float bumpD = evalTexture(sc, bumpProg, *tf).x;
+        const float du = 0.002f, dv = 0.002f;
+        // the two probes: position and uv moved along dpdu / dpdv (Fragment copies in the reference)
+        const float bumpDdu = evalTextureAt(sc, bumpProg, *tf, tf->u + du, tf->v + 0.0f, p + du * tf->dpdu).x;
+        const float3 bumpDPDU = tf->dpdu + (bumpDdu - bumpD) / du * n;
+        const float bumpDdv = evalTextureAt(sc, bumpProg, *tf, tf->u + 0.0f, tf->v + dv, p + dv * tf->dpdv).x;
+        const float3 bumpDPDV = tf->dpdv + (bumpDdv - bumpD) / dv * n;
+        float3 bumpN = normalize3(cross3(bumpDPDU, bumpDPDV));
+        if (dot3(bumpN, n) < 0.0f) bumpN = bumpN * -1.0f;
+        tf->n = bumpN;
+        tf->dpdu = bumpDPDU;
+        tf->dpdv = bumpDPDV;
+    }
+    if (normalProg) {
+        const float3 c = evalTexture(sc, normalProg, *tf);
+        const float3 nShade = 2.0f * c - make3(1.0f, 1.0f, 1.0f);
+        Frag tmp;
+        tmp.n = tf->n;
+        tmp.dpdu = tf->dpdu;
+        float3 nWorld = normalize3(shadeToWorld(makeFrame(tmp), nShade));
+        if (dot3(nWorld, tf->n) < 0.0f) nWorld = nWorld * -1.0f;
+        tf->n = nWorld;
+    }
+}
 
 // Looks up the textured slots of material `material` at this hit and writes them over the constants
-// in m.  primary: the hit of a camera ray (the only rays that carry differentials,
+// in m; applies the material's bump / normal maps to the fragment first, like Scene::intersect does.
+// primary: the hit of a camera ray (the only rays that carry differentials,
 // GoblinPathtracer.cpp:77 + RayDifferential(p, wi, epsilon) afterwards).
 __device__ __noinline__ void applyTextures(const DeviceScene& sc, int material, int matType, const HitRec& hit, float3 o,
-    float3 d, const Frag& fr, bool primary, float imageX, float imageY, float lensU1, float lensU2, DeviceMaterial* m) {
-    const int4 slots = __ldg(sc.matTex + material); // program offsets: kd, kt, exponent; 0 = constant
-    if ((slots.x | slots.y | slots.z) == 0) return;
+    float3 d, const Frag& fr, bool primary, float imageX, float imageY, float lensU1, float lensU2, DeviceMaterial* m,
+    float3* nOut, float3* dpduOut) {
+    const int4 slots = __ldg(sc.matTex + 2 * (size_t)material);      // programs: kd, kt, exponent, bump; 0 = none
+    const int4 slots2 = __ldg(sc.matTex + 2 * (size_t)material + 1); // normal map, -, -, -
+    if ((slots.x | slots.y | slots.z | slots.w | slots2.x) == 0) return;
     TexFrag tf;
     texFragment(sc, hit, o, d, fr, &tf);
+    if (slots.w | slots2.x) {
+        perturbFragment(sc, (unsigned int)slots.w, (unsigned int)slots2.x, &tf);
+        *nOut = tf.n;
+        *dpduOut = tf.dpdu;
+    }
     if (primary) texDifferentials(sc, imageX, imageY, lensU1, lensU2, &tf);
     if (slots.x) {
         const float3 c = evalTexture(sc, (unsigned int)slots.x, tf);
@@ -387,6 +431,19 @@ __device__ __noinline__ void applyTextures(const DeviceScene& sc, int material, 
     if (slots.z && matType == GB_MAT_BLINN) { // blinn packing: ktEta = (k, exponent, fresnel, eta)
         m->ktEta.y = evalTexture(sc, (unsigned int)slots.z, tf).x;
     }
+}
+
+// The perturbed frame alone (ambient occlusion only needs the hit frame)
+__device__ __noinline__ void perturbOnly(const DeviceScene& sc, const HitRec& hit, float3 o, float3 d, const Frag& fr,
+    float3* nOut, float3* dpduOut) {
+    const int4 slots = __ldg(sc.matTex + 2 * (size_t)fr.material);
+    const int4 slots2 = __ldg(sc.matTex + 2 * (size_t)fr.material + 1);
+    if ((slots.w | slots2.x) == 0) return;
+    TexFrag tf;
+    texFragment(sc, hit, o, d, fr, &tf);
+    perturbFragment(sc, (unsigned int)slots.w, (unsigned int)slots2.x, &tf);
+    *nOut = tf.n;
+    *dpduOut = tf.dpdu;
 }
 
 } // namespace gb

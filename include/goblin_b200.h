@@ -131,6 +131,11 @@ typedef struct gb_material {
     float transparent_color[3];
     int32_t alpha_tex;         /* 1 + texture index (a float texture), 0 = the constant alpha    */
     int32_t transparent_tex;   /* 1 + texture index, 0 = the constant transparent_color          */
+    /* BumpShaders (src/GoblinMaterial.cpp:221-281), applied to every hit of the material before it is
+     * shaded (Scene::intersect -> Material::perturb): 1 + texture index, 0 = none.  Constant textures
+     * are referenced too: even a flat bump map replaces the normal by that of the dpdu x dpdv frame. */
+    int32_t bump_tex;          /* float texture: height                                          */
+    int32_t normal_tex;        /* colour texture: tangent-space normal, 2 c - 1                  */
 } gb_material;
 
 /* Procedural textures (src/GoblinTexture.cpp:292-427): constant, checkerboard

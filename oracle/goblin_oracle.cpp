@@ -418,6 +418,40 @@ struct Oracle {
 
     // Scene::intersect -> BVH -> InstancedPrimitive::intersect -> Model::intersect
     // (src/GoblinScene.cpp:75-83, src/GoblinPrimitive.cpp:103-112, src/GoblinModel.cpp:39-52)
+    // Material::perturb -> BumpShaders::evaluate, src/GoblinMaterial.cpp:221-281 (Scene::intersect applies it
+    // to every hit it returns, src/GoblinScene.cpp:78-81)
+    void perturb(const gb_material& m, Frag& f) const {
+        if (m.bump_tex) {
+            V3 p = f.p, n = f.n;
+            float bumpD = texLookup(m.bump_tex - 1, f).x;
+            float du = 0.002f;
+            Frag fdu = f;
+            fdu.p = p + du * f.dpdu;
+            fdu.u = f.u + du; // uv + Vector2(du, 0)
+            fdu.v = f.v + 0.0f;
+            float bumpDdu = texLookup(m.bump_tex - 1, fdu).x;
+            V3 bumpDPDU = f.dpdu + (bumpDdu - bumpD) / du * n;
+            float dv = 0.002f;
+            Frag fdv = f;
+            fdv.p = p + dv * f.dpdv;
+            fdv.u = f.u + 0.0f;
+            fdv.v = f.v + dv;
+            float bumpDdv = texLookup(m.bump_tex - 1, fdv).x;
+            V3 bumpDPDV = f.dpdv + (bumpDdv - bumpD) / dv * n;
+            V3 bumpN = normalize(cross(bumpDPDU, bumpDPDV));
+            if (dot(bumpN, n) < 0.0f) bumpN = bumpN * -1.0f;
+            f.n = bumpN;
+            f.dpdu = bumpDPDU;
+            f.dpdv = bumpDPDV;
+        }
+        if (m.normal_tex) {
+            V3 c = texLookup(m.normal_tex - 1, f);
+            V3 nShade = 2.0f * c - V3(1.0f, 1.0f, 1.0f);
+            V3 nWorld = normalize(shadeToWorld(f, nShade));
+            if (dot(nWorld, f.n) < 0.0f) nWorld = nWorld * -1.0f;
+            f.n = nWorld;
+        }
+    }
     // filter: the IntersectFilter of src/GoblinPathtracer.cpp:5-11 (0 = none, 1 = isOpaque, 2 = notOpaque).
     // The reference applies it per refined Model, after walking a mesh's BVH (src/GoblinModel.cpp:44);
     // the material belongs to the model, so skipping the whole instance gives the same hits.
@@ -427,6 +461,15 @@ struct Oracle {
         return (filter == 1) != opaque;
     }
     bool intersect(Ray& ray, float* epsilon, Isect* isect, Stats& st, int filter = 0) const {
+        if (!intersectGeometry(ray, epsilon, isect, st, filter)) return false;
+        // *fragment = Fragment(position, normal, uv, dpdu, dpdv): a fresh Fragment has no differentials
+        isect->frag.dpdx = isect->frag.dpdy = V3();
+        isect->frag.dudx = isect->frag.dvdx = isect->frag.dudy = isect->frag.dvdy = 0.0f;
+        const gb_material& m = d->materials[d->models[d->instances[isect->inst].model].material];
+        if (m.bump_tex | m.normal_tex) perturb(m, isect->frag);
+        return true;
+    }
+    bool intersectGeometry(Ray& ray, float* epsilon, Isect* isect, Stats& st, int filter) const {
         st.closest++;
         return walk<false>(d->top_nodes, d->n_top_nodes, ray, st, [&](uint32_t slot) {
             uint32_t ii = d->top_order[slot];
