@@ -85,7 +85,7 @@ class FilmDesc(C.Structure):
 
 class RenderSetting(C.Structure):
     _fields_ = [("method", C.c_int32), ("spp", C.c_int32), ("max_ray_depth", C.c_int32),
-                ("ao_sample_num", C.c_int32)]
+                ("ao_sample_num", C.c_int32), ("gpu_num", C.c_int32), ("seed", C.c_int32)]
 
 
 class SceneDesc(C.Structure):

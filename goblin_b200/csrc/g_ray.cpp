@@ -23,8 +23,8 @@ int main(int argc, char** argv) {
         std::cout << "Usage: g_ray scene.json" << std::endl;
         return 0;
     }
-    int gpus = 1, spp = 0, depth = 0;
-    unsigned long long seed = 1;
+    int gpus = 0, spp = 0, depth = 0;        // 0: take render_setting.gpu_num / seed, else 1
+    unsigned long long seed = 0;
     std::string method, outFile, accel = "equal_count";
     bool stats = false;
     for (int i = 2; i < argc; ++i) {

@@ -176,6 +176,10 @@ public:
         }
         ScenePtr scene(new Scene(s));
         std::shared_ptr<Film> film(new Film(scene->desc().film, scene->outputPath()));
+        // 0 = not given by the caller: the scene's optional render_setting.gpu_num / seed, else 1
+        const gb_render_setting& rs = scene->desc().setting;
+        if (gpuNum <= 0) gpuNum = rs.gpu_num > 0 ? rs.gpu_num : 1;
+        if (seed == 0) seed = rs.seed > 0 ? (unsigned long long)rs.seed : 1ull;
         return new RenderContext(std::make_shared<GpuRenderer>(gpuNum, seed), scene, film);
     }
 };

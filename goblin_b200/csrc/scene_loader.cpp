@@ -287,6 +287,8 @@ struct Loader {
         out->threadNum = s.getInt("thread_num", 0);
         rs.max_ray_depth = std::max(1, s.getInt("max_ray_depth", 5));
         rs.ao_sample_num = s.getInt("ao_sample_num", 25);
+        rs.gpu_num = std::max(0, s.getInt("gpu_num", 0));
+        rs.seed = std::max(0, s.getInt("seed", 0));
         {
             // AORenderer::querySampleQuota -> SampleQuota::requestTwoDQuota rounds the ray count
             // up to a perfect square (src/GoblinSampler.cpp:29-33, src/GoblinUtils.h:126-132)

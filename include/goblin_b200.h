@@ -236,6 +236,10 @@ typedef struct gb_render_setting {
     int32_t spp;           /* sample_per_pixel as written in the scene         */
     int32_t max_ray_depth;
     int32_t ao_sample_num; /* rounded up to a perfect square, as the reference's sample quota does */
+    /* optional keys this implementation adds to "render_setting" (ignored by the reference):
+     * how many GPUs to shard the samples over and the Philox seed; 0 = not given */
+    int32_t gpu_num;
+    int32_t seed;
 } gb_render_setting;
 
 /* Flattened scene.  All pointers are host pointers owned by whoever filled the
