@@ -89,3 +89,18 @@ def test_g_ray_default_output_is_the_scene_name(built):
         for q in (p, os.path.join(d, "_cli_default.exr")):
             if os.path.exists(q):
                 os.remove(q)
+
+
+@pytest.mark.gpu
+def test_g_ray_two_gpus_equals_one(built, tmp_path):
+    """--gpus 2: one host thread per GPU renders half of the per-pixel sample indices of a scene replica,
+    the films are summed on the host (Film::mergeTile) and written through GPU 0: the same sample set,
+    so the same image up to float summation order."""
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    a, b = str(tmp_path / "one.pfm"), str(tmp_path / "two.pfm")
+    r1 = _run(util.TINY_PT, "--spp", "16", "--seed", "9", "--out", a)
+    r2 = _run(util.TINY_PT, "--spp", "16", "--seed", "9", "--gpus", "2", "--out", b, "--stats")
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    assert json.loads([l for l in r2.stdout.splitlines() if l.startswith("{")][-1])["gpus"] == 2
+    assert np.allclose(_read_pfm(a), _read_pfm(b), rtol=1e-4, atol=1e-5)
