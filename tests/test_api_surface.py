@@ -1,0 +1,96 @@
+"""The rest of the C ABI: device-resident trace calls, execution knobs that must not change results,
+kernel timing, upload accounting, status codes for calls made out of order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from goblin_b200 import api
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    wb = np.array(scene.desc.world_bound[:], np.float32)
+    o = rng.uniform(wb[:3], wb[3:], (n, 3))
+    d = rng.uniform(wb[:3], wb[3:], (n, 3)) - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d, np.full((n, 1), 1e-3), np.full((n, 1), np.inf)], 1).astype(np.float32)
+
+
+def test_device_resident_trace_equals_host_buffer_trace(built):
+    import torch
+    scene = api.Scene(util.gen_scene("bunny") + "/bunny_pt.json")
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    rays = _rays(scene, 200_000, 4)
+    want_h, want_o = ctx.trace_closest(rays), ctx.trace_any(rays)
+    d_rays = torch.from_numpy(rays).cuda()
+    d_hits = torch.zeros((len(rays), 4), dtype=torch.float32, device="cuda")
+    d_occ = torch.zeros(len(rays), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.trace_closest_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+    ctx.trace_any_device(d_rays.data_ptr(), len(rays), d_occ.data_ptr())
+    ctx.synchronize()
+    assert ctx.last_kernel_ms() > 0.0
+    got = d_hits.cpu().numpy().view(api.HIT_DTYPE).reshape(-1)
+    assert got.tobytes() == want_h.tobytes()
+    assert np.array_equal(d_occ.cpu().numpy(), want_o)
+
+
+def test_execution_knobs_do_not_change_results(built):
+    scene = api.Scene(util.gen_scene("spheres") + "/spheres_pt.json")
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    rays = _rays(scene, 300_000, 6)
+    base = ctx.trace_closest(rays)
+    ctx.film_clear()
+    ctx.render(seed=2, spp_total=1)
+    film = ctx.film_download()
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        ctx.set_tuning([int(v) for v in rng.integers(0, 34, 4)] + [int(rng.integers(1, 8))])
+        ctx.set_wave_paths(int(rng.integers(50_000, 2_000_000)))
+        assert ctx.trace_closest(rays).tobytes() == base.tobytes()
+        ctx.film_clear()
+        ctx.render(seed=2, spp_total=1)
+        again = ctx.film_download()
+        assert np.allclose(again, film, rtol=1e-5, atol=1e-6)  # same samples; film atomics may reorder sums
+
+
+def test_kernel_timing_and_upload_accounting(built):
+    scene = api.Scene(util.TINY_PT)
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    assert 0 < ctx.upload_bytes() < 64 << 20
+    ctx.enable_kernel_timing(True)
+    ctx.reset_kernel_times()
+    ctx.reset_counters()
+    ctx.film_clear()
+    ctx.render(seed=1, spp_total=4)
+    ctx.synchronize()
+    times = ctx.kernel_times()
+    ctx.enable_kernel_timing(False)
+    for cls in ("raygen", "extend", "shade", "shadow", "film"):
+        ms, launches = times[cls]
+        assert ms > 0.0 and launches > 0, cls
+    assert times["ao"][1] == 0
+    assert ctx.counters()["kernel_launches"] >= sum(v[1] for v in times.values())
+    ptr, n_floats = ctx.film_device_ptr()
+    assert ptr and n_floats == scene.desc.film.xres * scene.desc.film.yres * 4
+
+
+def test_calls_out_of_order_return_status_codes(built):
+    lib = api.lib()
+    h = C.c_void_p()
+    assert lib.gb_create(0, C.byref(h)) == 0
+    p = api.RenderParams(1, 4, 0, 4, 0, -1, 0)
+    assert lib.gb_render(h, C.byref(p)) == 4  # GB_ERR_STATE: no scene uploaded
+    assert b"no scene" in lib.gb_last_error()
+    buf = np.zeros(16, np.float32)
+    assert lib.gb_film_download(h, buf.ctypes.data) == 4
+    assert lib.gb_trace_closest(h, buf.ctypes.data, 1, buf.ctypes.data) == 4
+    assert lib.gb_create(99, C.byref(C.c_void_p())) == 1  # GB_ERR_INVALID: no such device
+    assert lib.gb_destroy(h) == 0
