@@ -243,3 +243,36 @@ def test_full_size_scenes_ray_batches(built, kind, json_name, n):
     half = rays[::2]
     assert np.array_equal(ctx.trace_closest(half)["t"].view(np.uint32), ctx.trace_closest(rays)["t"][::2].view(np.uint32))
     ctx.close()
+
+
+def test_empty_scene_and_empty_mesh(built):
+    """Edge cases of the scene format: no primitives at all (an empty top-level BVH: every ray misses,
+    the film only gathers weights) and a mesh whose OBJ file is missing (the reference keeps an empty mesh:
+    BVH::intersect returns false for it)."""
+    import json
+    import os
+    d = os.path.dirname(util.TINY_PT)
+    sc = json.load(open(util.TINY_PT))
+    sc["primitives"] = []
+    sc["lights"] = [l for l in sc["lights"] if l["type"] == "point"]
+    scene = api.Scene(json_text=json.dumps(sc), scene_dir=d)
+    assert scene.desc.n_instances == 0 and scene.desc.n_top_nodes == 0
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    rays = np.array([[0, 0, -5, 0, 0, 1, 1e-3, np.inf]] * 1000, np.float32)
+    assert (ctx.trace_closest(rays)["inst"] == -1).all() and not ctx.trace_any(rays).any()
+    ctx.film_clear()
+    ctx.render(seed=1, spp_total=4)
+    film = ctx.film_download()
+    assert (film[..., :3] == 0).all() and film[..., 3].min() > 0
+    ctx.close()
+    sc = json.load(open(util.TINY_PT))
+    sc["geometries"][0]["file"] = "models/_missing.obj"
+    p = os.path.join(d, "_missing_mesh.json")
+    json.dump(sc, open(p, "w"))
+    try:
+        ctx, scene = _ctx(p)
+        _check_traces(ctx, scene, _random_rays(scene, 50_000, 3))
+        ctx.close()
+    finally:
+        os.remove(p)
