@@ -1342,6 +1342,9 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         if (!compileTexturePrograms(d, &matTex, &matMask, &texProg, &terr)) return gb::failWith(GB_ERR_INVALID, terr);
     }
     const bool hasTextures = !texProg.empty();
+    if (hasMask && (topDepth > kSimpleStack || modelDepth > kSimpleStack)) {
+        return gb::failWith(GB_ERR_LIMIT, "mask scenes walk each BVH level with the reference's todo[64]: a tree is deeper");
+    }
     const size_t oMatMask = ar.take(hasMask ? 32 * (size_t)d->n_materials : 0);
     const size_t oMatTex = ar.take(hasTextures ? 32 * (size_t)d->n_materials : 0);
     const size_t oTexProg = ar.take(hasTextures ? 4 * texProg.size() : 0);
