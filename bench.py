@@ -455,7 +455,9 @@ def main():
         if os.path.exists(tr_path):
             traffic = json.load(open(tr_path)).get(args.scene)
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                    "frac": achieved / peak, "peak_source": peak_src,
+                    "frac_of_nominal_8000": achieved / 8000.0,  # north_star quotes the 8 TB/s nominal figure as well
+                    "traffic": traffic,
                     "algorithmic_bytes_per_ray": kbytes / max(krays, 1),
                     "algorithmic_bytes_per_launch": kbytes / max(launches_per_step, 1),
                     "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,
@@ -463,7 +465,7 @@ def main():
                     "kernel_share_of_step": kms[0] / total_ms,
                     "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]}}
         if stats_failed:
-            roofline.update({"achieved": None, "frac": None,
+            roofline.update({"achieved": None, "frac": None, "frac_of_nominal_8000": None,
                              "note": "no algorithmic bytes: the counters pass was skipped (--no-stats)" if args.no_stats
                              else "the counters pass failed; no algorithmic bytes"})
         line = {"metric": METRIC.get(args.scene, "path-traced Msamples/s (%s)" % args.scene), "value": value, "unit": "Msamples/s",
