@@ -26,7 +26,9 @@ __device__ __forceinline__ bool instanceFilteredOut(const DeviceScene& sc, unsig
 }
 
 // BVH::intersect / BVH::occluded over one level.  leaf(slot) tests primitive `slot` and returns true
-// to stop (any-hit); the closest-hit caller shrinks maxt through the reference it captured.
+// to stop (any-hit).  maxt is taken BY REFERENCE on purpose: the closest-hit caller's leaf functor shrinks
+// the same variable when it accepts a hit, and the box tests of the remaining walk must see the shrunk
+// value, like ray.maxt in the reference.
 template <typename Leaf>
 __device__ __forceinline__ bool simpleWalk(const float4* __restrict__ nodes, unsigned int nNodes, float3 o, float3 d,
     float mint, const float& maxt, Leaf leaf) {
