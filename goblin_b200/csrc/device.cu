@@ -391,7 +391,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 me.alpha = 1.0f; me.tc = make3(0.0f, 0.0f, 0.0f);
                 if (TEX && sc.matMask && __ldg(sc.matMask + 2 * (size_t)fr.material).x) {
                     masked = true;
-                    me = maskAt(sc, fr.material, h, o, d, fr, nullptr);
+                    me = maskAt(sc, fr.material, h, o, d, fr);
                 }
                 if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) { // specular BSDFs evaluate to black: no light sample survives
                     LightSampleResult ls = sampleLight<ML>(sc, li, fr.p, eps, uA.x, uA.y, uA.z);

@@ -138,7 +138,7 @@ __device__ __noinline__ bool simpleAny(const DeviceScene& sc, float3 o, float3 d
 // (no differentials: evalAttenuation and the bounce rays work on fresh Fragments).
 struct MaskEval { float alpha; float3 tc; };
 __device__ __noinline__ MaskEval maskAt(const DeviceScene& sc, int material, const HitRec& hit, float3 o, float3 d,
-    const Frag& fr, const TexFrag* tfIn) {
+    const Frag& fr) {
     const int4 info = __ldg(sc.matMask + 2 * (size_t)material);         // flag, alpha program, colour program, -
     const float4 val = __ldg(reinterpret_cast<const float4*>(sc.matMask + 2 * (size_t)material + 1)); // alpha, tc rgb
     MaskEval e;
@@ -146,8 +146,7 @@ __device__ __noinline__ MaskEval maskAt(const DeviceScene& sc, int material, con
     e.tc = make3(val.y, val.z, val.w);
     if (info.y | info.z) {
         TexFrag tf;
-        if (tfIn) tf = *tfIn;
-        else texFragment(sc, hit, o, d, fr, &tf);
+        texFragment(sc, hit, o, d, fr, &tf);
         if (info.y) e.alpha = evalTexture(sc, (unsigned int)info.y, tf).x;
         if (info.z) e.tc = evalTexture(sc, (unsigned int)info.z, tf);
     }
@@ -162,7 +161,7 @@ __device__ __noinline__ float3 evalAttenuation(const DeviceScene& sc, float3 o, 
         HitRec h;
         if (!simpleClosest(sc, o, d, curMint, maxt, FILTER_NOT_OPAQUE, &h)) break;
         const Frag fr = buildFragment(sc, h, o, d);
-        const MaskEval e = maskAt(sc, fr.material, h, o, d, fr, nullptr);
+        const MaskEval e = maskAt(sc, fr.material, h, o, d, fr);
         thr = mul3(thr, (1.0f - e.alpha) * e.tc); // sampleBSDF(..., BSDFnullptr)
         if (thr.x == 0.0f && thr.y == 0.0f && thr.z == 0.0f) break;
         curMint = h.t + 1e-3f * h.t; // currentRay.mint = currentRay.maxt + epsilon
