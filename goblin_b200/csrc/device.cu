@@ -818,6 +818,9 @@ struct gb_context {
     int device = 0;
     int numSMs = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // the shadow kernel of bounce b runs here, beside the extend of bounce b + 1
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool overlapTails = true;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool haveScene = false;
     DeviceScene sc{};
@@ -892,8 +895,9 @@ void freeWave(gb_context* ctx) {
 // Kernel-class timing: an event pair around each launch, resolved at collect time.
 struct KernelTick {
     gb_context* ctx;
+    cudaStream_t on;
     bool live = false;
-    KernelTick(gb_context* c, int cls) : ctx(c) {
+    KernelTick(gb_context* c, int cls, cudaStream_t s = nullptr) : ctx(c), on(s ? s : c->stream) {
         if (!ctx->timingOn) return;
         if (ctx->evUsed + 2 > ctx->evPool.size()) {
             for (int k = 0; k < 2; ++k) {
@@ -902,13 +906,13 @@ struct KernelTick {
                 ctx->evPool.push_back(e);
             }
         }
-        cudaEventRecord(ctx->evPool[ctx->evUsed], ctx->stream);
+        cudaEventRecord(ctx->evPool[ctx->evUsed], on);
         ctx->evClass.push_back(cls);
         live = true;
     }
     ~KernelTick() {
         if (!live) return;
-        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], ctx->stream);
+        cudaEventRecord(ctx->evPool[ctx->evUsed + 1], on);
         ctx->evUsed += 2;
     }
 };
@@ -998,6 +1002,10 @@ int gb_create(int device, gb_context** out) {
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->numSMs = prop.multiProcessorCount;
     GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    GB_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+    ctx->overlapTails = std::getenv("GB_NO_OVERLAP") == nullptr;
     GB_CUDA(cudaEventCreate(&ctx->evStart));
     GB_CUDA(cudaEventCreate(&ctx->evStop));
     GB_CUDA(cudaMalloc((void**)&ctx->ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
@@ -1025,6 +1033,9 @@ int gb_destroy(gb_context* ctx) {
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream2);
+    cudaEventDestroy(ctx->evFork);
+    cudaEventDestroy(ctx->evJoin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GB_OK;
@@ -1818,6 +1829,18 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         ctx->launches += 2;
     } else if (ctx->sc.nLights > 0) { // no lights: Li returns black before tracing (GoblinPathtracer.cpp:53-56)
         const int depth = wp.maxDepth;
+        // Tail overlap: the shadow kernel of bounce b and the extend kernel of bounce b + 1 touch disjoint
+        // data (one adds to L, the other writes hits), and both are single-wave persistent grids whose last
+        // CTAs run on a mostly idle machine.  The shadow kernel goes to a second stream, so the next
+        // extend's CTAs start as its CTAs retire; the shade kernels of bounce b + 1 (which reuse the shadow
+        // queue and may touch L) wait for it.  Not with an environment light (k_miss adds to L right after
+        // the extend) and not while counting.
+        const bool overlap = ctx->overlapTails && !ctx->statsOn && !ctx->sc.hasEnvLight && !ctx->sc.matMask;
+        bool pendingJoin = false;
+        auto join = [&]() {
+            if (pendingJoin) cudaStreamWaitEvent(st, ctx->evJoin, 0);
+            pendingJoin = false;
+        };
         for (int b = 0; b < depth; ++b) {
             // the last extend only feeds the BSDF-sampled emission term; skip it when no area light exists
             const bool last = b == depth - 1;
@@ -1832,6 +1855,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             unsigned int* cn = ctx->ctr + (b + 1) * kCtrStride;
             unsigned int* qn = ps.qExtend[(b + 1) & 1];
             int eo = last ? 1 : 0;
+            join(); // the previous bounce's shadow kernel is done with the shadow queue and L
             {
                 KernelTick tick(ctx, GB_K_SHADE);
 #define GB_SHADE(MATV, MLV) k_shade<MATV, MLV, false><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
@@ -1856,17 +1880,29 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                 if (ctx->sc.hasAreaLight | ctx->sc.hasEnvLight) k_mis_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, qn, cn, ctx->stats);
                 ctx->launches += 2;
             } else if (!last) {
-                KernelTick tick(ctx, GB_K_SHADOW);
-                if (ctx->statsOn) {
-                    if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
-                    k_shadow<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
-                } else {
-                    if ((rc = setupTraceKernel(ctx, k_shadow<false>, &grid)) != GB_OK) return rc;
-                    k_shadow<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
+                cudaStream_t ss = overlap ? ctx->stream2 : st;
+                if (overlap) {
+                    GB_CUDA(cudaEventRecord(ctx->evFork, st));
+                    GB_CUDA(cudaStreamWaitEvent(ss, ctx->evFork, 0));
+                }
+                {
+                    KernelTick tick(ctx, GB_K_SHADOW, ss);
+                    if (ctx->statsOn) {
+                        if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
+                        k_shadow<true><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
+                    } else {
+                        if ((rc = setupTraceKernel(ctx, k_shadow<false>, &grid)) != GB_OK) return rc;
+                        k_shadow<false><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
+                    }
+                }
+                if (overlap) {
+                    GB_CUDA(cudaEventRecord(ctx->evJoin, ss));
+                    pendingJoin = true;
                 }
                 ctx->launches++;
             }
         }
+        join(); // the film kernel (or the caller) reads L
     }
     if (toFilm) {
         const float wx = ctx->sc.filterWidthX, wy = ctx->sc.filterWidthY;
