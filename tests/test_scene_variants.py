@@ -200,18 +200,25 @@ VARIANTS = ["dof", "box", "triangle", "mitchell", "wide_gaussian", "crop", "spp5
             "img_nearest", "img_bilinear", "img_trilinear", "img_ewa", "mask", "mask_ibl", "ortho", "bump", "bump_ao"]
 
 
+def write_env_maps(d):
+    """The two HDR maps the image-textured / image-lit variants read: a small very bright region on noise,
+    written by the product's EXR writer (deterministic: the golden vectors depend on them)."""
+    rng = np.random.default_rng(5)
+    env = []
+    for w, h in ((40, 24), (32, 16)):
+        img = rng.uniform(0.05, 1.0, (h, w, 3)).astype(np.float32)
+        img[h // 6:h // 6 + 3, w // 4:w // 4 + 4] *= 40.0
+        env.append(os.path.join(d, f"_env_{w}x{h}.exr"))
+        api.write_rgb(env[-1], img)
+    return env
+
+
 @pytest.fixture(scope="module")
 def variant_files(tmp_path_factory, built):
     """JSON files next to the tiny scene's models (mesh paths are relative to the scene file)."""
     out = {}
     d = os.path.dirname(util.TINY_PT)
-    rng = np.random.default_rng(5)
-    env = []
-    for w, h in ((40, 24), (32, 16)):  # HDR maps with a small very bright region, written by the product's EXR writer
-        img = rng.uniform(0.05, 1.0, (h, w, 3)).astype(np.float32)
-        img[h // 6:h // 6 + 3, w // 4:w // 4 + 4] *= 40.0
-        env.append(os.path.join(d, f"_env_{w}x{h}.exr"))
-        api.write_rgb(env[-1], img)
+    env = write_env_maps(d)
     for v in VARIANTS:
         path = os.path.join(d, f"_variant_{v}.json")
         with open(path, "w") as f:
@@ -430,3 +437,39 @@ def test_exr_reader_matches_the_reference_loader(built, tmp_path, compression, p
     tex = np.ctypeslib.as_array(scene.desc.image_texels, (scene.desc.n_image_texels * 4,))
     assert np.array_equal(tex.view(np.uint32), dump["ibl0.level0"].view(np.uint32))
     assert dump["ibl0.level0"].reshape(-1, 4)[:, :3].max() > 1.0  # really the image, not the magenta fallback
+
+
+# ---- committed golden vectors from the unmodified reference (tests/golden/make_variant_golden.py): they travel
+# to the GPU box, where /root/reference does not exist
+
+GOLDEN_VARIANTS = ["tex_filtered", "ibl", "img_ewa", "mask", "mask_ibl", "bump", "ortho"]
+
+
+def _variant_golden():
+    return dict(np.load(os.path.join(util.GOLDEN, "variants_li.npz")))
+
+
+@pytest.mark.parametrize("v", GOLDEN_VARIANTS)
+def test_oracle_matches_reference_goldens(variant_files, v):
+    g = _variant_golden()
+    scene = api.Scene(variant_files[v])
+    L, calls = op.li(scene, g[v + ".rows"], calls=True)
+    same = (calls == g[v + ".calls"]).all(axis=1)
+    assert same.mean() > 0.995
+    close = np.isclose(L[same], g[v + ".L"][same], rtol=1e-4, atol=1e-5).all(axis=1)
+    assert close.mean() > 0.995
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("v", GOLDEN_VARIANTS)
+def test_gpu_matches_reference_goldens(variant_files, v):
+    """The CUDA path against radiance values computed by the reference itself."""
+    g = _variant_golden()
+    scene = api.Scene(variant_files[v])
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    got = ctx.li(g[v + ".rows"])
+    close = np.isclose(got, g[v + ".L"], rtol=2e-3, atol=2e-4).all(axis=1)
+    assert close.mean() >= 0.99, v
+    assert abs(got.sum() - g[v + ".L"].sum()) <= 2e-2 * g[v + ".L"].sum()
+    ctx.close()
