@@ -237,3 +237,74 @@ def test_obj_loader_errors(built, tmp_path):
     scene = api.Scene(str(d / "scene.json"))
     box = [m for m in scene.models() if m.kind == 0 and m.tri_count == 0]
     assert len(box) == 1 and box[0].node_count == 0
+
+
+# ---- materials / textures of the widened surface: what the loader folds, references and refuses
+
+def _tiny(mutator):
+    import json
+    sc = json.load(open(util.TINY_PT))
+    mutator(sc)
+    return api.Scene(json_text=json.dumps(sc), scene_dir=os.path.dirname(util.TINY_PT))
+
+
+def _materials(scene):
+    """The records of the scene file's own materials, in file order (record 0 is the magenta "error"
+    material; lens and area-light carriers come after them)."""
+    import json
+    n = len(json.load(open(util.TINY_PT))["materials"])
+    return [scene.desc.materials[i] for i in range(scene.desc.n_materials)], 1 + n
+
+
+def test_constant_textures_are_folded_and_procedural_ones_referenced(built):
+    def mut(sc):
+        sc["textures"] += [
+            {"format": "color", "name": "check", "type": "checkerboard", "texture1": "red", "texture2": "nope"},
+            {"format": "float", "name": "two", "type": "constant", "float": 2.0},
+            {"format": "color", "name": "twice", "type": "scale", "texture": "check", "scale": "two"},
+            {"format": "color", "name": "photo", "type": "image", "file": "_not_there.exr", "filter": "EWA"},
+        ]
+        sc["materials"] += [{"name": "a", "type": "lambert", "Kd": "red"}, {"name": "b", "type": "lambert", "Kd": "twice"},
+                            {"name": "c", "type": "lambert", "Kd": "undefined"}, {"name": "d", "type": "mirror", "Kr": "photo"}]
+    scene = _tiny(mut)
+    tex = [scene.desc.textures[i] for i in range(scene.desc.n_textures)]
+    mats, first_new = _materials(scene)
+    a, b, c, d = mats[first_new:first_new + 4]
+    assert a.kd_tex == 0 and np.allclose(a.kd[:], [0.8, 0.25, 0.2])          # constant: folded into the record
+    twice = tex[b.kd_tex - 1]
+    assert twice.type == 2 and tex[twice.child[0]].type == 1 and tex[twice.child[1]].value[0] == 2.0
+    check = tex[twice.child[0]]
+    assert list(tex[check.child[1]].value) == [1.0, 0.0, 1.0]               # "nope" -> the magenta error texture
+    assert c.kd_tex == 0 and list(c.kd) == [1.0, 0.0, 1.0]                   # undefined name: the same fallback
+    photo = tex[d.kd_tex - 1]
+    assert photo.type == 3 and photo.image_filter == 3 and photo.n_levels == 1
+    lvl = scene.desc.image_levels[photo.first_level]
+    assert (lvl.width, lvl.height) == (1, 1)                                  # unreadable file: 1 x 1 magenta
+    texels = np.ctypeslib.as_array(scene.desc.image_texels, (scene.desc.n_image_texels * 4,))
+    assert list(texels[4 * lvl.texel_offset:4 * lvl.texel_offset + 4]) == [1.0, 0.0, 1.0, 1.0]
+
+
+def test_mask_records_wrap_the_masked_material(built):
+    def mut(sc):
+        sc["textures"] += [{"format": "float", "name": "half", "type": "constant", "float": 0.5}]
+        sc["materials"] += [{"name": "veil", "type": "mask", "material": "glass", "alpha": "half"},
+                            {"name": "bare", "type": "mask", "material": "missing"}]
+    scene = _tiny(mut)
+    mats, first_new = _materials(scene)
+    veil, bare = mats[first_new:first_new + 2]
+    glass = next(m for m in mats if m.type == 2 and not m.mask)
+    assert veil.mask == 1 and veil.type == 2 and veil.alpha == 0.5 and veil.eta == glass.eta
+    assert list(veil.transparent_color) == [1.0, 1.0, 1.0] and veil.alpha_tex == 0
+    assert bare.mask == 1 and bare.alpha == 1.0 and list(bare.kd) == [1.0, 0.0, 1.0]  # the error material underneath
+
+
+@pytest.mark.parametrize("material,needle", [
+    ({"name": "x", "type": "subsurface", "Kd": "red"}, "subsurface"),
+    ({"name": "x", "type": "mask", "material": "m1"}, "mask around a mask"),
+])
+def test_unsupported_materials_are_refused_with_a_message(built, material, needle):
+    def mut(sc):
+        sc["materials"] += [{"name": "m1", "type": "mask", "material": "red"}, material]
+    with pytest.raises(api.GoblinError) as e:
+        _tiny(mut)
+    assert needle in str(e.value)
