@@ -182,11 +182,16 @@ def test_product_does_not_reference_the_oracle():
 
 @pytest.mark.skipif(not util.have_ref_tool(), reason="oracle/_ref/ref_tool not built")
 @pytest.mark.parametrize("kind,args,json_name", [("bunny", (), "bunny_pt.json"), ("grid", (160,), "grid_pt.json"),
-                                                  ("spheres", (), "spheres_pt.json")])
+                                                  ("spheres", (), "spheres_pt.json"),
+                                                  # BASELINE.json configs 4 and 5 at their real size: the
+                                                  # 9,999,392-triangle grid (19,998,783 nodes, ~1 min for the
+                                                  # reference to load and dump) and the 729-instance field
+                                                  ("grid", (), "grid_pt.json"), ("field", (), "field_pt.json")])
 def test_large_scenes_against_reference_dump(built, kind, args, json_name, tmp_path):
     """The multi-threaded OBJ parse / vertex de-duplication / BVH build paths (files > 1 MB,
-    > 65,536 corners or primitives) against the reference's own structures: every BVH node,
-    the leaf order, vertices and indices bit-exact."""
+    > 65,536 corners or primitives) against the reference's own structures
+    (src/GoblinBVH.cpp:34-151, src/GoblinPolygonMesh.cpp:58-262): every BVH node, the leaf order,
+    instance matrices, vertices and indices bit-exact."""
     import subprocess
     path = os.path.join(util.gen_scene(kind, *args), json_name)
     scene = api.Scene(path)
