@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--accel", default="equal_count", choices=["equal_count", "middle", "sah"],
                     help="BVH split method: equal_count = the reference's tree (the headline, parity mode); "
                          "sah = the non-parity fast tree (SURVEY 8(f) rank 1)")
+    ap.add_argument("--trace-mode", default="wide", choices=["wide", "exact"],
+                    help="wide = 4-wide nodes (default); exact = the pair-node walk (every box test of the reference)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
     ap.add_argument("--wave-paths", type=int, default=0)
     ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
@@ -284,6 +286,7 @@ def main():
             stats_pass = None
     ctx = api.Context(local_rank)
     ctx.upload_scene(scene)
+    ctx.set_trace_mode(args.trace_mode)
     if args.wave_paths:
         ctx.set_wave_paths(args.wave_paths)
     if args.tune:
@@ -477,7 +480,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": NOTES[args.scene], "scene": args.scene, "accel": args.accel, "spp": spp,
+                "config": {"workload": NOTES[args.scene], "scene": args.scene, "accel": args.accel, "trace_mode": ctx.trace_mode(), "spp": spp,
                            "spp_range_rank0": [spp_begin, spp_end], "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
                            "parallelism": f"spp x{world} (scene replica per GPU, NCCL film all-reduce)" if world > 1 else "1 GPU",
                            "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~176 B per camera sample, GBs per wave) exceeds L2",

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoblin_b200.so")
+# GOBLIN_B200_LIB: another build of the same library (tools/build_variants.sh, compile-time knob sweeps)
+LIB_PATH = os.environ.get("GOBLIN_B200_LIB") or os.path.join(_HERE, "libgoblin_b200.so")
 
 
 class GoblinError(RuntimeError):
@@ -147,7 +148,11 @@ EXPORTS = [
     "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
     "gb_last_kernel_ms", "gb_last_error", "gb_version", "gb_enable_kernel_timing", "gb_get_kernel_times",
     "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning", "gb_upload_bytes",
+    "gb_set_trace_mode", "gb_get_trace_mode",
 ]
+
+# GB_TRACE_*: how the traversal kernels walk the reference's tree
+TRACE_MODES = {"wide": 0, "exact": 1}
 
 KERNEL_CLASSES = ["raygen", "extend", "shade", "shadow", "ao", "film", "trace", "other"]
 
@@ -212,6 +217,8 @@ def lib():
         l.gb_set_wave_paths.argtypes = [C.c_void_p, C.c_size_t]
         l.gb_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         l.gb_set_tuning.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+        l.gb_set_trace_mode.argtypes = [C.c_void_p, C.c_int]
+        l.gb_get_trace_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _lib = l
     return _lib
 
@@ -335,6 +342,7 @@ class Context:
         self._h = C.c_void_p()
         check(lib().gb_create(device, C.byref(self._h)))
         self.scene = None
+        self.device = device
 
     def close(self):
         if self._h:
@@ -404,7 +412,10 @@ class Context:
         return out
 
     def film_upload(self, rgbw):
+        f = self.scene.desc.film
         rgbw = np.ascontiguousarray(rgbw, dtype=np.float32)
+        if rgbw.size != f.yres * f.xres * 4:  # gb_film_upload copies exactly the film's size from this buffer
+            raise ValueError(f"film_upload: expected {f.yres} x {f.xres} x 4 floats, got {rgbw.size}")
         check(lib().gb_film_upload(self._h, rgbw.ctypes.data))
 
     def film_device_ptr(self):
@@ -466,6 +477,15 @@ class Context:
     def set_tuning(self, values):
         arr = (C.c_int * len(values))(*values)
         check(lib().gb_set_tuning(self._h, arr, len(values)))
+
+    def set_trace_mode(self, mode):
+        """"wide" (default: 4-wide nodes) or "exact" (pair nodes, every box test of the reference)."""
+        check(lib().gb_set_trace_mode(self._h, TRACE_MODES[mode]))
+
+    def trace_mode(self):
+        m = C.c_int()
+        check(lib().gb_get_trace_mode(self._h, C.byref(m)))
+        return {v: k for k, v in TRACE_MODES.items()}[m.value]
 
     def last_kernel_ms(self):
         ms = C.c_float()

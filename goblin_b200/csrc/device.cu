@@ -43,6 +43,9 @@ namespace gb {
 #define GB_TRACE_BLOCK 128
 #define GB_TRACE_MIN_BLOCKS 7
 #endif
+#ifndef GB_WIDE_MIN_BLOCKS
+#define GB_WIDE_MIN_BLOCKS 5 // the 4-wide step holds four boxes at once: ~100 registers
+#endif
 constexpr int kTraceBlock = GB_TRACE_BLOCK;   // threads per traversal block
 // resident blocks per SM the register allocation must allow: 7 x 128 threads -> 73 registers,
 // the most the traversal loop can use without spilling
@@ -50,6 +53,7 @@ constexpr int kTraceMinBlocks = GB_TRACE_MIN_BLOCKS;
 constexpr int kShadeBlock = 128;
 constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[64] per level
 constexpr size_t kMaxTraceSmem = 200 * 1024;
+constexpr size_t kMaxWideSmem = 56 * 1024; // beyond this the 4-wide walk would run fewer than 4 CTAs per SM: walk pair-wise
 constexpr int kCtrStride = 16;     // counters per bounce
 // per-bounce counters; the *_HEAD cursors are 64-bit (two slots, 8-byte aligned)
 enum { C_EXTEND = 0, C_SHADOW = 1, C_MAT0 = 2 /* .. 5: one per GB_MAT_* */, C_EXTEND_HEAD = 6, C_SHADOW_HEAD = 8, C_AO_HEAD = 10 };
@@ -179,15 +183,23 @@ struct TracePolicy {
     }
 };
 
-template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
+// MODE of every traversal kernel: which walk of the reference's tree it runs (traverse.cuh)
+enum { WALK_WIDE = 0,   // 4-wide nodes: the default
+       WALK_PAIR = 1,   // pair nodes, box tests exactly where the reference evaluates them (GB_TRACE_EXACT)
+       WALK_STATS = 2 };// the pair walk with the traversal counters on
+#define GB_WALK_FLAGS(MODE) constexpr bool STATS = (MODE) == WALK_STATS, WIDE = (MODE) == WALK_WIDE
+constexpr int traceMinBlocks(int mode) { return mode == WALK_WIDE ? GB_WIDE_MIN_BLOCKS : kTraceMinBlocks; }
+
+template <bool ANY, int MODE>
+__global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
 k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned long long n, gb_hit* __restrict__ hits,
     unsigned char* __restrict__ occluded, unsigned long long* head, unsigned long long* stats, int stackEntries) {
+    GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
     TracePolicy<ANY> pol{rays, hits, occluded, &sc};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    persistentTrace<ANY, STATS>(sc, pol, n, head, s_stack, s_ray, ts, &done);
+    persistentTrace<ANY, STATS, WIDE>(sc, pol, n, head, s_stack, s_ray, ts, &done);
     flushStats<ANY, STATS>(stats, done, ts);
 }
 
@@ -262,15 +274,16 @@ struct ExtendPolicy {
     }
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
 k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
     unsigned long long* stats, int stackEntries) {
+    GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
     ExtendPolicy pol{&sc, ps, queue, ctr, singleBin, 0u};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    persistentTrace<false, STATS>(sc, pol, (unsigned long long)ctr[C_EXTEND],
+    persistentTrace<false, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_EXTEND],
         reinterpret_cast<unsigned long long*>(ctr + C_EXTEND_HEAD), s_stack, s_ray, ts, &done);
     flushStats<false, STATS>(stats, done, ts);
 }
@@ -298,14 +311,15 @@ struct ShadowPolicy {
     }
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
 k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats, int stackEntries) {
+    GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
     ShadowPolicy pol{ps};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    persistentTrace<true, STATS>(sc, pol, (unsigned long long)ctr[C_SHADOW],
+    persistentTrace<true, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_SHADOW],
         reinterpret_cast<unsigned long long*>(ctr + C_SHADOW_HEAD), s_stack, s_ray, ts, &done);
     flushStats<true, STATS>(stats, done, ts);
 }
@@ -639,16 +653,17 @@ struct AOPolicy {
     }
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(kTraceBlock, kTraceMinBlocks)
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
 k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int* ctr, unsigned long long* stats,
     int stackEntries) {
+    GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
     AOPolicy pol{&sc, ps, wp, src, 0u};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
     const unsigned long long n = (unsigned long long)ctr[C_MAT0] * (unsigned long long)wp.aoSamples;
-    persistentTrace<true, STATS>(sc, pol, n, reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD), s_stack, s_ray,
+    persistentTrace<true, STATS, WIDE>(sc, pol, n, reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD), s_stack, s_ray,
         ts, &done);
     flushStats<true, STATS>(stats, done, ts);
 }
@@ -846,7 +861,11 @@ struct gb_context {
     unsigned long long* stats = nullptr;
     bool statsOn = false;
     uint64_t launches = 0;
-    int traceGrid = 0, aoGrid = 0;
+    bool wideFits = false;  // the 4-wide walk's stack fits in shared memory for this scene
+    int traceMode = GB_TRACE_WIDE;
+    // launch geometry of the traversal kernels, keyed by kernel function: depends on the kernel, the
+    // stack size of the uploaded scene and the tuning only (invalidated by gb_upload_scene / gb_set_tuning)
+    std::vector<std::pair<const void*, int>> gridCache;
     size_t maxWavePaths = 32u << 20;
     TraceTuning tune{20u, 6u, 4u, 10u};
     int blocksPerSM = 0; // 0 = as many as fit
@@ -955,10 +974,15 @@ int ensureWave(gb_context* ctx, size_t paths) {
 }
 
 // per thread: stackEntries 8-byte stack entries + the 6-float world-space ray
-size_t traceSmem(const gb_context* ctx) { return ((size_t)ctx->stackEntries * sizeof(uint2) + 6 * sizeof(float)) * kTraceBlock; }
+size_t traceSmemFor(int stackEntries) { return ((size_t)stackEntries * sizeof(uint2) + 6 * sizeof(float)) * kTraceBlock; }
+size_t traceSmem(const gb_context* ctx) { return traceSmemFor(ctx->stackEntries); }
 
 template <typename K>
 int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (const auto& e : ctx->gridCache) {
+        if (e.first == key) { *grid = e.second; return GB_OK; }
+    }
     size_t smem = traceSmem(ctx);
     GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int perSM = 0;
@@ -966,7 +990,14 @@ int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
     if (perSM < 1) return gb::failWith(GB_ERR_LIMIT, "traversal kernel does not fit on an SM");
     if (ctx->blocksPerSM > 0) perSM = std::min(perSM, ctx->blocksPerSM);
     *grid = perSM * ctx->numSMs; // persistent: exactly one resident wave of CTAs
+    ctx->gridCache.emplace_back(key, *grid);
     return GB_OK;
+}
+
+// which walk the traversal kernels of this context run right now
+int walkMode(const gb_context* ctx) {
+    if (ctx->statsOn) return WALK_STATS;
+    return ctx->traceMode == GB_TRACE_WIDE && ctx->wideFits ? WALK_WIDE : WALK_PAIR;
 }
 
 } // namespace
@@ -1068,15 +1099,17 @@ void hostParallelFor(size_t n, size_t grain, F body) { // body(begin, end)
 // interior node.  Children always follow their parent in the reference's layout
 // (left = i + 1, right = secondChildOffset > i + 1).
 bool scanTree(const gb_bvh_node* nodes, uint32_t count, uint64_t primLimit, int* depthOut,
-    std::vector<uint32_t>& pairIndex, uint32_t* nPairsOut) {
+    std::vector<uint32_t>& pairIndex, uint32_t* nPairsOut, std::vector<uint32_t>& wideIndex, uint32_t* nWideOut) {
     *depthOut = 0;
     *nPairsOut = 0;
+    *nWideOut = 0;
     pairIndex.assign(count, 0u);
+    wideIndex.assign(count, WIDE_NOT_ROOT);
     if (count == 0) return true;
     std::vector<uint8_t> depth(count, 0);
     std::vector<uint8_t> reached(count, 0);
     reached[0] = 1;
-    uint32_t nPairs = 0;
+    uint32_t nPairs = 0, nWide = 0;
     int deepest = 0;
     for (uint32_t i = 0; i < count; ++i) {
         if (!reached[i]) return false;
@@ -1089,6 +1122,7 @@ bool scanTree(const gb_bvh_node* nodes, uint32_t count, uint64_t primLimit, int*
             reached[i + 1] = reached[nd.offset] = 1;
             depth[i + 1] = depth[nd.offset] = (uint8_t)(depth[i] + 1);
             pairIndex[i] = nPairs++;
+            if ((depth[i] & 1u) == 0u) wideIndex[i] = nWide++; // interior at an even depth: a wide root (wide_node.h)
         } else {
             if ((uint64_t)nd.offset + nd.nprims > primLimit) return false;
             if (nd.nprims == 1 ? nd.offset > REF_INDEX : i > REF_INDEX) return false;
@@ -1097,6 +1131,7 @@ bool scanTree(const gb_bvh_node* nodes, uint32_t count, uint64_t primLimit, int*
     if (nPairs > REF_INDEX) return false;
     *depthOut = deepest;
     *nPairsOut = nPairs;
+    *nWideOut = nWide;
     return true;
 }
 
@@ -1213,6 +1248,25 @@ __global__ void k_derive_pairs(const float4* __restrict__ nodes, const unsigned 
         __uint_as_float((word >> 8) & 0xffu), 0.0f);
 }
 
+// 4-wide nodes (wide_node.h) from the same nodes: one thread per node, wide roots (interior, even depth: the host
+// numbered them) gather their grandchildren.
+__global__ void k_derive_wide(const gb_bvh_node* __restrict__ nodes, const unsigned int* __restrict__ wideIndex,
+    unsigned int count, float4* __restrict__ out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned int w = wideIndex[i];
+    if (w == WIDE_NOT_ROOT) return;
+    WideNode wn;
+    deriveWideNode(nodes, wideIndex, i, &wn);
+    float4* q = out + 8 * (size_t)w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const WideChild& c = wn.c[k];
+        q[2 * k] = make_float4(c.lo[0], c.lo[1], c.lo[2], c.hi[0]);
+        q[2 * k + 1] = make_float4(c.hi[1], c.hi[2], __uint_as_float(c.ref), __uint_as_float(c.meta));
+    }
+}
+
 // Triangle test records (p0, e1, e2, face) and shading records (vertex normals, uvs) in BVH leaf order,
 // one thread per leaf slot: e1 = p1 - p0, e2 = p2 - p0 are the reference's per-test subtractions
 // (src/GoblinTriangle.cpp:51-54), done once.  Index errors are reported through `error`.
@@ -1281,14 +1335,15 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     };
     // ---- validate, measure tree depth (stack need), number the pair nodes
     int topDepth = 0, modelDepth = 0;
-    std::vector<uint32_t> topPairIndex;
-    uint32_t nTopPairs = 0;
-    if (!scanTree(d->top_nodes, d->n_top_nodes, nInst, &topDepth, topPairIndex, &nTopPairs)) {
+    std::vector<uint32_t> topPairIndex, topWideIndex;
+    uint32_t nTopPairs = 0, nTopWide = 0;
+    if (!scanTree(d->top_nodes, d->n_top_nodes, nInst, &topDepth, topPairIndex, &nTopPairs, topWideIndex, &nTopWide)) {
         return gb::failWith(GB_ERR_INVALID, "malformed top-level BVH");
     }
-    std::vector<std::vector<uint32_t>> modelPairIndex(d->n_models);
+    std::vector<std::vector<uint32_t>> modelPairIndex(d->n_models), modelWideIndex(d->n_models);
     std::vector<uint32_t> modelPairBase(d->n_models, 0u), modelPairCount(d->n_models, 0u);
-    uint64_t nModelPairs = 0;
+    std::vector<uint32_t> modelWideBase(d->n_models, 0u), modelWideCount(d->n_models, 0u);
+    uint64_t nModelPairs = 0, nModelWide = 0;
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
         if (md.material < 0 || (uint32_t)md.material >= d->n_materials) return gb::failWith(GB_ERR_INVALID, "model material out of range");
@@ -1298,19 +1353,31 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             return gb::failWith(GB_ERR_INVALID, "model ranges exceed the scene arrays");
         }
         int dm = 0;
-        if (!scanTree(d->model_nodes + md.node_offset, md.node_count, md.tri_count, &dm, modelPairIndex[m], &modelPairCount[m])) {
+        if (!scanTree(d->model_nodes + md.node_offset, md.node_count, md.tri_count, &dm, modelPairIndex[m], &modelPairCount[m],
+                modelWideIndex[m], &modelWideCount[m])) {
             return gb::failWith(GB_ERR_INVALID, "malformed model BVH");
         }
         modelDepth = std::max(modelDepth, dm);
         if (nModelPairs > 0xffffffffull) return gb::failWith(GB_ERR_LIMIT, "model BVHs exceed the 32-bit pair index");
         modelPairBase[m] = (uint32_t)nModelPairs;
         nModelPairs += modelPairCount[m];
+        modelWideBase[m] = (uint32_t)nModelWide;
+        nModelWide += modelWideCount[m];
     }
-    // push-far/go-near keeps at most one entry per level; both levels share one column
-    ctx->stackEntries = topDepth + modelDepth + 2;
-    if (ctx->stackEntries > 2 * kMaxStack) {
+    // The pair walk (push far / go near) keeps at most one entry per level, the 4-wide walk at most three per
+    // wide level; both levels of the scene share one column.  A scene too deep for the wide walk's column in
+    // shared memory is walked pair-wise; one too deep for that as well is refused -- before anything is touched.
+    const int pairEntries = topDepth + modelDepth + 2;
+    const int wideEntries = std::max(pairEntries, wideStackEntries(topDepth) + wideStackEntries(modelDepth) + 2);
+    if (pairEntries > 2 * kMaxStack) {
         return gb::failWith(GB_ERR_LIMIT, "BVH deeper than the traversal stack (reference: todo[64] per level)");
     }
+    if (traceSmemFor(pairEntries) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
+    size_t maxWideSmem = kMaxWideSmem;
+    if (const char* e = std::getenv("GB_MAX_WIDE_SMEM")) maxWideSmem = (size_t)std::strtoull(e, nullptr, 10); // tests: force the fallback
+    ctx->wideFits = traceSmemFor(wideEntries) <= maxWideSmem;
+    ctx->stackEntries = ctx->wideFits ? wideEntries : pairEntries;
+    ctx->gridCache.clear();
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         if (d->materials[m].type < 0 || d->materials[m].type >= GB_MAT_COUNT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
     }
@@ -1330,6 +1397,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     // what the derive kernels read (the reference's own arrays + the pair numbering): uploaded
     const size_t oRawTopPairIdx = ar.take(4 * (size_t)d->n_top_nodes);
     const size_t oRawModelPairIdx = ar.take(4 * (size_t)d->n_model_nodes);
+    const size_t oRawTopWideIdx = ar.take(4 * (size_t)d->n_top_nodes);
+    const size_t oRawModelWideIdx = ar.take(4 * (size_t)d->n_model_nodes);
     const size_t oRawOrder = ar.take(4 * (size_t)d->n_tris);
     const size_t oRawTriIndex = ar.take(12 * (size_t)d->n_tris);
     const size_t oRawPos = ar.take(12 * (size_t)d->n_verts);
@@ -1374,6 +1443,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t uploadSize = ar.size;
     const size_t oTopPairs = ar.take(64 * (size_t)nTopPairs);
     const size_t oModelPairs = ar.take(64 * (size_t)nModelPairs);
+    const size_t oTopWide = ar.take(128 * (size_t)nTopWide);
+    const size_t oModelWide = ar.take(128 * (size_t)nModelWide);
     const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
     const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
     if (ar.size > ctx->arenaCap) { // both arenas persist and only grow
@@ -1405,7 +1476,10 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     });
     // the pair numbering of every interior node and the meshes' own arrays: the derive kernels turn
     // them into pair nodes and leaf-order triangle records on the device
-    if (d->n_top_nodes) std::memcpy(H + oRawTopPairIdx, topPairIndex.data(), 4 * (size_t)d->n_top_nodes);
+    if (d->n_top_nodes) {
+        std::memcpy(H + oRawTopPairIdx, topPairIndex.data(), 4 * (size_t)d->n_top_nodes);
+        std::memcpy(H + oRawTopWideIdx, topWideIndex.data(), 4 * (size_t)d->n_top_nodes);
+    }
     const uint32_t topRootRef = d->n_top_nodes ? refOf(d->top_nodes, topPairIndex.data(), 0) : REF_NONE;
     std::vector<uint32_t> modelRootRef(d->n_models, REF_NONE);
     int4* modelShade = reinterpret_cast<int4*>(H + oModelShade);
@@ -1416,9 +1490,11 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         const gb_bvh_node* nodes = d->model_nodes + md.node_offset;
         if (md.node_count) {
             std::memcpy(H + oRawModelPairIdx + 4 * (size_t)md.node_offset, modelPairIndex[m].data(), 4 * (size_t)md.node_count);
-            modelRootRef[m] = refOf(nodes, modelPairIndex[m].data(), 0);
+            std::memcpy(H + oRawModelWideIdx + 4 * (size_t)md.node_offset, modelWideIndex[m].data(), 4 * (size_t)md.node_count);
+            modelRootRef[m] = refOf(nodes, modelPairIndex[m].data(), 0); // pair 0 = wide root 0 when the root is interior
         }
         std::vector<uint32_t>().swap(modelPairIndex[m]);
+        std::vector<uint32_t>().swap(modelWideIndex[m]);
     }
     if (d->n_tris) hostParallelFor(d->n_tris, 1u << 15, [&](size_t b, size_t e) {
         std::memcpy(H + oRawOrder + 4 * b, d->model_order + b, 4 * (e - b));
@@ -1447,7 +1523,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         std::memcpy(&radiusBits, &md.radius, 4);
         instInfo[s] = make_int4(md.kind, (int)md.node_offset, (int)md.tri_offset, radiusBits);
         instInfo2[s] = make_int4((int)modelRootRef[in.model], (int)modelPairBase[in.model],
-            md.kind == GB_GEOM_MESH ? (int)md.node_count : 0, 0);
+            md.kind == GB_GEOM_MESH ? (int)md.node_count : 0, (int)modelWideBase[in.model]);
         instShade[s] = make_int4((int)id, in.model, md.material, md.area_light);
         if (md.area_light >= 0) hasArea = true;
     }
@@ -1580,6 +1656,11 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
             reinterpret_cast<const unsigned int*>(D + oRawTopPairIdx), d->n_top_nodes, reinterpret_cast<float4*>(D + oTopPairs));
         ctx->launches++;
     }
+    if (nTopWide) {
+        k_derive_wide<<<(d->n_top_nodes + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const gb_bvh_node*>(D + oTopNodes),
+            reinterpret_cast<const unsigned int*>(D + oRawTopWideIdx), d->n_top_nodes, reinterpret_cast<float4*>(D + oTopWide));
+        ctx->launches++;
+    }
     for (uint32_t m = 0; m < d->n_models; ++m) {
         const gb_model& md = d->models[m];
         if (md.kind != GB_GEOM_MESH) continue;
@@ -1588,6 +1669,13 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
                 reinterpret_cast<const float4*>(D + oModelNodes) + 2 * (size_t)md.node_offset,
                 reinterpret_cast<const unsigned int*>(D + oRawModelPairIdx) + md.node_offset, md.node_count,
                 reinterpret_cast<float4*>(D + oModelPairs) + 4 * (size_t)modelPairBase[m]);
+            ctx->launches++;
+        }
+        if (modelWideCount[m]) {
+            k_derive_wide<<<(md.node_count + 255) / 256, 256, 0, ctx->stream>>>(
+                reinterpret_cast<const gb_bvh_node*>(D + oModelNodes) + md.node_offset,
+                reinterpret_cast<const unsigned int*>(D + oRawModelWideIdx) + md.node_offset, md.node_count,
+                reinterpret_cast<float4*>(D + oModelWide) + 8 * (size_t)modelWideBase[m]);
             ctx->launches++;
         }
         if (md.tri_count) {
@@ -1609,6 +1697,8 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.modelNodes = reinterpret_cast<const float4*>(D + oModelNodes);
     sc.topPairs = reinterpret_cast<const float4*>(D + oTopPairs);
     sc.modelPairs = reinterpret_cast<const float4*>(D + oModelPairs);
+    sc.topWide = reinterpret_cast<const float4*>(D + oTopWide);
+    sc.modelWide = reinterpret_cast<const float4*>(D + oModelWide);
     sc.instToObject = reinterpret_cast<const float4*>(D + oInstToObject);
     sc.instToWorld = reinterpret_cast<const float4*>(D + oInstToWorld);
     sc.instInfo = reinterpret_cast<const int4*>(D + oInstInfo);
@@ -1663,8 +1753,7 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     ctx->hasBlinn = hasBlinn;
     ctx->hasMeshLight = hasMeshLight;
     lap("copy+sync");
-    ctx->haveScene = true;
-    if (traceSmem(ctx) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
+    ctx->haveScene = true; // every check has passed
     return GB_OK;
 }
 
@@ -1676,15 +1765,19 @@ static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n
     int grid = 0, rc;
     GB_CUDA(cudaMemsetAsync(ctx->traceHead, 0, 8, ctx->stream));
     GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
-#define LAUNCH(ANYV, STATSV)                                                                       \
+#define LAUNCH(ANYV, MODEV)                                                                        \
     do {                                                                                           \
-        if ((rc = setupTraceKernel(ctx, k_trace<ANYV, STATSV>, &grid)) != GB_OK) return rc;         \
+        if ((rc = setupTraceKernel(ctx, k_trace<ANYV, MODEV>, &grid)) != GB_OK) return rc;          \
         KernelTick tick(ctx, GB_K_TRACE);                                                           \
-        k_trace<ANYV, STATSV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned long long)n, d_hits, \
+        k_trace<ANYV, MODEV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned long long)n, d_hits, \
             d_occ, ctx->traceHead, ctx->stats, ctx->stackEntries);                                  \
     } while (0)
-    if (any) { if (ctx->statsOn) LAUNCH(true, true); else LAUNCH(true, false); }
-    else { if (ctx->statsOn) LAUNCH(false, true); else LAUNCH(false, false); }
+    const int mode = walkMode(ctx);
+    if (any) {
+        if (mode == WALK_WIDE) LAUNCH(true, WALK_WIDE); else if (mode == WALK_PAIR) LAUNCH(true, WALK_PAIR); else LAUNCH(true, WALK_STATS);
+    } else {
+        if (mode == WALK_WIDE) LAUNCH(false, WALK_WIDE); else if (mode == WALK_PAIR) LAUNCH(false, WALK_PAIR); else LAUNCH(false, WALK_STATS);
+    }
 #undef LAUNCH
     ctx->launches++;
     GB_CUDA(cudaGetLastError());
@@ -1790,17 +1883,18 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     }
     ctx->launches++;
     const int shadeGrid = ctx->numSMs * 8;
+    const int mode = walkMode(ctx);
     auto extend = [&](int b, int singleBin) -> int {
         unsigned int* c = ctx->ctr + b * kCtrStride;
         const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
         KernelTick tick(ctx, GB_K_EXTEND);
-        if (ctx->statsOn) {
-            if ((rc = setupTraceKernel(ctx, k_extend<true>, &grid)) != GB_OK) return rc;
-            k_extend<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries);
-        } else {
-            if ((rc = setupTraceKernel(ctx, k_extend<false>, &grid)) != GB_OK) return rc;
-            k_extend<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries);
-        }
+#define GB_EXTEND(MODEV)                                                                                            \
+    do {                                                                                                            \
+        if ((rc = setupTraceKernel(ctx, k_extend<MODEV>, &grid)) != GB_OK) return rc;                                \
+        k_extend<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries); \
+    } while (0)
+        if (mode == WALK_WIDE) GB_EXTEND(WALK_WIDE); else if (mode == WALK_PAIR) GB_EXTEND(WALK_PAIR); else GB_EXTEND(WALK_STATS);
+#undef GB_EXTEND
         ctx->launches++;
         return GB_OK;
     };
@@ -1814,13 +1908,13 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         }
         {
             KernelTick tick(ctx, GB_K_AO);
-            if (ctx->statsOn) {
-                if ((rc = setupTraceKernel(ctx, k_ao<true>, &grid)) != GB_OK) return rc;
-                k_ao<true><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);
-            } else {
-                if ((rc = setupTraceKernel(ctx, k_ao<false>, &grid)) != GB_OK) return rc;
-                k_ao<false><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);
-            }
+#define GB_AO(MODEV)                                                                                                  \
+    do {                                                                                                              \
+        if ((rc = setupTraceKernel(ctx, k_ao<MODEV>, &grid)) != GB_OK) return rc;                                      \
+        k_ao<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);    \
+    } while (0)
+            if (mode == WALK_WIDE) GB_AO(WALK_WIDE); else if (mode == WALK_PAIR) GB_AO(WALK_PAIR); else GB_AO(WALK_STATS);
+#undef GB_AO
         }
         {
             KernelTick tick(ctx, GB_K_OTHER);
@@ -1837,10 +1931,20 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         // the extend) and not while counting.
         const bool overlap = ctx->overlapTails && !ctx->statsOn && !ctx->sc.hasEnvLight && !ctx->sc.matMask;
         bool pendingJoin = false;
+        cudaError_t joinStatus = cudaSuccess;
         auto join = [&]() {
-            if (pendingJoin) cudaStreamWaitEvent(st, ctx->evJoin, 0);
+            if (pendingJoin) {
+                const cudaError_t e = cudaStreamWaitEvent(st, ctx->evJoin, 0);
+                if (e != cudaSuccess) joinStatus = e;
+            }
             pendingJoin = false;
         };
+        // every way out of the bounce loop (errors included) makes the context's stream wait for a shadow
+        // kernel still queued on the second one: the next wave's memset / raygen must not overtake it
+        struct JoinGuard {
+            decltype(join)& f;
+            ~JoinGuard() { f(); }
+        } joinGuard{join};
         for (int b = 0; b < depth; ++b) {
             // the last extend only feeds the BSDF-sampled emission term; skip it when no area light exists
             const bool last = b == depth - 1;
@@ -1887,13 +1991,13 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                 }
                 {
                     KernelTick tick(ctx, GB_K_SHADOW, ss);
-                    if (ctx->statsOn) {
-                        if ((rc = setupTraceKernel(ctx, k_shadow<true>, &grid)) != GB_OK) return rc;
-                        k_shadow<true><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
-                    } else {
-                        if ((rc = setupTraceKernel(ctx, k_shadow<false>, &grid)) != GB_OK) return rc;
-                        k_shadow<false><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);
-                    }
+#define GB_SHADOW(MODEV)                                                                                      \
+    do {                                                                                                      \
+        if ((rc = setupTraceKernel(ctx, k_shadow<MODEV>, &grid)) != GB_OK) return rc;                          \
+        k_shadow<MODEV><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);        \
+    } while (0)
+                    if (mode == WALK_WIDE) GB_SHADOW(WALK_WIDE); else if (mode == WALK_PAIR) GB_SHADOW(WALK_PAIR); else GB_SHADOW(WALK_STATS);
+#undef GB_SHADOW
                 }
                 if (overlap) {
                     GB_CUDA(cudaEventRecord(ctx->evJoin, ss));
@@ -1903,6 +2007,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             }
         }
         join(); // the film kernel (or the caller) reads L
+        if (joinStatus != cudaSuccess) return gb::failWith(GB_ERR_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(joinStatus));
     }
     if (toFilm) {
         const float wx = ctx->sc.filterWidthX, wy = ctx->sc.filterWidthY;
@@ -2209,6 +2314,21 @@ int gb_set_tuning(gb_context* ctx, const int* values, int n) {
     }
     if (n > 4) ctx->blocksPerSM = values[4];
     ctx->sc.tune = ctx->tune;
+    ctx->gridCache.clear();
+    return GB_OK;
+}
+
+int gb_set_trace_mode(gb_context* ctx, int mode) {
+    if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
+    if (mode != GB_TRACE_WIDE && mode != GB_TRACE_EXACT) return gb::failWith(GB_ERR_INVALID, "unknown trace mode");
+    ctx->traceMode = mode;
+    return GB_OK;
+}
+
+int gb_get_trace_mode(gb_context* ctx, int* mode) {
+    if (!ctx || !mode) return gb::failWith(GB_ERR_INVALID, "null argument");
+    // what the kernels actually run: a scene too deep for the wide walk's shared-memory stack is walked pair-wise
+    *mode = ctx->traceMode == GB_TRACE_WIDE && (!ctx->haveScene || ctx->wideFits) ? GB_TRACE_WIDE : GB_TRACE_EXACT;
     return GB_OK;
 }
 

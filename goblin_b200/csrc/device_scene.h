@@ -3,10 +3,11 @@
 // Everything a traversal step touches is a 16-byte-aligned float4 / int4 array
 // read with 128-bit __ldg loads:
 //   * BVH nodes stay bit-identical to the reference's 32-byte CompactBVHNode
-//     (src/GoblinBVH.h:8-30); the traversal reads a derived "pair node" per
-//     interior node -- both children's boxes and references in 64 bytes, so one
-//     step tests two boxes (still 32 bytes per box test) -- and the original
-//     nodes only for each level's root and for the rare multi-primitive leaf;
+//     (src/GoblinBVH.h:8-30); the traversal reads records derived from them on the
+//     device at upload -- by default a 128-byte 4-wide node per interior node of
+//     even depth (four grandchild boxes + references, wide_node.h), for the exact /
+//     counting walk a 64-byte "pair node" per interior node (both children) -- and
+//     the original nodes only for each level's root and the rare multi-primitive leaf;
 //   * instances and triangles are stored in BVH leaf order, so a leaf's
 //     primitives are contiguous and no order[] indirection is paid per test;
 //   * a triangle test record is p0, e1 = p1 - p0, e2 = p2 - p0 (the values the
@@ -49,12 +50,14 @@ struct DeviceScene {
     uint32_t nTopNodes;
     uint32_t nInstances;
     const float4* topPairs;     // 4 per interior node of the top-level BVH (pair nodes, traverse.cuh)
+    const float4* topWide;      // 8 per wide root of the top-level BVH (4-wide nodes, wide_node.h)
     uint32_t topRootRef;        // pair index 0, or a leaf reference when the root is a leaf
     const float4* instToObject; // 3 per instance slot (BVH leaf order)
     const int4* instInfo;       // per slot: kind, node base (in modelNodes), tri base (in triRec), __float_as_int(radius)
-    const int4* instInfo2;      // per slot: root reference, pair base (in modelPairs), node count (0 = empty mesh), 0
+    const int4* instInfo2;      // per slot: root reference, pair base (in modelPairs), node count (0 = empty mesh), wide base (in modelWide)
     const float4* modelNodes;   // 2 per node, all models concatenated
     const float4* modelPairs;   // 4 per interior node, all models concatenated
+    const float4* modelWide;    // 8 per wide root, all models concatenated
     const float4* triRec;       // 3 per triangle slot (BVH leaf order, all models concatenated)
     // ---- shading data
     const float4* instToWorld;  // 3 per instance slot

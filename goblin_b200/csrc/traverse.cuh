@@ -2,15 +2,17 @@
 //
 // What is walked is the reference's tree in the reference's order
 // (src/GoblinBVH.cpp:189-280: near child first by dirIsNeg[axis], far child
-// pushed, leaves tested as they are reached, t <= maxt accepted), so hit ids,
-// distances and the visited-node counts equal the CPU build's.  How it is
-// walked is B200-shaped:
-//   * "pair nodes": one 64-byte record per interior node holds BOTH child boxes
-//     and child references, fetched as 4 x 128-bit read-only loads; a step
-//     tests two boxes, which halves the dependent-load chain of the 32-byte
-//     one-box-per-visit layout (same 32 algorithmic bytes per box test);
-//   * the far child's entry distance rides on the stack (8-byte entries in a
-//     shared-memory column per thread) and is re-checked against the shrunk
+// pushed, leaves tested as they are reached, t <= maxt accepted), so hit ids and
+// distances equal the CPU build's.  How it is walked is B200-shaped:
+//   * WIDE (the default): 128-byte 4-wide nodes (wide_node.h) -- two binary levels
+//     per step, fetched as 8 x 128-bit read-only loads, four independent slab tests
+//     per step, children visited in the reference's order;
+//   * !WIDE: "pair nodes", one 64-byte record per interior node with BOTH child
+//     boxes (4 x 128-bit loads, two box tests per step).  This is the walk whose
+//     box-test count equals the reference's exactly: the STATS instantiation
+//     (gb_get_counters, the roofline's N_node) and GB_TRACE_EXACT run it;
+//   * the far children's entry distances ride on the stack (8-byte entries in a
+//     shared-memory column per thread) and are re-checked against the shrunk
 //     maxt when popped -- exactly the box test the reference evaluates at pop
 //     time, since nothing else in that test depends on maxt;
 //   * branch-free slab tests that keep the reference's comparison structure
@@ -22,15 +24,18 @@
 //     warp-aggregated atomic instead of idling until the whole warp is done.
 #pragma once
 #include "rt_core.cuh"
+#include "wide_node.h"
 
 namespace gb {
 
-constexpr unsigned int REF_LEAF = 0x80000000u;  // child is a leaf
-constexpr unsigned int REF_MULTI = 0x40000000u; // leaf with nprims != 1: index = original node
-constexpr unsigned int REF_INDEX = 0x3FFFFFFFu;
-constexpr unsigned int REF_NONE = 0xFFFFFFFFu;  // nothing left at this level
-constexpr unsigned int REF_POP = 0xFFFFFFFEu;   // take the next entry off the stack
-constexpr int kStepsPerCheck = 2;               // interior + pop stages between two scheduling checks
+#ifndef GB_STEPS_PAIR
+#define GB_STEPS_PAIR 2
+#endif
+#ifndef GB_STEPS_WIDE
+#define GB_STEPS_WIDE 2
+#endif
+// interior + pop stages between two scheduling checks
+constexpr int kStepsPerCheckPair = GB_STEPS_PAIR, kStepsPerCheckWide = GB_STEPS_WIDE;
 // scheduling knobs live in DeviceScene::tune (gb_set_tuning): refillBelow = pull new rays when
 // fewer lanes than this are busy; leafBatch / levelBatch = run the triangle / level stage once
 // this many lanes wait for it; moveFloor = ... or when fewer lanes than this can still move
@@ -46,23 +51,10 @@ struct TravStack {
     __device__ __forceinline__ uint2 get(int k) const { return base[k * stride]; }
 };
 
-// The reference's ordered slab test on sign-selected bounds, without early returns.
+// The reference's ordered slab test on sign-selected bounds, without early returns (wide_node.h).
 __device__ __forceinline__ bool slabNoBranch(float nearX, float nearY, float nearZ, float farX, float farY, float farZ,
     float3 o, float3 inv, float mint, float maxt, float* tEntry) {
-    float tMin = (nearX - o.x) * inv.x;
-    float tMax = (farX - o.x) * inv.x;
-    float tYMin = (nearY - o.y) * inv.y;
-    float tYMax = (farY - o.y) * inv.y;
-    bool miss = (tYMax < tMin) | (tYMin > tMax);
-    tMin = tYMin > tMin ? tYMin : tMin;
-    tMax = tYMax < tMax ? tYMax : tMax;
-    float tZMin = (nearZ - o.z) * inv.z;
-    float tZMax = (farZ - o.z) * inv.z;
-    miss |= (tZMax < tMin) | (tZMin > tMax);
-    tMin = tZMin > tMin ? tZMin : tMin;
-    tMax = tZMax < tMax ? tZMax : tMax;
-    *tEntry = tMin;
-    return !miss & (tMin < maxt) & (tMax > mint);
+    return slabOrdered(nearX, nearY, nearZ, farX, farY, farZ, o.x, o.y, o.z, inv.x, inv.y, inv.z, mint, maxt, tEntry);
 }
 
 // One original 32-byte node (two float4) against a ray: used for the root of each level.
@@ -86,7 +78,7 @@ __device__ __forceinline__ unsigned int signBits(float3 d) {
 //
 // s_stack: stackEntries x blockDim.x uint2, s_ray: 6 x blockDim.x floats (the world-space ray
 // while a lane is inside an instance).
-template <bool ANY, bool STATS, typename Policy>
+template <bool ANY, bool STATS, bool WIDE, typename Policy>
 __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& pol, unsigned long long n,
     unsigned long long* head, uint2* s_stack, float* s_ray, TraceStats& ts, unsigned int* raysDone) {
     const unsigned int FULL = 0xffffffffu;
@@ -101,7 +93,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
     unsigned int neg = 0, cur = REF_NONE;
     float mint = 0.0f, maxt = 0.0f;
     int sp = 0, spFloor = 0, level = 0, curSlot = 0;
-    const float4* pairs = sc.topPairs;
+    const float4* pairs = WIDE ? sc.topWide : sc.topPairs; // interior records of the current level
     unsigned int triBase = 0, nodeBase = 0, instNext = 0, instEnd = 0;
     HitRec hit;
     hit.inst = -1; hit.prim = 0; hit.t = 0.0f; hit.b1 = hit.b2 = 0.0f;
@@ -125,7 +117,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     found = false;
                     hit.inst = -1; hit.prim = 0; hit.b1 = hit.b2 = 0.0f;
                     level = 0; sp = 0; spFloor = 0; instNext = instEnd = 0;
-                    pairs = sc.topPairs;
+                    pairs = WIDE ? sc.topWide : sc.topPairs;
                     cur = REF_NONE;
                     if (pol.fetch(item, &o, &d, &mint, &maxt)) {
                         ++*raysDone;
@@ -201,7 +193,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     if (level == 1) { // this instance is exhausted: back to world space
                         level = 0;
                         spFloor = 0;
-                        pairs = sc.topPairs;
+                        pairs = WIDE ? sc.topWide : sc.topPairs;
                         o = make3(wr[0], wr[ws], wr[2 * ws]);
                         d = make3(wr[3 * ws], wr[4 * ws], wr[5 * ws]);
                         inv = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -245,7 +237,8 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             curSlot = (int)slot;
                             nodeBase = (unsigned int)info.y;
                             triBase = (unsigned int)info.z;
-                            pairs = sc.modelPairs + 4 * (size_t)(unsigned int)info2.y;
+                            pairs = WIDE ? sc.modelWide + 8 * (size_t)(unsigned int)info2.w
+                                         : sc.modelPairs + 4 * (size_t)(unsigned int)info2.y;
                             o = oo; d = od; inv = oinv; neg = oneg;
                             cur = (unsigned int)info2.x;
                             descended = true;
@@ -286,8 +279,33 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 }
             }
 #pragma unroll
-            for (int rep = 0; rep < kStepsPerCheck; ++rep) {
-                if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
+            for (int rep = 0; rep < (WIDE ? kStepsPerCheckWide : kStepsPerCheckPair); ++rep) {
+                if (WIDE) {
+                    if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: four box tests (wide_node.h)
+                        const float4* p = pairs + 8 * (size_t)cur;
+                        const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
+                        const float4 c0 = __ldg(p + 4), c1 = __ldg(p + 5), d0 = __ldg(p + 6), d1 = __ldg(p + 7);
+                        const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+                        float t0, t1, t2, t3;
+#define GB_WIDE_BOX(n0, n1, tt)                                                                                   \
+    (slabNoBranch(nx ? n0.w : n0.x, ny ? n1.x : n0.y, nz ? n1.y : n0.z, nx ? n0.x : n0.w, ny ? n0.y : n1.x,       \
+         nz ? n0.z : n1.y, o, inv, mint, maxt, &tt)                                                                \
+            ? __float_as_uint(n1.z)                                                                                \
+            : REF_POP)
+                        // a child that is missed (or an empty slot, whose reference already says so) becomes REF_POP
+                        unsigned int r0 = GB_WIDE_BOX(a0, a1, t0), r1 = GB_WIDE_BOX(b0, b1, t1);
+                        unsigned int r2 = GB_WIDE_BOX(c0, c1, t2), r3 = GB_WIDE_BOX(d0, d1, t3);
+#undef GB_WIDE_BOX
+                        wideVisitOrder(neg, __float_as_uint(a1.w), r0, r1, r2, r3, t0, t1, t2, t3);
+                        // nearest hit child next; the others wait on the stack, nearest on top
+                        unsigned int next = r3;
+                        float tn = t3;
+                        if (r2 != REF_POP) { if (next != REF_POP) st.put(sp++, next, tn); next = r2; tn = t2; }
+                        if (r1 != REF_POP) { if (next != REF_POP) st.put(sp++, next, tn); next = r1; tn = t1; }
+                        if (r0 != REF_POP) { if (next != REF_POP) st.put(sp++, next, tn); next = r0; tn = t0; }
+                        cur = next;
+                    }
+                } else if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
                     const float4* p = pairs + 4 * (size_t)cur;
                     const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
                     const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));

@@ -41,17 +41,17 @@ def allreduce_film(film, group=None):
     return film
 
 
-def render_sharded(ctx, scene, seed, rank, world, spp=None, stream=None, **render_kw):
+def render_sharded(ctx, scene, seed, rank, world, spp=None, **render_kw):
     """Render this rank's share of the samples into the context's device film and all-reduce it.
-    Asynchronous on the context's stream (pass the torch ExternalStream wrapping it so that the
-    NCCL all-reduce is ordered after the render kernels)."""
+    Asynchronous on the context's own stream, on the context's own device: the NCCL all-reduce is
+    issued on a torch ExternalStream wrapping that stream, so it is ordered after the render kernels
+    whatever torch's current device / stream are."""
     import torch
     spp_total = scene.spp_squared(spp)
     begin, end = spp_shard(spp_total, rank, world)
-    device = torch.device("cuda", torch.cuda.current_device())
-    if stream is None:
-        stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
-    with torch.cuda.stream(stream):
+    device = torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    with torch.cuda.device(device), torch.cuda.stream(stream):
         ctx.film_clear()
         ctx.render(seed=seed, spp_total=spp_total, spp_begin=begin, spp_end=end, **render_kw)
         film = DeviceFilm(ctx).tensor(device)

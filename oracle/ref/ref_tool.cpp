@@ -13,6 +13,7 @@
  *   render  timed RenderContext::render() with Scene::intersect/occluded call
  *           counters (linker --wrap) and a raw float dump of the film
  *   post    Goblin::bloom / Goblin::toneMapping / the PPM writer on a raw rgb image
+ *   session load the scene once, then run any of the above from stdin (large scenes)
  * Only this TU is compiled with -fno-access-control so it can read private
  * members; it observes the reference, it never reimplements it.
  *
@@ -44,6 +45,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <random>
 #include <sstream>
 #include <thread>
 
@@ -109,6 +111,9 @@ static thread_local TLCount tl_count;
 struct RecordedRay { float v[8]; uint32_t kind; };
 static bool g_record = false;
 static thread_local std::vector<RecordedRay>* tl_rec = nullptr;
+// per-thread recording caps per kind (0 = intersect, 1 = occluded); ~0 = unlimited
+static uint64_t g_recordCap[2] = {~0ull, ~0ull};
+static thread_local uint64_t tl_recorded[2] = {0, 0};
 static std::vector<RecordedRay> g_recorded;
 
 extern "C" {
@@ -120,9 +125,10 @@ bool __real__ZNK6Goblin5Scene8occludedERKNS_3RayEPFbPKNS_9PrimitiveES3_E(
 bool __wrap__ZNK6Goblin5Scene9intersectERKNS_3RayEPfPNS_12IntersectionEPFbPKNS_9PrimitiveES3_E(
     const Scene* s, const Ray& r, float* e, Intersection* is, IntersectFilter f) {
     tl_count.i++;
-    if (g_record && tl_rec) {
+    if (g_record && tl_rec && tl_recorded[0] < g_recordCap[0]) {
         RecordedRay rr = {{r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.mint, r.maxt}, 0u};
         tl_rec->push_back(rr);
+        tl_recorded[0]++;
     }
     return __real__ZNK6Goblin5Scene9intersectERKNS_3RayEPfPNS_12IntersectionEPFbPKNS_9PrimitiveES3_E(
         s, r, e, is, f);
@@ -130,9 +136,10 @@ bool __wrap__ZNK6Goblin5Scene9intersectERKNS_3RayEPfPNS_12IntersectionEPFbPKNS_9
 bool __wrap__ZNK6Goblin5Scene8occludedERKNS_3RayEPFbPKNS_9PrimitiveES3_E(
     const Scene* s, const Ray& r, IntersectFilter f) {
     tl_count.o++;
-    if (g_record && tl_rec) {
+    if (g_record && tl_rec && tl_recorded[1] < g_recordCap[1]) {
         RecordedRay rr = {{r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.mint, r.maxt}, 1u};
         tl_rec->push_back(rr);
+        tl_recorded[1]++;
     }
     return __real__ZNK6Goblin5Scene8occludedERKNS_3RayEPFbPKNS_9PrimitiveES3_E(s, r, f);
 }
@@ -393,12 +400,12 @@ struct Tracer {
     }
 };
 
-static int cmdTrace(SceneView& v, const char* raysPath, const char* outPath) {
+static int cmdTrace(SceneView& v, const char* raysPath, const char* outPath, bool withFrag = true) {
     std::vector<float> rays = read_f32_file(raysPath);
     size_t n = rays.size() / 8;
     Tracer tr(v);
     std::vector<int32_t> hit(n), inst(n), prim(n), occ(n);
-    std::vector<float> t(n), eps(n), frag(n * 14);
+    std::vector<float> t(n), eps(n), frag(withFrag ? n * 14 : 0);
     unsigned nt = std::max(1u, std::thread::hardware_concurrency());
     std::vector<std::thread> pool;
     for (unsigned k = 0; k < nt; ++k) {
@@ -417,7 +424,7 @@ static int cmdTrace(SceneView& v, const char* raysPath, const char* outPath) {
                 prim[i] = h ? tr.primIndex(tl_lastInstance, is.primitive) : -1;
                 t[i] = h ? ray.maxt : 0.0f;
                 eps[i] = h ? e : 0.0f;
-                if (h) {
+                if (h && withFrag) {
                     const Fragment& fr = is.fragment;
                     float* o = &frag[14 * i];
                     const Vector3& p = fr.getPosition();
@@ -441,7 +448,7 @@ static int cmdTrace(SceneView& v, const char* raysPath, const char* outPath) {
     put_i32(f, "occluded", occ);
     put_f32(f, "t", t);
     put_f32(f, "eps", eps);
-    put_f32(f, "frag", frag, {n, 14});
+    if (withFrag) put_f32(f, "frag", frag, {n, 14});
     fclose(f);
     return 0;
 }
@@ -479,7 +486,10 @@ static int cmdCamRays(SceneView& v, const char* samplesPath, const char* outPath
  * The values are routed to the slots the integrator itself reads
  * (GoblinPathtracer.cpp:78-81 via GoblinLight.cpp:28-33, GoblinMaterial.cpp:31-37).
  */
-static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, bool record) {
+// samplesPath "@N:seed[:capI:capO]": N rows of mt19937 uniforms generated here (image position scaled to the
+// film) instead of a file -- for exporting large ray batches from the reference's own integrator; with caps the
+// run stops recording (and each thread stops sampling) once that many intersect / occluded rays are held.
+static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, bool record, bool recordThreads = false) {
     Renderer* r = v.ctx->mRenderer.get();
     PathTracer* pt = dynamic_cast<PathTracer*>(r);
     AORenderer* ao = dynamic_cast<AORenderer*>(r);
@@ -489,23 +499,46 @@ static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, boo
     // the AO renderer shoots mAOSampleIndex.sampleNum rays: ao_sample_num rounded up to a square
     const int aoRays = ao ? (int)ao->mAOSampleIndex.sampleNum : 0;
     size_t row = 4 + (pt ? 7 * (size_t)pt->mMaxRayDepth : 2 * (size_t)aoRays);
-    std::vector<float> sm = read_f32_file(samplesPath);
-    size_t n = sm.size() / row;
-    std::vector<float> out(n * 3);
-    std::vector<uint32_t> calls(n * 2);
-    unsigned nt = record ? 1u : std::max(1u, std::thread::hardware_concurrency());
+    std::vector<float> sm;
+    size_t n = 0;
+    const bool generated = samplesPath[0] == '@';
+    unsigned long long genSeed = 0, capI = 0, capO = 0;
+    if (generated) {
+        unsigned long long nn = 0;
+        sscanf(samplesPath + 1, "%llu:%llu:%llu:%llu", &nn, &genSeed, &capI, &capO);
+        n = (size_t)nn;
+    } else {
+        sm = read_f32_file(samplesPath);
+        n = sm.size() / row;
+    }
+    std::vector<float> out(generated ? 0 : n * 3);
+    std::vector<uint32_t> calls(generated ? 0 : n * 2);
+    // --record keeps the rays in sample order (one thread); --record-mt records on all cores (any order)
+    unsigned nt = record && !recordThreads ? 1u : std::max(1u, std::thread::hardware_concurrency());
     g_record = record;
+    g_recordCap[0] = capI ? (capI + nt - 1) / nt : ~0ull;
+    g_recordCap[1] = capO ? (capO + nt - 1) / nt : ~0ull;
+    const float filmW = (float)v.scene->getCamera()->getFilm()->mXRes, filmH = (float)v.scene->getCamera()->getFilm()->mYRes;
     std::vector<std::vector<RecordedRay>> recs(nt);
     std::vector<std::thread> pool;
     const CameraPtr cam = v.scene->getCamera();
     for (unsigned k = 0; k < nt; ++k) {
         pool.emplace_back([&, k]() {
             tl_rec = &recs[k];
+            tl_recorded[0] = tl_recorded[1] = 0;
             RNG rng;
             Sample s;
             s.allocateQuota(quota);
+            std::mt19937 gen((unsigned)(genSeed * 7919ull + k));
+            std::vector<float> rowBuf(row);
             for (size_t i = k; i < n; i += nt) {
-                const float* u = &sm[row * i];
+                if (generated) {
+                    if (capI && capO && tl_recorded[0] >= g_recordCap[0] && tl_recorded[1] >= g_recordCap[1]) break;
+                    for (size_t c = 0; c < row; ++c) rowBuf[c] = (float)(gen() >> 8) * (1.0f / 16777216.0f);
+                    rowBuf[0] *= filmW;
+                    rowBuf[1] *= filmH;
+                }
+                const float* u = generated ? rowBuf.data() : &sm[row * i];
                 s.imageX = u[0]; s.imageY = u[1]; s.lensU1 = u[2]; s.lensU2 = u[3];
                 if (pt) {
                     for (int b = 0; b < pt->mMaxRayDepth; ++b) {
@@ -530,6 +563,7 @@ static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, boo
                 float w = cam->generateRay(s, &ray);
                 uint64_t i0 = tl_count.i, o0 = tl_count.o;
                 Color L = r->Li(v.ctx->mScene, ray, s, rng, nullptr);
+                if (generated) continue;
                 calls[2 * i] = (uint32_t)(tl_count.i - i0);
                 calls[2 * i + 1] = (uint32_t)(tl_count.o - o0);
                 out[3 * i] = w * L.r; out[3 * i + 1] = w * L.g; out[3 * i + 2] = w * L.b;
@@ -540,8 +574,12 @@ static int cmdLi(SceneView& v, const char* samplesPath, const char* outPath, boo
     for (auto& th : pool) th.join();
     FILE* f = fopen(outPath, "wb");
     if (!f) return 2;
-    put_f32(f, "L", out, {n, 3});
-    put_u32(f, "calls", calls, {n, 2});
+    if (!generated) {
+        put_f32(f, "L", out, {n, 3});
+        put_u32(f, "calls", calls, {n, 2});
+    }
+    g_record = false;
+    g_recordCap[0] = g_recordCap[1] = ~0ull;
     if (record) {
         std::vector<float> rr;
         std::vector<uint32_t> kind;
@@ -569,6 +607,12 @@ static int cmdRender(SceneView& v, const char* outPath, int seed, int threads, i
     uint64_t samples = (uint64_t)(sr.xEnd - sr.xStart) * (uint64_t)(sr.yEnd - sr.yStart) * sppSq;
     unsigned cores = std::min<unsigned>(std::thread::hardware_concurrency(),
         r->mThreadNum == 0 ? ~0u : (unsigned)r->mThreadNum);
+    // a session renders the same context repeatedly: Film::mergeTile accumulates, so start from an empty film
+    for (size_t i = 0; i < (size_t)film->mXRes * film->mYRes; ++i) {
+        film->mPixels[i].color = Color(0.0f, 0.0f, 0.0f);
+        film->mPixels[i].weight = 0.0f;
+    }
+    g_intersectCalls = 0; g_occludedCalls = 0;
     auto t0 = std::chrono::steady_clock::now();
     v.ctx->render();
     auto t1 = std::chrono::steady_clock::now();
@@ -601,8 +645,9 @@ static void usage() {
     fprintf(stderr,
         "usage: ref_tool dump    scene.json out.gbar\n"
         "       ref_tool camrays scene.json samples.f32 out.gbar\n"
-        "       ref_tool trace   scene.json rays.f32 out.gbar\n"
-        "       ref_tool li      scene.json samples.f32 out.gbar [--record]\n"
+        "       ref_tool trace   scene.json rays.f32 out.gbar [--no-frag]\n"
+        "       ref_tool li      scene.json samples.f32 out.gbar [--record|--record-mt]\n"
+        "       ref_tool session scene.json   (commands on stdin, one per line, without the scene path)\n"
         "       ref_tool render  scene.json film.gbar|- [--seed S] [--threads T] [--spp N]\n"
         "       ref_tool post    in.f32 out.f32|out.ppm W H bloomRadius bloomWeight tone\n");
 }
@@ -635,39 +680,69 @@ static int cmdPost(int argc, char** argv) {
     return 0;
 }
 
+static std::streambuf* g_cout = nullptr;
+static std::ostringstream g_sink;
+
+// one command against a loaded scene; a = {cmd, args...}
+static int runCommand(SceneView& view, const std::vector<std::string>& a) {
+    const std::string& cmd = a[0];
+    if (cmd == "dump" && a.size() >= 2) return cmdDump(view, a[1].c_str());
+    if (cmd == "camrays" && a.size() >= 3) return cmdCamRays(view, a[1].c_str(), a[2].c_str());
+    if (cmd == "trace" && a.size() >= 3) return cmdTrace(view, a[1].c_str(), a[2].c_str(), !(a.size() >= 4 && a[3] == "--no-frag"));
+    if (cmd == "li" && a.size() >= 3) {
+        bool rec = a.size() >= 4 && (a[3] == "--record" || a[3] == "--record-mt");
+        return cmdLi(view, a[1].c_str(), a[2].c_str(), rec, rec && a[3] == "--record-mt");
+    }
+    if (cmd == "render" && a.size() >= 2) {
+        int seed = 1, threads = 0, spp = 0;
+        for (size_t i = 2; i + 1 < a.size(); i += 2) {
+            if (a[i] == "--seed") seed = atoi(a[i + 1].c_str());
+            else if (a[i] == "--threads") threads = atoi(a[i + 1].c_str());
+            else if (a[i] == "--spp") spp = atoi(a[i + 1].c_str());
+        }
+        std::cout.rdbuf(g_sink.rdbuf()); // progress + "write image" chatter
+        int rc = cmdRender(view, a[1].c_str(), seed, threads, spp);
+        std::cout.rdbuf(g_cout);
+        return rc;
+    }
+    return -1;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 4) { usage(); return 1; }
+    if (argc < 3) { usage(); return 1; }
     std::string cmd = argv[1];
     if (cmd == "post") return cmdPost(argc, argv);
+    if (cmd != "session" && argc < 4) { usage(); return 1; }
     // the loader echoes every parameter to stdout; silence it while loading
-    std::streambuf* old = std::cout.rdbuf();
-    std::ostringstream sink;
-    std::cout.rdbuf(sink.rdbuf());
+    g_cout = std::cout.rdbuf();
+    std::cout.rdbuf(g_sink.rdbuf());
     RenderContext* ctx = ContextLoader::load(argv[2]);
-    std::cout.rdbuf(old);
+    std::cout.rdbuf(g_cout);
     if (!ctx) { fprintf(stderr, "failed to load %s\n", argv[2]); return 2; }
     SceneView view;
     buildView(view, ctx);
-    if (cmd == "dump") return cmdDump(view, argv[3]);
-    if (cmd == "camrays" && argc >= 5) return cmdCamRays(view, argv[3], argv[4]);
-    if (cmd == "trace" && argc >= 5) return cmdTrace(view, argv[3], argv[4]);
-    if (cmd == "li" && argc >= 5) {
-        bool rec = argc >= 6 && std::string(argv[5]) == "--record";
-        return cmdLi(view, argv[3], argv[4], rec);
-    }
-    if (cmd == "render") {
-        int seed = 1, threads = 0, spp = 0;
-        for (int i = 4; i + 1 < argc; i += 2) {
-            std::string k = argv[i];
-            if (k == "--seed") seed = atoi(argv[i + 1]);
-            else if (k == "--threads") threads = atoi(argv[i + 1]);
-            else if (k == "--spp") spp = atoi(argv[i + 1]);
+    if (cmd == "session") {
+        // session scene.json: the scene is loaded once (a 10 M-triangle scene takes the reference a minute),
+        // then one command per line of stdin, same words as the one-shot forms without the scene path
+        printf("SESSION_READY\n");
+        fflush(stdout);
+        std::string line;
+        while (std::getline(std::cin, line)) {
+            std::istringstream is(line);
+            std::vector<std::string> a;
+            for (std::string w; is >> w;) a.push_back(w);
+            if (a.empty()) continue;
+            if (a[0] == "quit") break;
+            int rc = runCommand(view, a);
+            printf("SESSION_DONE %d %s\n", rc, a[0].c_str());
+            fflush(stdout);
+            if (rc != 0) return rc < 0 ? 1 : rc;
         }
-        std::cout.rdbuf(sink.rdbuf()); // progress + "write image" chatter
-        int rc = cmdRender(view, argv[3], seed, threads, spp);
-        std::cout.rdbuf(old);
-        return rc;
+        return 0;
     }
-    usage();
-    return 1;
+    std::vector<std::string> a = {cmd};
+    for (int i = 3; i < argc; ++i) a.push_back(argv[i]);
+    int rc = runCommand(view, a);
+    if (rc < 0) { usage(); return 1; }
+    return rc;
 }

@@ -33,14 +33,20 @@ def _random_rays(scene, n, seed, finite_frac=0.3):
     return np.concatenate([o, d.astype(np.float32), mint, maxt], 1).astype(np.float32)
 
 
-def _check_traces(ctx, scene, rays):
+def _check_traces(ctx, scene, rays, modes=("wide", "exact")):
+    """Both walks of the traversal kernels (include/goblin_b200.h GB_TRACE_*): the default 4-wide one and the
+    pair-node one, bit for bit against the oracle's walk of the reference tree."""
     want = op.trace_closest(scene, rays)
-    got = ctx.trace_closest(rays)
-    assert np.array_equal(got["inst"], want["inst"])
-    assert np.array_equal(got["prim"], want["prim"])
-    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
-    assert np.array_equal(got["eps"].view(np.uint32), want["eps"].view(np.uint32))
-    assert np.array_equal(ctx.trace_any(rays), op.trace_any(scene, rays))
+    want_any = op.trace_any(scene, rays)
+    for mode in modes:
+        ctx.set_trace_mode(mode)
+        got = ctx.trace_closest(rays)
+        assert np.array_equal(got["inst"], want["inst"]), mode
+        assert np.array_equal(got["prim"], want["prim"]), mode
+        assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), mode
+        assert np.array_equal(got["eps"].view(np.uint32), want["eps"].view(np.uint32)), mode
+        assert np.array_equal(ctx.trace_any(rays), want_any), mode
+    ctx.set_trace_mode("wide")
     return (want["inst"] >= 0).mean()
 
 
@@ -160,11 +166,21 @@ def test_large_ray_batches_bunny(built):
 
 
 def test_bvh_depth_and_stack_limits(built):
-    """A degenerate scene whose BVH is as deep as the reference's todo[64] allows still traces
-    exactly (deep shared-memory stacks), and the counters keep matching."""
+    """Stack sizing follows the trees of the uploaded scene.  A scene whose wide-walk stack column (three
+    entries per wide level) would not leave room for four CTAs per SM is walked pair-wise instead, and
+    gb_get_trace_mode says so: forced here by shrinking the limit (GB_MAX_WIDE_SMEM, read at upload)."""
     import os
     d = util.gen_scene("grid", 48)
+    os.environ["GB_MAX_WIDE_SMEM"] = "4096"
+    try:
+        ctx, scene = _ctx(os.path.join(d, "grid_pt.json"))
+    finally:
+        del os.environ["GB_MAX_WIDE_SMEM"]
+    assert ctx.trace_mode() == "exact"
+    _check_traces(ctx, scene, _random_rays(scene, 50_000, 12, finite_frac=0.5), modes=("wide",))
+    ctx.close()
     ctx, scene = _ctx(os.path.join(d, "grid_pt.json"))
+    assert ctx.trace_mode() == "wide"
     rays = _random_rays(scene, 50_000, 13, finite_frac=0.5)
     _check_traces(ctx, scene, rays)
     ctx.enable_counters(True)
@@ -214,9 +230,15 @@ def test_axis_aligned_rays_nan_in_the_slab_test(built):
     assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
     assert gc["nodes_visited"] == wc["nodes_visited"] and gc["prims_tested"] == wc["prims_tested"]
     ctx.enable_counters(False)
-    got2 = ctx.trace_closest(rays)
-    assert np.array_equal(got2["inst"], want["inst"]) and np.array_equal(got2["t"].view(np.uint32), want["t"].view(np.uint32))
-    assert np.array_equal(ctx.trace_any(rays), op.trace_any(scene, rays))
+    want_any = op.trace_any(scene, rays)
+    for mode in ("exact", "wide"):
+        # the wide walk skips the intermediate nodes' own box tests (where a NaN would make the reference prune);
+        # on this batch the CPU emulation of the wide walk (tests/test_wide_walk.py) agrees with the reference
+        # on every ray, so the kernel must as well
+        ctx.set_trace_mode(mode)
+        got2 = ctx.trace_closest(rays)
+        assert np.array_equal(got2["inst"], want["inst"]) and np.array_equal(got2["t"].view(np.uint32), want["t"].view(np.uint32)), mode
+        assert np.array_equal(ctx.trace_any(rays), want_any), mode
     assert (want["inst"] >= 0).mean() > 0.2
 
 
@@ -226,9 +248,9 @@ def test_axis_aligned_rays_nan_in_the_slab_test(built):
 ])
 def test_full_size_scenes_ray_batches(built, kind, json_name, n):
     """The two largest named scenes at BASELINE.json's sizes: coherent camera rays and incoherent
-    segments, closest and any-hit, bit-exact against the oracle's walk of the same flattened scene,
-    and a render whose film weights (which only depend on where the samples fall) match the oracle's
-    on a strided subset of pixels."""
+    segments, closest and any-hit, both walks bit-exact against the oracle's walk of the same flattened
+    scene, plus a batch-independence property (a ray's answer does not depend on which rays share its warp).
+    The reference itself is compared on these scenes in tests/test_gpu_vs_reference.py."""
     import os
     d = util.gen_scene(kind)
     ctx, scene = _ctx(os.path.join(d, json_name))

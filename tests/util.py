@@ -62,3 +62,56 @@ def film_ttest(images, gold, rel_floor=2e-3):
     floor = (rel_floor * np.maximum(ref, mean)) ** 2 + 1e-12
     t = (mean - ref) / np.sqrt(var_of_mean + ref_var + floor)
     return t[ref.sum(axis=2) > 0]
+
+
+class RefSession:
+    """`ref_tool session scene.json`: the UNMODIFIED reference (oracle/_ref) with the scene loaded once,
+    then commands from stdin.  Loading the 10 M-triangle scene takes the reference about a minute; the
+    tests that compare with it on that scene do everything in one session."""
+
+    def __init__(self, scene_path, cwd=None):
+        self.proc = subprocess.Popen([REF_TOOL, "session", scene_path], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                     stderr=subprocess.PIPE, text=True, cwd=cwd)
+        self._expect("SESSION_READY")
+
+    def _expect(self, prefix):
+        lines = []
+        while True:
+            line = self.proc.stdout.readline()
+            if not line:
+                raise RuntimeError("ref_tool session ended: " + "".join(lines[-5:]) + self.proc.stderr.read()[-2000:])
+            lines.append(line)
+            if line.startswith(prefix):
+                return line, lines
+
+    def run(self, *words):
+        """One command (e.g. run("trace", rays_path, out_path)); returns the lines it printed."""
+        self.proc.stdin.write(" ".join(str(w) for w in words) + "\n")
+        self.proc.stdin.flush()
+        line, lines = self._expect("SESSION_DONE")
+        if int(line.split()[1]) != 0:
+            raise RuntimeError(f"ref_tool {words[0]} failed: {line}")
+        return lines
+
+    def render(self, out, seed, spp, threads=0):
+        """Timed RenderContext::render(); returns the REF_RESULT record."""
+        import json
+        words = ["render", out, "--seed", seed, "--spp", spp] + (["--threads", threads] if threads else [])
+        lines = self.run(*words)
+        rec = [l for l in lines if "REF_RESULT" in l]
+        return json.loads(rec[-1].split("REF_RESULT", 1)[1])
+
+    def close(self):
+        if self.proc.poll() is None:
+            try:
+                self.proc.stdin.write("quit\n")
+                self.proc.stdin.flush()
+                self.proc.wait(timeout=60)
+            except Exception:
+                self.proc.kill()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
