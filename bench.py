@@ -158,14 +158,50 @@ def cpu_reference_sample(scene_json, budget_s=12.0):
             "mrays_per_s": (calls[0] + calls[1]) / dt * 1e-6, "seconds": dt}
 
 
+def workload_config(scene_name, scene_json, world, spp_override=0):
+    """The `config` of the JSON line: what is rendered, read from the scene file alone, so that the CUDA arm and
+    the reference arm (--impl reference) describe the same workload with the same keys and values."""
+    import math
+    sc = json.load(open(scene_json))
+    rs, cam = sc["render_setting"], sc["camera"]
+    xres, yres = cam["film"]["resolution"]
+    fw = cam.get("filter", {}).get("width", [2.0, 2.0])
+    spp = spp_override or int(rs["sample_per_pixel"])
+    root = int(math.ceil(math.sqrt(spp)))  # sample_per_pixel rounded up to a square (src/GoblinSampler.cpp:72)
+    samples = (xres + 2 * math.ceil(fw[0])) * (yres + 2 * math.ceil(fw[1])) * root * root  # Film::getSampleRange
+    return {"workload": NOTES[scene_name], "scene": scene_name, "resolution": [xres, yres], "spp": root * root,
+            "max_ray_depth": int(rs.get("max_ray_depth", 5)), "render_method": rs.get("render_method", "path_tracing"),
+            "camera_samples_per_gpu_step": samples, "camera_samples_per_step": samples * world,
+            "parallelism": (f"weak scaling: {world} GPUs x one full frame each (scene replica per GPU, own sample set, NCCL film "
+                            f"all-reduce per step)") if world > 1 else "1 GPU",
+            "l2": "CUDA arm: L2 flushed between steps (256 MB fill, its time subtracted), per-step path state exceeds L2; "
+                  "reference arm: host CPU, not applicable"}
+
+
 def bench_reference(args, rank):
+    """The reference's own CPU path (oracle/_ref: the unmodified sources) on this box's host cores: every step is one
+    render of the same frame at the same spp as the CUDA arm's step when that takes <= ~8 s (the headline scene does),
+    else a bounded spp sample of it."""
     if rank != 0:
         return
     scene_json = scene_path(args.scene)
+    config = workload_config(args.scene, scene_json, args.gpus, args.spp)
     vals = []
     last = None
+    full_spp = None
+    if os.path.exists(REF_TOOL) and not args.ref_budget:
+        probe = run_ref_tool(scene_json, 1)
+        if config["camera_samples_per_gpu_step"] / max(probe["camera_samples"] / max(probe["seconds"], 1e-3), 1.0) <= 8.0:
+            full_spp = config["spp"]
     for step in range(args.warmup + args.steps):
-        last = cpu_reference_sample(scene_json, budget_s=args.ref_budget or 4.0)
+        if full_spp:
+            res = run_ref_tool(scene_json, full_spp)
+            last = {"value": res["msamples_per_s"], "cores": res["cores"], "kind": "reference", "seconds": res["seconds"],
+                    "mrays_per_s": res["mrays_per_s"],
+                    "sample": f"the whole frame: {res['spp']} spp ({res['camera_samples']} camera samples) in {res['seconds']:.2f} s, "
+                              f"g_ray thread pool on all host cores"}
+        else:
+            last = cpu_reference_sample(scene_json, budget_s=args.ref_budget or 4.0)
         if step >= args.warmup:
             vals.append(last)
     value = sum(v["value"] for v in vals) / len(vals)
@@ -174,12 +210,80 @@ def bench_reference(args, rank):
             "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": NOTES[args.scene], "scene": args.scene, "step": last["sample"]},
+            "config": config,
+            "reference_step": last["sample"],
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
             "mrays_per_s": sum(v["mrays_per_s"] for v in vals) / len(vals),
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def strong_record(ctx, scene, spp, rank, world, stream, flush, barrier, steps):
+    """One frame of `scene` at `spp` samples per pixel, the sample indices split over the ranks: per
+    frame film clear + render of this rank's slice + NCCL all-reduce, timed with CUDA events on the context's
+    stream, max over ranks.  Rank 0 then renders the same frames alone (same seeds): the 1-GPU frame time on this
+    box for the efficiency, and the film the all-reduced one must equal."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from goblin_b200 import distributed
+    b, e = distributed.spp_shard(spp, rank, world)
+    sr = scene.sample_range()
+    frame_samples = (sr[1] - sr[0]) * (sr[3] - sr[2]) * spp
+
+    def frames(n, begin, end, merge, seed0):
+        evs = []
+        for i in range(n):
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xFF)
+                a, z, m = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record()
+                ctx.film_clear()
+                ctx.render(seed=seed0 + i, spp_total=spp, spp_begin=begin, spp_end=end)
+                m.record()
+                if merge:
+                    ctx.film_allreduce()
+                z.record()
+                evs.append((a, m, z))
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        return evs
+
+    frames(2, b, e, True, 7000)  # warm-up (allocates the wave buffers of this slice size)
+    barrier()
+    ctx.reset_kernel_times()
+    ctx.enable_kernel_timing(True)
+    evs = frames(steps, b, e, True, 7100)
+    ctx.enable_kernel_timing(False)
+    kt = ctx.kernel_times()
+    merged = ctx.film_download().copy() if rank == 0 else None  # the last frame, all-reduced
+    ms = sum(a.elapsed_time(z) for a, _, z in evs) / steps
+    ar_ms = sum(m.elapsed_time(z) for _, m, z in evs) / steps
+    t = torch.tensor([ms, ar_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0].item()), float(t[1].item())
+    barrier()
+    rec = None
+    if rank == 0:
+        frames(1, 0, spp, False, 7000)
+        one = frames(steps, 0, spp, False, 7100)
+        one_ms = sum(a.elapsed_time(z) for a, _, z in one) / steps
+        whole = ctx.film_download()
+        denom = np.maximum(np.abs(whole), 1e-3)
+        rel = float((np.abs(merged - whole) / denom).max())
+        ok = bool(np.allclose(merged, whole, rtol=5e-4, atol=1e-4))
+        overhead = ms - one_ms / world
+        rec = {"spp_total": spp, "spp_per_gpu": [e - b if r == rank else distributed.spp_shard(spp, r, world)[1] - distributed.spp_shard(spp, r, world)[0] for r in range(world)],
+               "camera_samples_per_frame": frame_samples, "ms_per_frame": ms, "value": frame_samples / (ms * 1e-3) * 1e-6,
+               "unit": "Msamples/s", "steps": steps, "one_gpu_ms_per_frame": one_ms, "speedup": one_ms / ms,
+               "efficiency": one_ms / (world * ms), "allreduce_ms": ar_ms, "film_bytes": int(whole.nbytes),
+               "allreduce_check": ok, "allreduce_max_rel_diff": rel,
+               "kernel_ms_per_frame_rank0": {k: v[0] / steps for k, v in kt.items() if v[1]},
+               "limiter": (f"{overhead:.2f} ms per frame do not shrink with N: {ar_ms:.2f} ms film all-reduce, the rest are the late-bounce "
+                           f"launches (a few thousand paths on 148 SMs) and per-frame fixed costs (film clear, launch latency)")}
+    barrier()
+    return rec
 
 
 class DevBuf:
@@ -215,6 +319,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-stats", action="store_true", help="skip the counters child process (ncu runs: no roofline)")
     ap.add_argument("--no-fast-tree", action="store_true", help="skip the extra --accel sah leg of the default run")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling records")
+    ap.add_argument("--no-strong-grid", action="store_true", help="N > 1: skip the 10 M-triangle strong-scaling record")
     ap.add_argument("--stats-only", default="", help=argparse.SUPPRESS)  # internal: "seed,spp_total,begin,end"
     ap.add_argument("--ref-budget", type=float, default=0.0,
                     help="seconds of CPU work per reference sample (default: 12 for the cpu_baseline of the CUDA arm, 4 per step of --impl reference)")
@@ -304,8 +410,12 @@ def main():
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     film_ptr, film_floats = ctx.film_device_ptr()
-    film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    if world > 1:
+        # Film::mergeTile across GPUs is the library's own NCCL all-reduce (gb_film_allreduce); torch.distributed only
+        # carries the communicator id to the other ranks
+        from goblin_b200 import distributed
+        distributed.init_film_comm(ctx, rank, world)
 
     def step(i, flush_l2=True):
         with torch.cuda.stream(stream):
@@ -314,7 +424,7 @@ def main():
             ctx.film_clear()
             ctx.render(seed=seed_of(i), spp_total=spp, spp_begin=spp_begin, spp_end=spp_end)
             if world > 1:
-                dist.all_reduce(film_t)  # Film::mergeTile across GPUs
+                ctx.film_allreduce()
 
     # traversal statistics of one step (counters on: a different, slower instantiation of the
     # traversal kernels) give the algorithmic bytes.  They are gathered by a short-lived child
@@ -375,24 +485,42 @@ def main():
     host_film = np.zeros(1, np.float32)
     for i in range(2 if e2e_steps else 0):
         ctx.upload_scene(scene)
-    film_ptr, film_floats = ctx.film_device_ptr()
-    film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
     host_buf = np.zeros((scene.desc.film.yres, scene.desc.film.xres, 4), np.float32)
     barrier()
     torch.cuda.synchronize()
+    # Every step: the scene goes host -> device from the caller's arrays (gb_upload_scene_async: staged and copied on the
+    # library's copy stream), the frame is rendered (+ all-reduced), the film comes back device -> host into the caller's
+    # buffer.  Software-pipelined like a frame loop: the upload for step i + 1 is issued while step i renders, so the
+    # host staging and the PCIe copy overlap device work; every step still pays its own H2D and D2H inside the timed region.
     w0 = time.perf_counter()
+    if e2e_steps:
+        ctx.upload_scene_async(scene)
     for i in range(e2e_steps):
-        ctx.upload_scene(scene)  # frees and reallocates the film: re-wrap it
-        film_ptr, film_floats = ctx.film_device_ptr()
-        film_t = torch.as_tensor(DevBuf(film_ptr, film_floats), device=torch.device("cuda", local_rank))
         step(10000 + i, flush_l2=False)
+        if i + 1 < e2e_steps:
+            ctx.upload_scene_async(scene)
         host_film = ctx.film_download(out=host_buf)  # the caller's film buffer, reused like Film::mPixels
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - w0) * 1e3
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    # the unpipelined figure beside it: upload, render, download strictly one after the other
+    w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx.upload_scene(scene)
+        step(11000 + i, flush_l2=False)
+        host_film = ctx.film_download(out=host_buf)
+    torch.cuda.synchronize()
+    e2e_serial_ms = (time.perf_counter() - w0) * 1e3
+    up_ms = None
+    if e2e_steps:  # one synchronous upload by itself: host validation + staging + PCIe copy + device-side derivation
+        ctx.synchronize()
+        u0 = time.perf_counter()
+        for i in range(3):
+            ctx.upload_scene(scene)
+        up_ms = (time.perf_counter() - u0) * 1e3 / 3
+    te = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms, e2e_serial_ms = float(te[0].item()), float(te[1].item())
     e2e_value = samples_per_step_all / (e2e_ms / e2e_steps * 1e-3) * 1e-6 if e2e_steps else None
     assert np.isfinite(host_film).all()
 
@@ -426,6 +554,29 @@ def main():
             ctx.upload_scene(scene)
         except Exception as e:  # an extra, never fatal
             fast_tree = {"accel": "sah", "value": None, "note": f"failed: {e}"}
+
+    # ---- strong scaling, driver-visible (N > 1): ONE sample set split N ways by sample index, film all-reduce inside the
+    # timed frame, the all-reduced frame checked on rank 0 against the same frame rendered by rank 0 alone
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = {}
+        strong[args.scene] = strong_record(ctx, scene, spp, rank, world, stream, flush, barrier, steps=max(3, min(args.steps, 10)))
+        if args.scene == "bunny" and not args.no_strong_grid:  # BASELINE.json config 4: the 10 M-triangle grid, 64 spp split N ways
+            try:
+                if rank == 0:
+                    scene_path("grid")
+                barrier()
+                grid = api.Scene(scene_path("grid"), accel=args.accel)
+                ctx.upload_scene(grid)
+                ctx.set_trace_mode(args.trace_mode)
+                strong["grid"] = strong_record(ctx, grid, grid.spp_squared(), rank, world, stream, flush, barrier, steps=3)
+                if strong["grid"] is not None:
+                    strong["grid"]["workload"] = NOTES["grid"]
+                ctx.upload_scene(scene)
+                ctx.set_trace_mode(args.trace_mode)
+                del grid
+            except Exception as e:  # an extra, never fatal -- but every rank must fail alike or the barriers hang
+                strong["grid"] = {"failed": str(e)}
 
     if rank == 0 and st is None:
         st = {k: 0 for k in ("nodes_visited", "nodes_visited_any", "prims_tested", "prims_tested_any", "instances_entered",
@@ -480,18 +631,25 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": NOTES[args.scene], "scene": args.scene, "accel": args.accel, "trace_mode": ctx.trace_mode(), "spp": spp,
-                           "spp_range_rank0": [spp_begin, spp_end], "camera_samples_per_step": samples_per_step_all, "triangles": int(scene.desc.n_tris),
-                           "parallelism": f"spp x{world} (scene replica per GPU, NCCL film all-reduce)" if world > 1 else "1 GPU",
-                           "l2": "L2 flushed between steps (256 MB fill, its time subtracted); per-step path state (~176 B per camera sample, GBs per wave) exceeds L2",
-                           "scene_load_s": load_s},
+                "config": workload_config(args.scene, scene_json, world, args.spp),
+                "run": {"accel": args.accel, "trace_mode": ctx.trace_mode(), "spp_range_rank0": [spp_begin, spp_end],
+                        "camera_samples_per_step_measured": samples_per_step_all, "triangles": int(scene.desc.n_tris),
+                        "scene_load_s": load_s,
+                        "film_merge": "gb_film_allreduce (NCCL, library-owned communicator)" if world > 1 else "none (1 GPU)"},
                 "mrays_per_s": mrays, "rays_per_sample": rays_all / (samples_per_step_all * args.steps),
                 "gpu_launches": int(timed["kernel_launches"]),
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(ctx.upload_bytes()),
                         "d2h_bytes_per_step": int(film_floats * 4), "steps": e2e_steps,
-                        "what": "gb_upload_scene (host arrays) + gb_film_clear + gb_render + gb_film_download per step"},
+                        "serial_value": samples_per_step_all / (e2e_serial_ms / e2e_steps * 1e-3) * 1e-6 if e2e_steps else None,
+                        "upload_ms": up_ms, "upload_gb_per_s": (ctx.upload_bytes() / (up_ms * 1e-3) * 1e-9) if up_ms else None,
+                        "what": "per step: gb_upload_scene_async (host arrays -> pinned staging -> H2D on the copy stream, issued one step "
+                                "ahead so it overlaps the previous step's kernels) + gb_film_clear + gb_render (+ gb_film_allreduce) + "
+                                "gb_film_download into the caller's buffer; serial_value = the same with gb_upload_scene, nothing overlapped"},
                 "roofline": roofline}
+        if strong is not None:
+            line["strong"] = strong
+            line["allreduce_check"] = all(v.get("allreduce_check") is True for v in strong.values() if v and "failed" not in v)
         if fast_tree is not None:
             line["fast_tree"] = fast_tree
         if world == 1 and not args.no_cpu_baseline:

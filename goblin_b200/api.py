@@ -148,8 +148,11 @@ EXPORTS = [
     "gb_synchronize", "gb_stream", "gb_enable_counters", "gb_get_counters", "gb_reset_counters",
     "gb_last_kernel_ms", "gb_last_error", "gb_version", "gb_enable_kernel_timing", "gb_get_kernel_times",
     "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning", "gb_upload_bytes",
-    "gb_set_trace_mode", "gb_get_trace_mode",
+    "gb_set_trace_mode", "gb_get_trace_mode", "gb_upload_scene_async",
+    "gb_comm_init_all", "gb_comm_unique_id", "gb_comm_init_rank", "gb_comm_attach", "gb_comm_destroy", "gb_comm_size",
+    "gb_film_allreduce", "gb_film_allreduce_all", "gb_nccl_version",
 ]
+COMM_ID_BYTES = 128
 
 # GB_TRACE_*: how the traversal kernels walk the reference's tree
 TRACE_MODES = {"wide": 0, "exact": 1}
@@ -190,6 +193,7 @@ def lib():
         l.gb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.gb_destroy.argtypes = [C.c_void_p]
         l.gb_upload_scene.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+        l.gb_upload_scene_async.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
         l.gb_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         l.gb_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         l.gb_trace_closest_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -217,6 +221,15 @@ def lib():
         l.gb_set_wave_paths.argtypes = [C.c_void_p, C.c_size_t]
         l.gb_upload_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         l.gb_set_tuning.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+        l.gb_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        l.gb_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        l.gb_comm_init_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        l.gb_comm_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        l.gb_comm_destroy.argtypes = [C.c_void_p]
+        l.gb_comm_size.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        l.gb_film_allreduce.argtypes = [C.c_void_p]
+        l.gb_film_allreduce_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        l.gb_nccl_version.argtypes = [C.POINTER(C.c_int)]
         l.gb_set_trace_mode.argtypes = [C.c_void_p, C.c_int]
         l.gb_get_trace_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _lib = l
@@ -359,6 +372,12 @@ class Context:
         check(lib().gb_upload_scene(self._h, C.byref(scene.desc)))
         self.scene = scene
 
+    def upload_scene_async(self, scene):
+        """gb_upload_scene_async: stage + copy on the copy stream while queued kernels still read the current
+        scene; what is queued afterwards uses the new one.  Does not clear the film."""
+        check(lib().gb_upload_scene_async(self._h, C.byref(scene.desc)))
+        self.scene = scene
+
     def trace_closest(self, rays):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
         hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
@@ -478,6 +497,25 @@ class Context:
         arr = (C.c_int * len(values))(*values)
         check(lib().gb_set_tuning(self._h, arr, len(values)))
 
+    # ---- Film::mergeTile across GPUs: NCCL all-reduce of the device film, issued by the library
+    def comm_init_rank(self, comm_id, nranks, rank):
+        """One process per GPU: join the film communicator (comm_id: the 128 bytes of comm_unique_id()
+        made on rank 0 and carried here by the launcher's own channel)."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        check(lib().gb_comm_init_rank(self._h, buf, COMM_ID_BYTES, nranks, rank))
+
+    def comm_size(self):
+        n = C.c_int()
+        check(lib().gb_comm_size(self._h, C.byref(n)))
+        return n.value
+
+    def comm_destroy(self):
+        check(lib().gb_comm_destroy(self._h))
+
+    def film_allreduce(self):
+        """Sum the device film over all ranks, in place, asynchronously on the context's stream."""
+        check(lib().gb_film_allreduce(self._h))
+
     def set_trace_mode(self, mode):
         """"wide" (default: 4-wide nodes) or "exact" (pair nodes, every box test of the reference)."""
         check(lib().gb_set_trace_mode(self._h, TRACE_MODES[mode]))
@@ -491,6 +529,29 @@ class Context:
         ms = C.c_float()
         check(lib().gb_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    check(lib().gb_comm_unique_id(buf, COMM_ID_BYTES))
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """One process, one Context per GPU: a communicator over all of them (ncclCommInitAll)."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    check(lib().gb_comm_init_all(arr, len(contexts)))
+
+
+def film_allreduce_all(contexts):
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    check(lib().gb_film_allreduce_all(arr, len(contexts)))
+
+
+def nccl_version():
+    v = C.c_int()
+    check(lib().gb_nccl_version(C.byref(v)))
+    return v.value
 
 
 def device_count():

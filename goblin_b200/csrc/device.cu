@@ -174,7 +174,7 @@ struct TracePolicy {
             out.inst = sh.x;
             out.prim = 0;
             if (info.x == GB_GEOM_MESH) {
-                out.prim = (int)__float_as_uint(__ldg(sc->triRec + 3 * (size_t)(info.z + h.prim) + 2).y);
+                out.prim = (int)__float_as_uint(__ldg(sc->triRec + kTriRecVec4 * (size_t)(info.z + h.prim) + 2).y);
             }
         } else {
             out.t = 0.0f; out.eps = 0.0f; out.inst = -1; out.prim = -1;
@@ -839,16 +839,28 @@ struct gb_context {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool haveScene = false;
     DeviceScene sc{};
-    char* arenaDev = nullptr;   // every scene array lives in one device allocation ...
-    char* arenaHost = nullptr;  // ... filled through one (pinned) staging buffer
-    size_t arenaCap = 0, hostCap = 0, uploadBytes = 0;
-    int* deriveError = nullptr;      // device flag of the derive kernels (bad index in the scene arrays)
-    int* deriveErrorHost = nullptr;  // pinned
+    // Every scene array lives in one device allocation, filled through one pinned staging buffer.  There are two
+    // such pairs ("slots"): gb_upload_scene_async stages and copies the NEXT scene into the idle slot on its own
+    // stream while kernels still read the current one; the second slot only exists once that call has been used.
+    struct SceneSlot {
+        char* dev = nullptr;
+        char* host = nullptr;
+        size_t devCap = 0, hostCap = 0;
+        bool pinned = false;
+        cudaEvent_t uploaded = nullptr; // copy + derive kernels of the last upload into this slot are done
+        cudaEvent_t lastUse = nullptr;  // everything queued on the context's stream while this slot was current
+        int* deriveError = nullptr;     // device flag of the derive kernels (bad index in the scene arrays)
+        int* deriveErrorHost = nullptr; // pinned
+        bool checkPending = false;      // an asynchronous upload whose deriveErrorHost has not been looked at yet
+    } slots[2];
+    int slot = 0;                   // the slot ctx->sc points into
+    cudaStream_t copyStream = nullptr;
+    size_t uploadBytes = 0;
     float* filmHost = nullptr;       // pinned staging for film downloads
     size_t filmHostPixels = 0;
-    bool arenaPinned = false;
     gb_render_setting setting{};
-    int stackEntries = 0; // per-thread traversal stack entries this scene needs
+    int stackEntries = 0; // per-thread traversal stack entries this scene needs: the 4-wide walk's ...
+    int stackEntriesPair = 0; // ... and the pair walk's (one per level)
     float4* film = nullptr;
     size_t filmPixels = 0;
     gb_film_desc filmDesc{};
@@ -861,6 +873,9 @@ struct gb_context {
     unsigned long long* stats = nullptr;
     bool statsOn = false;
     uint64_t launches = 0;
+    void* comm = nullptr;   // ncclComm_t of the film all-reduce (film_comm.inl); owned unless attached
+    bool commOwned = false;
+    int commRanks = 0;
     bool wideFits = false;  // the 4-wide walk's stack fits in shared memory for this scene
     int traceMode = GB_TRACE_WIDE;
     // launch geometry of the traversal kernels, keyed by kernel function: depends on the kernel, the
@@ -893,12 +908,14 @@ constexpr int kMaxDepthCtr = 66;
     } while (0)
 
 void freeScene(gb_context* ctx) {
-    if (ctx->arenaDev) cudaFree(ctx->arenaDev);
-    if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
-    ctx->arenaDev = nullptr;
-    ctx->arenaHost = nullptr;
-    ctx->arenaCap = 0;
-    ctx->hostCap = 0;
+    for (gb_context::SceneSlot& sl : ctx->slots) {
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.host) { if (sl.pinned) cudaFreeHost(sl.host); else std::free(sl.host); }
+        sl.dev = nullptr;
+        sl.host = nullptr;
+        sl.devCap = sl.hostCap = 0;
+        sl.checkPending = false;
+    }
     if (ctx->film) cudaFree(ctx->film);
     ctx->film = nullptr;
     ctx->filmPixels = 0;
@@ -975,15 +992,16 @@ int ensureWave(gb_context* ctx, size_t paths) {
 
 // per thread: stackEntries 8-byte stack entries + the 6-float world-space ray
 size_t traceSmemFor(int stackEntries) { return ((size_t)stackEntries * sizeof(uint2) + 6 * sizeof(float)) * kTraceBlock; }
-size_t traceSmem(const gb_context* ctx) { return traceSmemFor(ctx->stackEntries); }
+int stackEntriesOf(const gb_context* ctx, int mode); // by walk (defined below, next to walkMode)
+size_t traceSmem(const gb_context* ctx, int mode) { return traceSmemFor(stackEntriesOf(ctx, mode)); }
 
 template <typename K>
-int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
+int setupTraceKernel(gb_context* ctx, K kernel, int mode, int* grid) {
     const void* key = reinterpret_cast<const void*>(kernel);
     for (const auto& e : ctx->gridCache) {
         if (e.first == key) { *grid = e.second; return GB_OK; }
     }
-    size_t smem = traceSmem(ctx);
+    size_t smem = traceSmem(ctx, mode);
     GB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int perSM = 0;
     GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kTraceBlock, smem));
@@ -993,6 +1011,8 @@ int setupTraceKernel(gb_context* ctx, K kernel, int* grid) {
     ctx->gridCache.emplace_back(key, *grid);
     return GB_OK;
 }
+
+int stackEntriesOf(const gb_context* ctx, int mode) { return mode == WALK_WIDE ? ctx->stackEntries : ctx->stackEntriesPair; }
 
 // which walk the traversal kernels of this context run right now
 int walkMode(const gb_context* ctx) {
@@ -1043,23 +1063,39 @@ int gb_create(int device, gb_context** out) {
     GB_CUDA(cudaMalloc((void**)&ctx->traceHead, 64));
     GB_CUDA(cudaMalloc((void**)&ctx->stats, S_COUNT * sizeof(unsigned long long)));
     GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
-    GB_CUDA(cudaMalloc((void**)&ctx->deriveError, sizeof(int)));
-    GB_CUDA(cudaMallocHost((void**)&ctx->deriveErrorHost, sizeof(int)));
+    GB_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    for (gb_context::SceneSlot& sl : ctx->slots) {
+        GB_CUDA(cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&sl.lastUse, cudaEventDisableTiming));
+        GB_CUDA(cudaMalloc((void**)&sl.deriveError, sizeof(int)));
+        GB_CUDA(cudaMallocHost((void**)&sl.deriveErrorHost, sizeof(int)));
+        *sl.deriveErrorHost = 0;
+    }
     *out = ctx;
     return GB_OK;
 }
+
+int gb_comm_destroy(gb_context* ctx);
 
 int gb_destroy(gb_context* ctx) {
     if (!ctx) return GB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    gb_comm_destroy(ctx);
+    cudaStreamSynchronize(ctx->copyStream);
     freeScene(ctx);
     freeWave(ctx);
     cudaFree(ctx->ctr);
     cudaFree(ctx->traceHead);
     cudaFree(ctx->stats);
-    cudaFree(ctx->deriveError);
-    cudaFreeHost(ctx->deriveErrorHost);
+    cudaStreamSynchronize(ctx->copyStream);
+    for (gb_context::SceneSlot& sl : ctx->slots) {
+        cudaFree(sl.deriveError);
+        cudaFreeHost(sl.deriveErrorHost);
+        cudaEventDestroy(sl.uploaded);
+        cudaEventDestroy(sl.lastUse);
+    }
+    cudaStreamDestroy(ctx->copyStream);
     if (ctx->filmHost) cudaFreeHost(ctx->filmHost);
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
@@ -1286,10 +1322,11 @@ __global__ void k_derive_tris(const unsigned int* __restrict__ order, const unsi
     const float p0x = __ldg(p0), p0y = __ldg(p0 + 1), p0z = __ldg(p0 + 2);
     const float e1x = __ldg(p1) - p0x, e1y = __ldg(p1 + 1) - p0y, e1z = __ldg(p1 + 2) - p0z;
     const float e2x = __ldg(p2) - p0x, e2y = __ldg(p2 + 1) - p0y, e2z = __ldg(p2 + 2) - p0z;
-    float4* r = triRec + 3 * (size_t)k;
+    float4* r = triRec + kTriRecVec4 * (size_t)k;
     r[0] = make_float4(p0x, p0y, p0z, e1x);
     r[1] = make_float4(e1y, e1z, e2x, e2y);
     r[2] = make_float4(e2z, __uint_as_float(face), 0.0f, 0.0f);
+    if (kTriRecVec4 == 4) r[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const float* n0 = nrm + 3 * (size_t)v0;
     const float* n1 = nrm + 3 * (size_t)v1;
     const float* n2 = nrm + 3 * (size_t)v2;
@@ -1316,11 +1353,37 @@ struct Arena { // offsets into the staging / device arena, 256-byte aligned
 
 } // namespace
 
-extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
+namespace {
+
+// An asynchronous upload reports a bad index found by its derive kernels at the next call that waits for the device.
+int checkDeferredUpload(gb_context* ctx) {
+    for (gb_context::SceneSlot& sl : ctx->slots) {
+        if (!sl.checkPending || cudaEventQuery(sl.uploaded) != cudaSuccess) continue;
+        sl.checkPending = false;
+        const int code = *sl.deriveErrorHost;
+        if (code != 0) {
+            ctx->haveScene = false;
+            return gb::failWith(GB_ERR_INVALID, code == 1 ? "model_order entry out of range (asynchronous upload)"
+                                                          : "vertex index out of range (asynchronous upload)");
+        }
+    }
+    return GB_OK;
+}
+
+} // namespace
+
+// async = false: gb_upload_scene (waits for the device before and after, clears the film, one slot).
+// async = true:  gb_upload_scene_async (include/goblin_b200.h): the idle slot, the copy stream, no wait.
+static int uploadScene(gb_context* ctx, const gb_scene_desc* d, bool async) {
     if (!ctx || !d) return gb::failWith(GB_ERR_INVALID, "null argument");
     GB_CUDA(cudaSetDevice(ctx->device));
-    GB_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->haveScene = false;
+    if (!async) {
+        GB_CUDA(cudaStreamSynchronize(ctx->stream));
+        GB_CUDA(cudaStreamSynchronize(ctx->copyStream));
+        ctx->haveScene = false;
+    }
+    const int k = async && ctx->haveScene ? 1 - ctx->slot : ctx->slot; // the slot this upload fills
+    gb_context::SceneSlot& slot = ctx->slots[k];
     const uint32_t nInst = d->n_instances;
     const gb_film_desc& f = d->film;
     if (f.xres <= 0 || f.yres <= 0) return gb::failWith(GB_ERR_INVALID, "bad film resolution");
@@ -1375,9 +1438,9 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     if (traceSmemFor(pairEntries) > kMaxTraceSmem) return gb::failWith(GB_ERR_LIMIT, "BVH too deep for the shared-memory stack");
     size_t maxWideSmem = kMaxWideSmem;
     if (const char* e = std::getenv("GB_MAX_WIDE_SMEM")) maxWideSmem = (size_t)std::strtoull(e, nullptr, 10); // tests: force the fallback
-    ctx->wideFits = traceSmemFor(wideEntries) <= maxWideSmem;
-    ctx->stackEntries = ctx->wideFits ? wideEntries : pairEntries;
-    ctx->gridCache.clear();
+    const bool wideFits = traceSmemFor(wideEntries) <= maxWideSmem;
+    const int stackEntries = wideFits ? wideEntries : pairEntries;
+    const int stackEntriesPair = pairEntries;
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         if (d->materials[m].type < 0 || d->materials[m].type >= GB_MAT_COUNT) return gb::failWith(GB_ERR_INVALID, "unsupported material type");
     }
@@ -1445,29 +1508,33 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     const size_t oModelPairs = ar.take(64 * (size_t)nModelPairs);
     const size_t oTopWide = ar.take(128 * (size_t)nTopWide);
     const size_t oModelWide = ar.take(128 * (size_t)nModelWide);
-    const size_t oTriRec = ar.take(48 * (size_t)d->n_tris);
+    const size_t oTriRec = ar.take(16 * (size_t)kTriRecVec4 * (size_t)d->n_tris);
     const size_t oTriShade = ar.take(64 * (size_t)d->n_tris);
-    if (ar.size > ctx->arenaCap) { // both arenas persist and only grow
-        if (ctx->arenaDev) cudaFree(ctx->arenaDev);
-        ctx->arenaDev = nullptr; ctx->arenaCap = 0;
-        GB_CUDA(cudaMalloc((void**)&ctx->arenaDev, ar.size));
-        ctx->arenaCap = ar.size;
+    // the staging buffer of this slot is free once its previous copy has left it; its device arena once the kernels
+    // that read it have finished (two uploads ago in a pipeline: both long done)
+    GB_CUDA(cudaEventSynchronize(slot.uploaded));
+    if (ar.size > slot.devCap) { // both arenas persist and only grow
+        GB_CUDA(cudaEventSynchronize(slot.lastUse));
+        if (slot.dev) cudaFree(slot.dev);
+        slot.dev = nullptr; slot.devCap = 0;
+        GB_CUDA(cudaMalloc((void**)&slot.dev, ar.size));
+        slot.devCap = ar.size;
     }
-    if (uploadSize > ctx->hostCap) {
-        if (ctx->arenaHost) { if (ctx->arenaPinned) cudaFreeHost(ctx->arenaHost); else std::free(ctx->arenaHost); }
-        ctx->arenaHost = nullptr; ctx->hostCap = 0;
+    if (uploadSize > slot.hostCap) {
+        if (slot.host) { if (slot.pinned) cudaFreeHost(slot.host); else std::free(slot.host); }
+        slot.host = nullptr; slot.hostCap = 0;
         void* hp = nullptr;
-        if (cudaMallocHost(&hp, uploadSize) == cudaSuccess) { ctx->arenaPinned = true; }
+        if (cudaMallocHost(&hp, uploadSize) == cudaSuccess) { slot.pinned = true; }
         else {
             cudaGetLastError();
             hp = std::malloc(uploadSize);
-            ctx->arenaPinned = false;
+            slot.pinned = false;
             if (!hp) return gb::failWith(GB_ERR_INVALID, "out of host memory for the staging arena");
         }
-        ctx->arenaHost = static_cast<char*>(hp);
-        ctx->hostCap = uploadSize;
+        slot.host = static_cast<char*>(hp);
+        slot.hostCap = uploadSize;
     }
-    char* H = ctx->arenaHost;
+    char* H = slot.host;
     lap("layout");
     // ---- fill the staging arena
     std::memcpy(H + oTopNodes, d->top_nodes, 32 * (size_t)d->n_top_nodes);
@@ -1646,18 +1713,21 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     }
     lap("fill");
     // ---- one host-to-device copy
-    GB_CUDA(cudaMemcpyAsync(ctx->arenaDev, H, uploadSize, cudaMemcpyHostToDevice, ctx->stream));
+    // on the copy stream, behind the last kernel that read this slot's device arena
+    cudaStream_t cs = ctx->copyStream;
+    GB_CUDA(cudaStreamWaitEvent(cs, slot.lastUse, 0));
+    GB_CUDA(cudaMemcpyAsync(slot.dev, H, uploadSize, cudaMemcpyHostToDevice, cs));
     ctx->uploadBytes = uploadSize;
-    char* D = ctx->arenaDev;
+    char* D = slot.dev;
     // ---- derive the traversal / shading records on the device, at HBM speed instead of PCIe speed
-    GB_CUDA(cudaMemsetAsync(ctx->deriveError, 0, sizeof(int), ctx->stream));
+    GB_CUDA(cudaMemsetAsync(slot.deriveError, 0, sizeof(int), cs));
     if (nTopPairs) {
-        k_derive_pairs<<<(d->n_top_nodes + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(D + oTopNodes),
+        k_derive_pairs<<<(d->n_top_nodes + 255) / 256, 256, 0, cs>>>(reinterpret_cast<const float4*>(D + oTopNodes),
             reinterpret_cast<const unsigned int*>(D + oRawTopPairIdx), d->n_top_nodes, reinterpret_cast<float4*>(D + oTopPairs));
         ctx->launches++;
     }
     if (nTopWide) {
-        k_derive_wide<<<(d->n_top_nodes + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const gb_bvh_node*>(D + oTopNodes),
+        k_derive_wide<<<(d->n_top_nodes + 255) / 256, 256, 0, cs>>>(reinterpret_cast<const gb_bvh_node*>(D + oTopNodes),
             reinterpret_cast<const unsigned int*>(D + oRawTopWideIdx), d->n_top_nodes, reinterpret_cast<float4*>(D + oTopWide));
         ctx->launches++;
     }
@@ -1665,32 +1735,33 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
         const gb_model& md = d->models[m];
         if (md.kind != GB_GEOM_MESH) continue;
         if (modelPairCount[m]) {
-            k_derive_pairs<<<(md.node_count + 255) / 256, 256, 0, ctx->stream>>>(
+            k_derive_pairs<<<(md.node_count + 255) / 256, 256, 0, cs>>>(
                 reinterpret_cast<const float4*>(D + oModelNodes) + 2 * (size_t)md.node_offset,
                 reinterpret_cast<const unsigned int*>(D + oRawModelPairIdx) + md.node_offset, md.node_count,
                 reinterpret_cast<float4*>(D + oModelPairs) + 4 * (size_t)modelPairBase[m]);
             ctx->launches++;
         }
         if (modelWideCount[m]) {
-            k_derive_wide<<<(md.node_count + 255) / 256, 256, 0, ctx->stream>>>(
+            k_derive_wide<<<(md.node_count + 255) / 256, 256, 0, cs>>>(
                 reinterpret_cast<const gb_bvh_node*>(D + oModelNodes) + md.node_offset,
                 reinterpret_cast<const unsigned int*>(D + oRawModelWideIdx) + md.node_offset, md.node_count,
                 reinterpret_cast<float4*>(D + oModelWide) + 8 * (size_t)modelWideBase[m]);
             ctx->launches++;
         }
         if (md.tri_count) {
-            k_derive_tris<<<(md.tri_count + 255) / 256, 256, 0, ctx->stream>>>(
+            k_derive_tris<<<(md.tri_count + 255) / 256, 256, 0, cs>>>(
                 reinterpret_cast<const unsigned int*>(D + oRawOrder) + md.tri_offset,
                 reinterpret_cast<const unsigned int*>(D + oRawTriIndex) + 3 * (size_t)md.tri_offset,
                 reinterpret_cast<const float*>(D + oRawPos) + 3 * (size_t)md.vert_offset,
                 reinterpret_cast<const float*>(D + oRawNrm) + 3 * (size_t)md.vert_offset,
                 reinterpret_cast<const float*>(D + oRawUv) + 2 * (size_t)md.vert_offset, md.tri_count, md.vert_count,
-                reinterpret_cast<float4*>(D + oTriRec) + 3 * (size_t)md.tri_offset,
-                reinterpret_cast<float4*>(D + oTriShade) + 4 * (size_t)md.tri_offset, ctx->deriveError);
+                reinterpret_cast<float4*>(D + oTriRec) + kTriRecVec4 * (size_t)md.tri_offset,
+                reinterpret_cast<float4*>(D + oTriShade) + 4 * (size_t)md.tri_offset, slot.deriveError);
             ctx->launches++;
         }
     }
-    GB_CUDA(cudaMemcpyAsync(ctx->deriveErrorHost, ctx->deriveError, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaMemcpyAsync(slot.deriveErrorHost, slot.deriveError, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    GB_CUDA(cudaEventRecord(slot.uploaded, cs));
     DeviceScene sc{};
     sc.tune = ctx->tune;
     sc.topNodes = reinterpret_cast<const float4*>(D + oTopNodes);
@@ -1737,42 +1808,67 @@ extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) {
     sc.filterWidthX = f.filter_width[0];
     sc.filterWidthY = f.filter_width[1];
     const size_t filmPixels = (size_t)f.xres * f.yres;
+    bool newFilm = false;
     if (filmPixels != ctx->filmPixels || !ctx->film) {
+        GB_CUDA(cudaStreamSynchronize(ctx->stream)); // kernels may still add to the old film
         if (ctx->film) cudaFree(ctx->film);
         ctx->film = nullptr;
+        ctx->filmPixels = 0;
         GB_CUDA(cudaMalloc((void**)&ctx->film, filmPixels * sizeof(float4)));
         ctx->filmPixels = filmPixels;
+        newFilm = true;
     }
+    if (!async) {
+        GB_CUDA(cudaStreamSynchronize(cs)); // the staging arena may be refilled after this
+        if (*slot.deriveErrorHost == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
+        if (*slot.deriveErrorHost == 2) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
+        slot.checkPending = false;
+    } else {
+        // what is queued on the context's stream so far read the current slot: the NEXT upload into it waits for this
+        // marker; what is queued from now on reads the new slot, once its copy and derive kernels are through
+        GB_CUDA(cudaEventRecord(ctx->slots[ctx->slot].lastUse, ctx->stream));
+        GB_CUDA(cudaStreamWaitEvent(ctx->stream, slot.uploaded, 0));
+        slot.checkPending = true;
+    }
+    // the synchronous call hands back an empty film (as it always did); the asynchronous one leaves the film alone:
+    // in a pipeline the previous frame is still waiting there to be downloaded
+    if (!async || newFilm) GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
     ctx->filmDesc = d->film;
-    GB_CUDA(cudaMemsetAsync(ctx->film, 0, ctx->filmPixels * sizeof(float4), ctx->stream));
-    GB_CUDA(cudaStreamSynchronize(ctx->stream)); // the staging arena may be refilled after this
-    if (*ctx->deriveErrorHost == 1) return gb::failWith(GB_ERR_INVALID, "model_order entry out of range");
-    if (*ctx->deriveErrorHost == 2) return gb::failWith(GB_ERR_INVALID, "vertex index out of range");
+    ctx->slot = k;
     ctx->sc = sc;
     ctx->setting = d->setting;
     ctx->hasBlinn = hasBlinn;
     ctx->hasMeshLight = hasMeshLight;
+    ctx->wideFits = wideFits;
+    ctx->stackEntries = stackEntries;
+    ctx->stackEntriesPair = stackEntriesPair;
+    ctx->gridCache.clear();
     lap("copy+sync");
     ctx->haveScene = true; // every check has passed
     return GB_OK;
 }
 
+extern "C" int gb_upload_scene(gb_context* ctx, const gb_scene_desc* d) { return uploadScene(ctx, d, false); }
+
+extern "C" int gb_upload_scene_async(gb_context* ctx, const gb_scene_desc* d) { return uploadScene(ctx, d, true); }
+
 extern "C" {
 
 static int launchTrace(gb_context* ctx, bool any, const gb_ray* d_rays, size_t n, gb_hit* d_hits, unsigned char* d_occ) {
     if (!ctx->haveScene) return gb::failWith(GB_ERR_STATE, "no scene uploaded");
-    size_t smem = traceSmem(ctx);
+    const int mode = walkMode(ctx);
+    const size_t smem = traceSmem(ctx, mode);
+    const int stackEntries = stackEntriesOf(ctx, mode);
     int grid = 0, rc;
     GB_CUDA(cudaMemsetAsync(ctx->traceHead, 0, 8, ctx->stream));
     GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
 #define LAUNCH(ANYV, MODEV)                                                                        \
     do {                                                                                           \
-        if ((rc = setupTraceKernel(ctx, k_trace<ANYV, MODEV>, &grid)) != GB_OK) return rc;          \
+        if ((rc = setupTraceKernel(ctx, k_trace<ANYV, MODEV>, MODEV, &grid)) != GB_OK) return rc;   \
         KernelTick tick(ctx, GB_K_TRACE);                                                           \
         k_trace<ANYV, MODEV><<<grid, kTraceBlock, smem, ctx->stream>>>(ctx->sc, d_rays, (unsigned long long)n, d_hits, \
-            d_occ, ctx->traceHead, ctx->stats, ctx->stackEntries);                                  \
+            d_occ, ctx->traceHead, ctx->stats, stackEntries);                                       \
     } while (0)
-    const int mode = walkMode(ctx);
     if (any) {
         if (mode == WALK_WIDE) LAUNCH(true, WALK_WIDE); else if (mode == WALK_PAIR) LAUNCH(true, WALK_PAIR); else LAUNCH(true, WALK_STATS);
     } else {
@@ -1871,7 +1967,9 @@ int gb_camera_rays(gb_context* ctx, const float* samples, size_t n, gb_ray* rays
 static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& src, int method, bool toFilm) {
     PathState& ps = ctx->ps;
     cudaStream_t st = ctx->stream;
-    const size_t smem = traceSmem(ctx);
+    const int mode = walkMode(ctx);
+    const size_t smem = traceSmem(ctx, mode);
+    const int stackEntries = stackEntriesOf(ctx, mode);
     const unsigned int n = wp.nPaths;
     int rc, grid = 0;
     GB_CUDA(cudaMemsetAsync(ctx->ctr, 0, kMaxDepthCtr * kCtrStride * sizeof(unsigned int), st));
@@ -1883,15 +1981,14 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     }
     ctx->launches++;
     const int shadeGrid = ctx->numSMs * 8;
-    const int mode = walkMode(ctx);
     auto extend = [&](int b, int singleBin) -> int {
         unsigned int* c = ctx->ctr + b * kCtrStride;
         const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
         KernelTick tick(ctx, GB_K_EXTEND);
 #define GB_EXTEND(MODEV)                                                                                            \
     do {                                                                                                            \
-        if ((rc = setupTraceKernel(ctx, k_extend<MODEV>, &grid)) != GB_OK) return rc;                                \
-        k_extend<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, ctx->stackEntries); \
+        if ((rc = setupTraceKernel(ctx, k_extend<MODEV>, MODEV, &grid)) != GB_OK) return rc;                         \
+        k_extend<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, stackEntries);    \
     } while (0)
         if (mode == WALK_WIDE) GB_EXTEND(WALK_WIDE); else if (mode == WALK_PAIR) GB_EXTEND(WALK_PAIR); else GB_EXTEND(WALK_STATS);
 #undef GB_EXTEND
@@ -1910,8 +2007,8 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             KernelTick tick(ctx, GB_K_AO);
 #define GB_AO(MODEV)                                                                                                  \
     do {                                                                                                              \
-        if ((rc = setupTraceKernel(ctx, k_ao<MODEV>, &grid)) != GB_OK) return rc;                                      \
-        k_ao<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, ctx->stackEntries);    \
+        if ((rc = setupTraceKernel(ctx, k_ao<MODEV>, MODEV, &grid)) != GB_OK) return rc;                               \
+        k_ao<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, stackEntries);         \
     } while (0)
             if (mode == WALK_WIDE) GB_AO(WALK_WIDE); else if (mode == WALK_PAIR) GB_AO(WALK_PAIR); else GB_AO(WALK_STATS);
 #undef GB_AO
@@ -1993,8 +2090,8 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
                     KernelTick tick(ctx, GB_K_SHADOW, ss);
 #define GB_SHADOW(MODEV)                                                                                      \
     do {                                                                                                      \
-        if ((rc = setupTraceKernel(ctx, k_shadow<MODEV>, &grid)) != GB_OK) return rc;                          \
-        k_shadow<MODEV><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, ctx->stackEntries);        \
+        if ((rc = setupTraceKernel(ctx, k_shadow<MODEV>, MODEV, &grid)) != GB_OK) return rc;                   \
+        k_shadow<MODEV><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, stackEntries);             \
     } while (0)
                     if (mode == WALK_WIDE) GB_SHADOW(WALK_WIDE); else if (mode == WALK_PAIR) GB_SHADOW(WALK_PAIR); else GB_SHADOW(WALK_STATS);
 #undef GB_SHADOW
@@ -2159,7 +2256,7 @@ int gb_film_download(gb_context* ctx, float* rgbw) {
     GB_CUDA(cudaMemcpyAsync(dst, ctx->film, ctx->filmPixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (dst != rgbw) std::memcpy(rgbw, dst, ctx->filmPixels * sizeof(float4));
-    return GB_OK;
+    return checkDeferredUpload(ctx);
 }
 
 int gb_film_upload(gb_context* ctx, const float* rgbw) {
@@ -2232,7 +2329,7 @@ int gb_synchronize(gb_context* ctx) {
     if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
     GB_CUDA(cudaSetDevice(ctx->device));
     GB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return GB_OK;
+    return checkDeferredUpload(ctx);
 }
 
 int gb_stream(gb_context* ctx, void** cuda_stream) {
@@ -2354,3 +2451,5 @@ int gb_last_kernel_ms(gb_context* ctx, float* ms) {
 }
 
 } // extern "C"
+
+#include "film_comm.inl"

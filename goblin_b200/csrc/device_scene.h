@@ -25,6 +25,17 @@ namespace gb {
 
 constexpr int kMaxLights = 1 << 20;
 
+// Traversal records are fetched with 256-bit loads (LDG.E.256, sm_100+): a lane's gather of one 32-byte sector
+// is then ONE pass through the L1 data pipe instead of two 128-bit ones.  The traversal kernels are bound by
+// exactly that pipe (ncu: l1tex__data_pipe_lsu_wavefronts at 72 - 79 % of peak on incoherent rays with 128-bit
+// loads: every lane of a warp reads a different line, so every lane is a wavefront of its own).  Triangle
+// records are padded from 48 to 64 bytes so that both halves are 32-byte aligned.  GB_LD256=0 restores the
+// 128-bit loads and the 48-byte records (A/B builds).
+#ifndef GB_LD256
+#define GB_LD256 1
+#endif
+constexpr int kTriRecVec4 = GB_LD256 ? 4 : 3; // float4 per triangle test record
+
 struct DeviceLight { // 128 bytes
     float4 colorType;   // rgb, __int_as_float(type)
     float4 posRadius;   // position xyz, radius
@@ -58,7 +69,7 @@ struct DeviceScene {
     const float4* modelNodes;   // 2 per node, all models concatenated
     const float4* modelPairs;   // 4 per interior node, all models concatenated
     const float4* modelWide;    // 8 per wide root, all models concatenated
-    const float4* triRec;       // 3 per triangle slot (BVH leaf order, all models concatenated)
+    const float4* triRec;       // kTriRecVec4 per triangle slot (BVH leaf order, all models concatenated)
     // ---- shading data
     const float4* instToWorld;  // 3 per instance slot
     const int4* instShade;      // per slot: original instance index, model index, material, area light (-1)

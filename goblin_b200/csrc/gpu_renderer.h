@@ -10,6 +10,7 @@
 // (src/GoblinRenderContext.h:19-22, src/GoblinRenderer.h:55-57,
 //  src/GoblinFilm.cpp:131-138,164-192)
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -53,15 +54,16 @@ public:
     void getSampleRange(SampleRange& r) const {
         r.xStart = mDesc.sx0; r.xEnd = mDesc.sx1; r.yStart = mDesc.sy0; r.yEnd = mDesc.sy1;
     }
+    void clear() { std::fill(mPixels.begin(), mPixels.end(), 0.0f); }
     // Film::mergeTile: add another (r, g, b, weight) buffer into the film
     void merge(const std::vector<float>& rgbw) {
         for (size_t i = 0; i < mPixels.size(); ++i) mPixels[i] += rgbw[i];
     }
     // Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, bloom, then the writer
     // (tone mapping for .ppm).  The resolve and the bloom run on `ctx`'s GPU over the merged film.
+    // The device film of `ctx` already holds the merged frame (it is where mPixels was downloaded from).
     void writeImage(gb_context* ctx) {
         std::printf("write image to : %s\n", mFilename.c_str());
-        checkRc(gb_film_upload(ctx, mPixels.data()), "gb_film_upload");
         checkRc(gb_film_write(ctx, mFilename.c_str()), "writeImage");
     }
     const std::vector<float>& pixels() const { return mPixels; }
@@ -97,6 +99,8 @@ public:
             mContexts.push_back(c);
             checkRc(gb_upload_scene(c, &scene->desc()), "gb_upload_scene");
         }
+        // Film::mergeTile across GPUs is an NCCL all-reduce of the device films (src/GoblinFilm.cpp:140-153)
+        if (mGpuNum > 1) checkRc(gb_comm_init_all(mContexts.data(), mGpuNum), "gb_comm_init_all");
     }
 
     void render(const ScenePtr& scene, Film* film) {
@@ -105,11 +109,14 @@ public:
         if (root < 1) root = 1;
         const int sppTotal = root * root;
         const int G = (int)mContexts.size();
+        // a second RenderContext::render() starts from an empty film, on the devices and on the host
+        film->clear();
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> workers;
         std::vector<std::string> errors(G);
         for (int g = 0; g < G; ++g) {
             workers.emplace_back([&, g]() {
+                if (gb_film_clear(mContexts[g]) != GB_OK) { errors[g] = gb_last_error(); return; }
                 gb_render_params p{};
                 p.seed = mSeed;
                 p.spp_total = sppTotal;
@@ -118,18 +125,25 @@ public:
                 p.max_ray_depth = 0;
                 p.method = -1;
                 p.ao_sample_num = 0;
-                if (gb_render(mContexts[g], &p) != GB_OK || gb_synchronize(mContexts[g]) != GB_OK) {
+                // with several GPUs the render stays queued: the all-reduce below goes behind it on the same stream
+                if (gb_render(mContexts[g], &p) != GB_OK || (G == 1 && gb_synchronize(mContexts[g]) != GB_OK)) {
                     errors[g] = gb_last_error();
                 }
             });
         }
         for (auto& w : workers) w.join();
         for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error("gb_render: " + e);
+        // Film::mergeTile: the G device films are summed over NVLink; every GPU then holds the frame, GPU 0's is
+        // the one that is normalised and written
+        if (G > 1) {
+            checkRc(gb_film_allreduce_all(mContexts.data(), G), "gb_film_allreduce_all");
+            for (int g = 0; g < G; ++g) checkRc(gb_synchronize(mContexts[g]), "gb_synchronize");
+        }
         mStats.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::vector<float> tmp(film->pixels().size());
+        checkRc(gb_film_download(mContexts[0], tmp.data()), "gb_film_download");
+        film->merge(tmp);
         for (int g = 0; g < G; ++g) {
-            checkRc(gb_film_download(mContexts[g], tmp.data()), "gb_film_download");
-            film->merge(tmp);
             gb_counters c{};
             gb_get_counters(mContexts[g], &c);
             mStats.cameraSamples += c.camera_samples;

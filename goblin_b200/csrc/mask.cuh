@@ -84,7 +84,7 @@ __device__ __noinline__ bool simpleClosest(const DeviceScene& sc, float3 o, floa
             const int4 info2 = __ldg(sc.instInfo2 + slot);
             simpleWalk(sc.modelNodes + 2 * (size_t)(unsigned int)info.y, (unsigned int)info2.z, oo, od, mint, maxt,
                 [&](unsigned int ts) {
-                    const float4* tr = sc.triRec + 3 * ((size_t)(unsigned int)info.z + ts);
+                    const float4* tr = sc.triRec + kTriRecVec4 * ((size_t)(unsigned int)info.z + ts);
                     const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
                     float t, b1, b2;
                     if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), oo, od, mint, maxt, &t,
@@ -121,7 +121,7 @@ __device__ __noinline__ bool simpleAny(const DeviceScene& sc, float3 o, float3 d
             const int4 info2 = __ldg(sc.instInfo2 + slot);
             return simpleWalk(sc.modelNodes + 2 * (size_t)(unsigned int)info.y, (unsigned int)info2.z, oo, od, mint, maxt,
                 [&](unsigned int ts) {
-                    const float4* tr = sc.triRec + 3 * ((size_t)(unsigned int)info.z + ts);
+                    const float4* tr = sc.triRec + kTriRecVec4 * ((size_t)(unsigned int)info.z + ts);
                     const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
                     float t, b1, b2;
                     return triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), oo, od, mint, maxt, &t,

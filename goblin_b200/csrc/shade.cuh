@@ -207,7 +207,7 @@ __device__ __forceinline__ Frag buildFragment(const DeviceScene& sc, const HitRe
     float3 pObj = oo + hit.t * od; // ray(t) in object space
     float3 nObj, dpduObj;
     if (info.x == GB_GEOM_MESH) {
-        const float4* tr = sc.triRec + 3 * (size_t)(info.z + hit.prim);
+        const float4* tr = sc.triRec + kTriRecVec4 * (size_t)(info.z + hit.prim);
         float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
         float3 e1 = make3(a.w, b.x, b.y), e2 = make3(b.z, b.w, c.x);
         int4 ms = __ldg(sc.modelShade + sh.y);

@@ -39,7 +39,7 @@ __device__ __noinline__ void texFragment(const DeviceScene& sc, const HitRec& hi
     const float3 pObj = oo + hit.t * od;
     float3 dpdvObj;
     if (info.x == GB_GEOM_MESH) {
-        const float4* tr = sc.triRec + 3 * (size_t)(info.z + hit.prim);
+        const float4* tr = sc.triRec + kTriRecVec4 * (size_t)(info.z + hit.prim);
         const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
         const float3 e1 = make3(a.w, b.x, b.y), e2 = make3(b.z, b.w, c.x);
         const int4 ms = __ldg(sc.modelShade + sh.y);

@@ -40,6 +40,21 @@ constexpr int kStepsPerCheckPair = GB_STEPS_PAIR, kStepsPerCheckWide = GB_STEPS_
 // fewer lanes than this are busy; leafBatch / levelBatch = run the triangle / level stage once
 // this many lanes wait for it; moveFloor = ... or when fewer lanes than this can still move
 
+// One 32-byte sector as two float4: a single 256-bit read-only load where the build allows it.
+struct Sector { float4 lo, hi; };
+__device__ __forceinline__ Sector ldgSector(const float4* p) {
+    Sector r;
+#if GB_LD256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+#else
+    r.lo = __ldg(p);
+    r.hi = __ldg(p + 1);
+#endif
+    return r;
+}
+
 // Per-thread columns in shared memory: entry k of thread t lives at [k * blockDim.x + t],
 // so a warp's pushes / pops are contiguous.
 struct TravStack {
@@ -168,8 +183,13 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 }
                 cur = REF_POP;
                 for (unsigned int k = 0; k < count; ++k) {
-                    const float4* tr = sc.triRec + 3 * ((size_t)triBase + first + k);
+                    const float4* tr = sc.triRec + kTriRecVec4 * ((size_t)triBase + first + k);
+#if GB_LD256
+                    const Sector ab = ldgSector(tr);
+                    const float4 a = ab.lo, b = ab.hi, c = __ldg(tr + 2);
+#else
                     const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
+#endif
                     if (STATS) ts.prims++;
                     float t, b1, b2;
                     if (triangleTest(make3(a.x, a.y, a.z), make3(a.w, b.x, b.y), make3(b.z, b.w, c.x), o, d, mint,
@@ -283,8 +303,8 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 if (WIDE) {
                     if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: four box tests (wide_node.h)
                         const float4* p = pairs + 8 * (size_t)cur;
-                        const float4 a0 = __ldg(p), a1 = __ldg(p + 1), b0 = __ldg(p + 2), b1 = __ldg(p + 3);
-                        const float4 c0 = __ldg(p + 4), c1 = __ldg(p + 5), d0 = __ldg(p + 6), d1 = __ldg(p + 7);
+                        const Sector sa = ldgSector(p), sb = ldgSector(p + 2), sc4 = ldgSector(p + 4), sd = ldgSector(p + 6);
+                        const float4 a0 = sa.lo, a1 = sa.hi, b0 = sb.lo, b1 = sb.hi, c0 = sc4.lo, c1 = sc4.hi, d0 = sd.lo, d1 = sd.hi;
                         const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
                         float t0, t1, t2, t3;
 #define GB_WIDE_BOX(n0, n1, tt)                                                                                   \
@@ -307,8 +327,9 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     }
                 } else if (have && !fin && !(cur & REF_LEAF)) { // ---- interior stage: two box tests
                     const float4* p = pairs + 4 * (size_t)cur;
-                    const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-                    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
+                    const Sector s01 = ldgSector(p), s23 = ldgSector(p + 2);
+                    const float4 q0 = s01.lo, q1 = s01.hi, q2 = s23.lo;
+                    const uint4 q3 = make_uint4(__float_as_uint(s23.hi.x), __float_as_uint(s23.hi.y), __float_as_uint(s23.hi.z), __float_as_uint(s23.hi.w));
                     const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
                     float tL, tR;
                     const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,

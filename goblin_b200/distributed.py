@@ -3,10 +3,13 @@
 The reference has one collective-like step, Film::mergeTile (src/GoblinFilm.cpp:
 140-153): every worker thread's full-frame (colour, weight) tile is summed into
 the film under a mutex.  Across GPUs that is an all-reduce(sum) of the 4 W H
-float film buffer, done here with torch.distributed (NCCL over NVLink on the
-GPU box; any backend for host tensors in the CPU tests).  Geometry is never
-partitioned: every rank holds a full scene replica and camera samples are
-independent, so the film sum is the only data-path exchange.
+float film buffer.  The library does it itself (gb_film_allreduce: NCCL on the
+context's stream, include/goblin_b200.h); torch.distributed is only the launcher's
+channel that carries the 128-byte communicator id from rank 0 to the other ranks
+(init_film_comm), and the stand-in collective of the CPU (gloo) tests, where
+there is no device film.  Geometry is never partitioned: every rank holds a full
+scene replica and camera samples are independent, so the film sum is the only
+data-path exchange.
 """
 import numpy as np
 
@@ -32,6 +35,24 @@ class DeviceFilm:
         return torch.as_tensor(self, device=device)
 
 
+def init_film_comm(ctx, rank, world, group=None):
+    """Create the library's own NCCL communicator for `ctx` (gb_comm_init_rank).  The id is made on rank 0
+    and broadcast over the already initialised torch.distributed group (any backend)."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    if world < 2:
+        return
+    if dist.get_backend(group) == "nccl":
+        t = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device=torch.device("cuda", ctx.device))
+    else:
+        t = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    ctx.comm_init_rank(bytes(t.cpu().numpy().tobytes()), world, rank)
+
+
 def allreduce_film(film, group=None):
     """Sum the (r, g, b, weight) film over all ranks, in place.  `film` is a torch tensor (the
     device film on the GPU path, a host tensor in the gloo tests)."""
@@ -43,13 +64,19 @@ def allreduce_film(film, group=None):
 
 def render_sharded(ctx, scene, seed, rank, world, spp=None, **render_kw):
     """Render this rank's share of the samples into the context's device film and all-reduce it.
-    Asynchronous on the context's own stream, on the context's own device: the NCCL all-reduce is
-    issued on a torch ExternalStream wrapping that stream, so it is ordered after the render kernels
-    whatever torch's current device / stream are."""
+    Asynchronous on the context's own stream, on the context's own device.  With a library communicator
+    (init_film_comm) the all-reduce is gb_film_allreduce; otherwise torch.distributed does it on a torch
+    ExternalStream wrapping the context's stream, so that it is ordered after the render kernels whatever
+    torch's current device / stream are."""
     import torch
     spp_total = scene.spp_squared(spp)
     begin, end = spp_shard(spp_total, rank, world)
     device = torch.device("cuda", ctx.device)
+    if ctx.comm_size() == world and world > 1:
+        ctx.film_clear()
+        ctx.render(seed=seed, spp_total=spp_total, spp_begin=begin, spp_end=end, **render_kw)
+        ctx.film_allreduce()
+        return DeviceFilm(ctx).tensor(device)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
     with torch.cuda.device(device), torch.cuda.stream(stream):
         ctx.film_clear()

@@ -356,6 +356,15 @@ int gb_device_count(int* count);
 int gb_create(int device, gb_context** out);
 int gb_destroy(gb_context* ctx);
 int gb_upload_scene(gb_context* ctx, const gb_scene_desc* desc);
+/* The same without waiting for the device, for callers that stream scenes (an animation, one upload per frame):
+ * the scene is staged into a SECOND pinned buffer / device arena and copied on the library's copy stream while the
+ * kernels already queued on the context's stream keep reading the current scene; everything queued after the call
+ * uses the new scene (the context's stream waits for the copy on the device, not the host).  The caller's arrays
+ * may be freed when the call returns, as with gb_upload_scene.  Differences: the film is NOT cleared (the previous
+ * frame may still be waiting to be downloaded; call gb_film_clear), unless its resolution changes; a bad vertex /
+ * order index in the mesh arrays, which only the device-side derivation sees, is reported by the next
+ * gb_synchronize / gb_film_download instead of by this call. */
+int gb_upload_scene_async(gb_context* ctx, const gb_scene_desc* desc);
 /* bytes the last gb_upload_scene moved host -> device (one copy of the staging arena) */
 int gb_upload_bytes(gb_context* ctx, size_t* bytes);
 
@@ -391,6 +400,24 @@ int gb_film_upload(gb_context* ctx, const float* rgbw);
  * (torch.distributed / NCCL): the analogue of Film::mergeTile
  * (src/GoblinFilm.cpp:140-153). */
 int gb_film_device_ptr(gb_context* ctx, void** ptr, size_t* n_floats);
+/* Film::mergeTile across GPUs (src/GoblinFilm.cpp:140-153: every worker's full-frame tile is summed
+ * into the film): one NCCL all-reduce(sum) of the device film over NVLink, issued by the library on the
+ * context's stream.  NCCL is bound at run time (libnccl.so.2); GB_ERR_STATE when it is not installed.
+ *   one process, one context per GPU:  gb_comm_init_all(ctxs, n), then gb_film_allreduce_all(ctxs, n)
+ *   one process per GPU:               rank 0: gb_comm_unique_id; every rank: gb_comm_init_rank, then
+ *                                      gb_film_allreduce(ctx) after each gb_render
+ *   a communicator the caller owns:    gb_comm_attach(ctx, ncclComm_t, nranks)
+ * After the all-reduce every rank's film holds the sum; rank 0 normalises and writes. */
+#define GB_COMM_ID_BYTES 128
+int gb_comm_init_all(gb_context** ctxs, int n);
+int gb_comm_unique_id(void* id, size_t bytes);
+int gb_comm_init_rank(gb_context* ctx, const void* id, size_t bytes, int nranks, int rank);
+int gb_comm_attach(gb_context* ctx, void* nccl_comm, int nranks);
+int gb_comm_destroy(gb_context* ctx);
+int gb_comm_size(gb_context* ctx, int* nranks);   /* 0 = no communicator */
+int gb_film_allreduce(gb_context* ctx);
+int gb_film_allreduce_all(gb_context** ctxs, int n);
+int gb_nccl_version(int* version);
 /* Film::writeImage (src/GoblinFilm.cpp:164-192): colour / weight, written as
  * .exr (half, like src/GoblinImageIO.cpp:35-98), .pfm or .ppm by extension. */
 int gb_film_write(gb_context* ctx, const char* path);

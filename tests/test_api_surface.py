@@ -94,3 +94,44 @@ def test_calls_out_of_order_return_status_codes(built):
     assert lib.gb_trace_closest(h, buf.ctypes.data, 1, buf.ctypes.data) == 4
     assert lib.gb_create(99, C.byref(C.c_void_p())) == 1  # GB_ERR_INVALID: no such device
     assert lib.gb_destroy(h) == 0
+
+
+def test_async_upload_pipeline_equals_synchronous_uploads(built):
+    """gb_upload_scene_async: frames of alternating scenes, each uploaded while the previous frame is still being
+    rendered and downloaded afterwards, equal the same frames rendered with synchronous uploads."""
+    tiny = api.Scene(util.TINY_PT)
+    bunny = api.Scene(util.gen_scene("bunny") + "/bunny_pt_small.json")
+    scenes = [tiny, bunny, tiny, bunny, bunny, tiny]
+    ctx = api.Context(0)
+    want = []
+    for i, sc in enumerate(scenes):
+        ctx.upload_scene(sc)
+        ctx.render(seed=40 + i, spp_total=4)
+        want.append(ctx.film_download().copy())
+    got = []
+    ctx.upload_scene_async(scenes[0])
+    for i, sc in enumerate(scenes):
+        ctx.film_clear()
+        ctx.render(seed=40 + i, spp_total=4)
+        film_scene = ctx.scene
+        if i + 1 < len(scenes) and scenes[i + 1].desc.film.xres == sc.desc.film.xres and scenes[i + 1].desc.film.yres == sc.desc.film.yres:
+            ctx.upload_scene_async(scenes[i + 1])  # overlaps the render just queued; the film is left alone
+            ctx.scene = film_scene
+            got.append(ctx.film_download().copy())
+            ctx.scene = scenes[i + 1]
+        else:
+            got.append(ctx.film_download().copy())
+            if i + 1 < len(scenes):
+                ctx.upload_scene_async(scenes[i + 1])  # a different film size: reallocated (and cleared) by the call
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-4, atol=1e-5)
+    # same scene re-uploaded many times in a row while rendering: both slots keep alternating
+    ctx.upload_scene(bunny)
+    ctx.render(seed=7, spp_total=4)
+    ref = ctx.film_download().copy()
+    for _ in range(6):
+        ctx.film_clear()
+        ctx.render(seed=7, spp_total=4)
+        ctx.upload_scene_async(bunny)
+        assert np.allclose(ctx.film_download(), ref, rtol=1e-4, atol=1e-5)
+    ctx.close()

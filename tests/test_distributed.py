@@ -91,11 +91,21 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 scene = api.Scene(util.TINY_PT)
 ctx = api.Context(rank)
 ctx.upload_scene(scene)
+# first through torch.distributed's all-reduce on the context's stream ...
 film = distributed.render_sharded(ctx, scene, seed=5, rank=rank, world=world, spp=16)
 ctx.synchronize()
 torch.cuda.synchronize()
+via_torch = film.cpu().numpy().copy()
+# ... then through the library's own NCCL communicator (gb_comm_init_rank + gb_film_allreduce)
+distributed.init_film_comm(ctx, rank, world)
+assert ctx.comm_size() == world
+film = distributed.render_sharded(ctx, scene, seed=5, rank=rank, world=world, spp=16)
+ctx.synchronize()
+via_lib = ctx.film_download().reshape(-1)
 if rank == 0:
-    np.save({out!r}, film.cpu().numpy())
+    np.save({out!r}, via_lib)
+    np.save({out!r} + ".torch.npy", via_torch)
+ctx.comm_destroy()
 dist.destroy_process_group()
 """
 
@@ -124,4 +134,45 @@ def test_nccl_world2_matches_single_gpu(built, tmp_path):
     ctx.film_clear()
     ctx.render(seed=5, spp_total=16)
     whole = ctx.film_download().reshape(-1)
-    assert np.allclose(np.load(out), whole, rtol=1e-4, atol=1e-5)
+    assert np.allclose(np.load(out), whole, rtol=1e-4, atol=1e-5)             # gb_film_allreduce
+    assert np.allclose(np.load(out + ".torch.npy"), whole, rtol=1e-4, atol=1e-5)  # torch.distributed on the same stream
+
+
+@pytest.mark.gpu
+def test_single_process_two_contexts_film_allreduce(built):
+    """g_ray --gpus N's merge: one process, one context per GPU, gb_comm_init_all + gb_film_allreduce_all
+    (Film::mergeTile, src/GoblinFilm.cpp:140-153).  Every GPU ends up holding the 1-GPU film."""
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene = api.Scene(util.TINY_PT)
+    ctxs = [api.Context(g) for g in range(2)]
+    for c in ctxs:
+        c.upload_scene(scene)
+    api.comm_init_all(ctxs)
+    assert api.nccl_version() > 20000 and all(c.comm_size() == 2 for c in ctxs)
+    for g, c in enumerate(ctxs):
+        b, e = distributed.spp_shard(16, g, 2)
+        c.film_clear()
+        c.render(seed=5, spp_total=16, spp_begin=b, spp_end=e)
+    api.film_allreduce_all(ctxs)
+    films = [c.film_download() for c in ctxs]
+    one = api.Context(0)
+    one.upload_scene(scene)
+    one.film_clear()
+    one.render(seed=5, spp_total=16)
+    whole = one.film_download()
+    for f in films:
+        assert np.allclose(f, whole, rtol=1e-4, atol=1e-5)
+    for c in ctxs:
+        c.close()
+
+
+def test_film_comm_entry_points_without_a_gpu(built):
+    """The collective entry points exist, NCCL is bound at run time, and nothing works without a device."""
+    import torch
+    v = api.nccl_version()
+    assert v > 20000
+    assert len(api.comm_unique_id()) == api.COMM_ID_BYTES
+    if not torch.cuda.is_available():
+        with pytest.raises(api.GoblinError):
+            api.Context(0)
