@@ -310,8 +310,8 @@ def main():
     ap.add_argument("--accel", default="equal_count", choices=["equal_count", "middle", "sah"],
                     help="BVH split method: equal_count = the reference's tree (the headline, parity mode); "
                          "sah = the non-parity fast tree (SURVEY 8(f) rank 1)")
-    ap.add_argument("--trace-mode", default="wide", choices=["wide", "exact"],
-                    help="wide = 4-wide nodes (default); exact = the pair-node walk (every box test of the reference)")
+    ap.add_argument("--trace-mode", default="pair", choices=["pair", "wide", "exact"],
+                    help="pair = the pair-node walk (default; 'exact' is its older name); wide = 4-wide nodes (measured slower)")
     ap.add_argument("--spp", type=int, default=0, help="override the scene's sample_per_pixel")
     ap.add_argument("--wave-paths", type=int, default=0)
     ap.add_argument("--tune", default="", help="comma list for gb_set_tuning (experiments)")
@@ -481,7 +481,7 @@ def main():
     mrays = rays_all / (total_ms * 1e-3) * 1e-6
 
     # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + film download (D2H)
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 20))
     host_film = np.zeros(1, np.float32)
     for i in range(2 if e2e_steps else 0):
         ctx.upload_scene(scene)

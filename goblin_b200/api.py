@@ -155,7 +155,7 @@ EXPORTS = [
 COMM_ID_BYTES = 128
 
 # GB_TRACE_*: how the traversal kernels walk the reference's tree
-TRACE_MODES = {"wide": 0, "exact": 1}
+TRACE_MODES = {"wide": 0, "pair": 1}
 
 KERNEL_CLASSES = ["raygen", "extend", "shade", "shadow", "ao", "film", "trace", "other"]
 
@@ -517,8 +517,9 @@ class Context:
         check(lib().gb_film_allreduce(self._h))
 
     def set_trace_mode(self, mode):
-        """"wide" (default: 4-wide nodes) or "exact" (pair nodes, every box test of the reference)."""
-        check(lib().gb_set_trace_mode(self._h, TRACE_MODES[mode]))
+        """"pair" (default: pair nodes, every box test of the reference; "exact" is its older name) or
+        "wide" (4-wide nodes)."""
+        check(lib().gb_set_trace_mode(self._h, TRACE_MODES["pair" if mode == "exact" else mode]))
 
     def trace_mode(self):
         m = C.c_int()

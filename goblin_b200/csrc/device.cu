@@ -91,7 +91,7 @@ struct WaveParams {
 };
 
 __device__ __forceinline__ unsigned long long sampleIdOf(const DeviceScene& sc, const WaveParams& wp, unsigned int i,
-    int* px, int* py, int* s) {
+    int* px, int* py, int* s, unsigned long long* pixel = nullptr) {
     unsigned int pix = i / (unsigned int)wp.nSpp;
     unsigned int k = i - pix * (unsigned int)wp.nSpp;
     unsigned int row = pix / (unsigned int)wp.width;
@@ -100,6 +100,7 @@ __device__ __forceinline__ unsigned long long sampleIdOf(const DeviceScene& sc, 
     *py = wp.y0 + (int)row;
     *s = wp.sppBegin + (int)k;
     unsigned long long pixelIndex = (unsigned long long)(*py - sc.sy0) * (unsigned long long)wp.width + col;
+    if (pixel) *pixel = pixelIndex;
     return pixelIndex * (unsigned long long)wp.sppTotal + (unsigned long long)(*s);
 }
 
@@ -184,8 +185,8 @@ struct TracePolicy {
 };
 
 // MODE of every traversal kernel: which walk of the reference's tree it runs (traverse.cuh)
-enum { WALK_WIDE = 0,   // 4-wide nodes: the default
-       WALK_PAIR = 1,   // pair nodes, box tests exactly where the reference evaluates them (GB_TRACE_EXACT)
+enum { WALK_WIDE = 0,   // 4-wide nodes (GB_TRACE_WIDE)
+       WALK_PAIR = 1,   // pair nodes, box tests exactly where the reference evaluates them: the default
        WALK_STATS = 2 };// the pair walk with the traversal counters on
 #define GB_WALK_FLAGS(MODE) constexpr bool STATS = (MODE) == WALK_STATS, WIDE = (MODE) == WALK_WIDE
 constexpr int traceMinBlocks(int mode) { return mode == WALK_WIDE ? GB_WIDE_MIN_BLOCKS : kTraceMinBlocks; }
@@ -213,8 +214,9 @@ __global__ void k_raygen(DeviceScene sc, PathState ps, WaveParams wp, SampleSour
     }
     if (i >= wp.nPaths) return;
     int px, py, s;
-    unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
-    float4 u = src.block(id, i, 0);
+    unsigned long long pixel;
+    unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s, &pixel);
+    float4 u = src.cameraBlock(id, i, pixel, (unsigned int)s, sc.camera.lens_radius > 0.0f);
     float imageX, imageY;
     imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
     float3 o, d;
@@ -373,9 +375,10 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
             }
             if (!emissionOnly) {
                 int px, py, s;
-                unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s);
-                float4 uA = src.block(id, i, 1u + 2u * (unsigned int)bounce);
-                float4 uB = src.block(id, i, 2u + 2u * (unsigned int)bounce);
+                unsigned long long pixel;
+                unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s, &pixel);
+                float4 uA, uB;
+                src.bounceBlocks(id, i, pixel, (unsigned int)s, (unsigned int)bounce, &uA, &uB);
                 float pickPdf;
                 int li = pickLight(sc, uB.z, &pickPdf);
                 float4 tv = ps.thr[i];
@@ -389,7 +392,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                     float imageX = 0.0f, imageY = 0.0f;
                     float4 u0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if (bounce == 0) { // only the camera ray carries differentials
-                        u0 = src.block(id, i, 0);
+                        u0 = src.cameraBlock(id, i, pixel, (unsigned int)s, sc.camera.lens_radius > 0.0f);
                         imagePosition(wp, px, py, s, u0, src.table != nullptr, &imageX, &imageY);
                     }
                     // bump / normal maps rewrite the frame: it comes back by value
@@ -631,8 +634,9 @@ struct AOPolicy {
         path = i;
         float4 po = ps.shO[i], ft = ps.thr[i], fb = ps.pend[i], fn = ps.shD[i];
         int px, py, s;
-        unsigned long long id = sampleIdOf(*sc, wp, i, &px, &py, &s);
-        float2 u = src.aoPair(id, i, a);
+        unsigned long long pixel;
+        unsigned long long id = sampleIdOf(*sc, wp, i, &px, &py, &s, &pixel);
+        float2 u = src.aoPair(id, i, pixel, (unsigned int)s, a);
         if (!src.table) { // the reference stratifies the AO directions on a root x root grid
             float sub = 1.0f / (float)wp.aoRoot;
             u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
@@ -877,7 +881,7 @@ struct gb_context {
     bool commOwned = false;
     int commRanks = 0;
     bool wideFits = false;  // the 4-wide walk's stack fits in shared memory for this scene
-    int traceMode = GB_TRACE_WIDE;
+    int traceMode = GB_TRACE_PAIR;
     // launch geometry of the traversal kernels, keyed by kernel function: depends on the kernel, the
     // stack size of the uploaded scene and the tuning only (invalidated by gb_upload_scene / gb_set_tuning)
     std::vector<std::pair<const void*, int>> gridCache;
@@ -2153,6 +2157,10 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
     src.table = nullptr;
     src.rowFloats = 0;
     src.key = make_uint2((unsigned int)p->seed, (unsigned int)(p->seed >> 32));
+    src.spp = (unsigned int)sppTotal;
+    src.root = (unsigned int)root;
+    src.invSpp = 1.0f / (float)sppTotal;
+    src.invRoot = 1.0f / (float)root;
     GB_CUDA(cudaEventRecord(ctx->evStart, ctx->stream));
     // waves: whole rows x a slice of the sample indices, at most maxWavePaths paths
     int sppChunk = p->spp_end - p->spp_begin;
@@ -2215,6 +2223,8 @@ int gb_li(gb_context* ctx, const float* samples, size_t n, size_t row_floats, fl
         src.table = d_s + off * row_floats;
         src.rowFloats = (unsigned int)row_floats;
         src.key = make_uint2(0, 0);
+        src.spp = src.root = 0u;
+        src.invSpp = src.invRoot = 0.0f;
         rc = runWave(ctx, wp, src, method, false);
         if (rc == GB_OK) {
             k_copy_L<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->ps, (unsigned int)cnt, d_out + 3 * off);
@@ -2417,7 +2427,7 @@ int gb_set_tuning(gb_context* ctx, const int* values, int n) {
 
 int gb_set_trace_mode(gb_context* ctx, int mode) {
     if (!ctx) return gb::failWith(GB_ERR_INVALID, "null argument");
-    if (mode != GB_TRACE_WIDE && mode != GB_TRACE_EXACT) return gb::failWith(GB_ERR_INVALID, "unknown trace mode");
+    if (mode != GB_TRACE_WIDE && mode != GB_TRACE_PAIR) return gb::failWith(GB_ERR_INVALID, "unknown trace mode");
     ctx->traceMode = mode;
     return GB_OK;
 }
@@ -2425,7 +2435,7 @@ int gb_set_trace_mode(gb_context* ctx, int mode) {
 int gb_get_trace_mode(gb_context* ctx, int* mode) {
     if (!ctx || !mode) return gb::failWith(GB_ERR_INVALID, "null argument");
     // what the kernels actually run: a scene too deep for the wide walk's shared-memory stack is walked pair-wise
-    *mode = ctx->traceMode == GB_TRACE_WIDE && (!ctx->haveScene || ctx->wideFits) ? GB_TRACE_WIDE : GB_TRACE_EXACT;
+    *mode = ctx->traceMode == GB_TRACE_WIDE && (!ctx->haveScene || ctx->wideFits) ? GB_TRACE_WIDE : GB_TRACE_PAIR;
     return GB_OK;
 }
 

@@ -37,10 +37,52 @@ struct Philox {
 // path tracing bounce b: block 1 + 2b = light component, light u0, light u1, bsdf component
 //                        block 2 + 2b = bsdf u0, bsdf u1, pick light, (spare)
 // ambient occlusion ray a: pair a of blocks 1.. (two rays per block)
+// Stratification across the samples of one pixel, in counter form.  The reference fills, per pixel, every 1-D
+// dimension with sample_per_pixel jittered strata and every 2-D dimension with a root x root jittered grid, then
+// shuffles each dimension independently so that the samples of the pixel see the strata in random order
+// (Sampler::requestSamples, stratifiedUniform1D / 2D, shuffle: src/GoblinSampler.cpp:108-197,276-333).  A table per
+// pixel does not exist here: sample s of a pixel takes stratum pi(s), pi a pseudo-random permutation of [0, spp)
+// keyed by (seed, pixel, dimension), and the Philox value becomes the jitter inside that stratum.  The permutation is
+// Kensler's hash-based `permute` (Correlated Multi-Jittered Sampling, Pixar TM 13-01): a cycle-walking bijection on
+// the next power of two.  Same estimator, same expectation; what it buys is the reference's variance per sample.
+__host__ __device__ __forceinline__ unsigned int permuteIndex(unsigned int i, unsigned int l, unsigned int p) {
+    unsigned int w = l - 1u;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8; i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1; i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11; i *= 0x74dcb303u;
+        i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+__host__ __device__ __forceinline__ unsigned int strataKey(unsigned int k0, unsigned int k1, unsigned long long pixel, unsigned int dim) {
+    unsigned int h = k0 ^ (k1 * 0x9E3779B1u) ^ ((unsigned int)pixel * 0x85EBCA6Bu) ^ ((unsigned int)(pixel >> 32) * 0xC2B2AE35u) ^
+                     (dim * 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+// dimension numbers: 5 per bounce (light component, light position, BSDF component, BSDF direction, light pick),
+// then the lens and the ambient-occlusion rays
+enum { DIM_LIGHT_COMP = 0, DIM_LIGHT_UV = 1, DIM_BSDF_COMP = 2, DIM_BSDF_UV = 3, DIM_PICK = 4, DIM_PER_BOUNCE = 5,
+       DIM_LENS = 0x10000, DIM_AO = 0x20000 };
+#define GB_ONE_MINUS_EPS 0.99999994f
+
 struct SampleSource {
     const float* table; // explicit rows or nullptr
     unsigned int rowFloats;
     uint2 key;
+    // samples per pixel of the whole job and its square root (0 = no stratification: explicit rows, 1 spp)
+    unsigned int spp, root;
+    float invSpp, invRoot;
     __device__ __forceinline__ float4 block(unsigned long long sampleId, unsigned int path, unsigned int blk) const {
         if (table) {
             const float* row = table + (size_t)path * rowFloats;
@@ -54,14 +96,52 @@ struct SampleSource {
         uint4 r = Philox::gen(key, make_uint4((unsigned int)sampleId, (unsigned int)(sampleId >> 32), blk, 0u));
         return make_float4(Philox::u01(r.x), Philox::u01(r.y), Philox::u01(r.z), Philox::u01(r.w));
     }
-    // ambient occlusion: ray a of a camera sample
-    __device__ __forceinline__ float2 aoPair(unsigned long long sampleId, unsigned int path, unsigned int a) const {
+    __device__ __forceinline__ bool stratified() const { return !table && spp > 1u; }
+    // jitter u -> a point of stratum pi(s) of spp strata
+    __device__ __forceinline__ float strat1(float u, unsigned long long pixel, unsigned int s, unsigned int dim) const {
+        const unsigned int k = permuteIndex(s, spp, strataKey(key.x, key.y, pixel, dim));
+        return fminf(((float)k + u) * invSpp, GB_ONE_MINUS_EPS);
+    }
+    // jitter (u0, u1) -> a point of cell pi(s) of the root x root grid
+    __device__ __forceinline__ void strat2(float* u0, float* u1, unsigned long long pixel, unsigned int s, unsigned int dim) const {
+        const unsigned int k = permuteIndex(s, spp, strataKey(key.x, key.y, pixel, dim));
+        const unsigned int cy = k / root, cx = k - cy * root;
+        *u0 = fminf(((float)cx + *u0) * invRoot, GB_ONE_MINUS_EPS);
+        *u1 = fminf(((float)cy + *u1) * invRoot, GB_ONE_MINUS_EPS);
+    }
+    // block 0 of a camera sample: image jitter (its strata are laid out by imagePosition) and the lens sample
+    __device__ __forceinline__ float4 cameraBlock(unsigned long long sampleId, unsigned int path, unsigned long long pixel,
+        unsigned int s, bool lens) const {
+        float4 u = block(sampleId, path, 0);
+        if (lens && stratified()) strat2(&u.z, &u.w, pixel, s, DIM_LENS);
+        return u;
+    }
+    // the seven numbers of bounce b: (light component, light u0, u1, BSDF component) and (BSDF u0, u1, light pick)
+    __device__ __forceinline__ void bounceBlocks(unsigned long long sampleId, unsigned int path, unsigned long long pixel,
+        unsigned int s, unsigned int bounce, float4* uA, float4* uB) const {
+        *uA = block(sampleId, path, 1u + 2u * bounce);
+        *uB = block(sampleId, path, 2u + 2u * bounce);
+        if (!stratified()) return;
+        const unsigned int d0 = DIM_PER_BOUNCE * bounce;
+        uA->x = strat1(uA->x, pixel, s, d0 + DIM_LIGHT_COMP);
+        strat2(&uA->y, &uA->z, pixel, s, d0 + DIM_LIGHT_UV);
+        uA->w = strat1(uA->w, pixel, s, d0 + DIM_BSDF_COMP);
+        strat2(&uB->x, &uB->y, pixel, s, d0 + DIM_BSDF_UV);
+        uB->z = strat1(uB->z, pixel, s, d0 + DIM_PICK);
+    }
+    // ambient occlusion: ray a of a camera sample; the caller places the pair in cell a of the pixel's aoRoot x aoRoot
+    // grid of directions, this sub-stratifies the cell over the samples of the pixel as the reference does
+    // (stratifiedUniform2D(buffer, n): n strata x sample_per_pixel sub-strata)
+    __device__ __forceinline__ float2 aoPair(unsigned long long sampleId, unsigned int path, unsigned long long pixel,
+        unsigned int s, unsigned int a) const {
         if (table) {
             const float* row = table + (size_t)path * rowFloats;
             return make_float2(row[4 + 2 * a], row[4 + 2 * a + 1]);
         }
         uint4 r = Philox::gen(key, make_uint4((unsigned int)sampleId, (unsigned int)(sampleId >> 32), 1u + (a >> 1), 0u));
-        return (a & 1) ? make_float2(Philox::u01(r.z), Philox::u01(r.w)) : make_float2(Philox::u01(r.x), Philox::u01(r.y));
+        float2 u = (a & 1) ? make_float2(Philox::u01(r.z), Philox::u01(r.w)) : make_float2(Philox::u01(r.x), Philox::u01(r.y));
+        if (stratified()) strat2(&u.x, &u.y, pixel, s, DIM_AO + a);
+        return u;
     }
 };
 

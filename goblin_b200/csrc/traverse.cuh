@@ -4,13 +4,16 @@
 // (src/GoblinBVH.cpp:189-280: near child first by dirIsNeg[axis], far child
 // pushed, leaves tested as they are reached, t <= maxt accepted), so hit ids and
 // distances equal the CPU build's.  How it is walked is B200-shaped:
-//   * WIDE (the default): 128-byte 4-wide nodes (wide_node.h) -- two binary levels
-//     per step, fetched as 8 x 128-bit read-only loads, four independent slab tests
-//     per step, children visited in the reference's order;
-//   * !WIDE: "pair nodes", one 64-byte record per interior node with BOTH child
-//     boxes (4 x 128-bit loads, two box tests per step).  This is the walk whose
-//     box-test count equals the reference's exactly: the STATS instantiation
-//     (gb_get_counters, the roofline's N_node) and GB_TRACE_EXACT run it;
+//   * !WIDE (the default): "pair nodes", one 64-byte record per interior node with
+//     BOTH child boxes (two 256-bit loads = two 32-byte sectors, two box tests per
+//     step).  This is the walk whose box-test count equals the reference's exactly:
+//     its STATS instantiation feeds gb_get_counters and the roofline's N_node;
+//   * WIDE (GB_TRACE_WIDE): 128-byte 4-wide nodes (wide_node.h) -- two binary levels
+//     per step, four slab tests per step, children visited in the reference's order.
+//     Built because the dependent-fetch chain looked like the limiter; measured 8 - 18 %
+//     SLOWER than the pair walk on every scene: it tests ~30 % more boxes,
+//     and the kernels are bound by issue slots and L1 gather wavefronts, both of which
+//     scale with boxes tested, not by the latency of the chain;
 //   * the far children's entry distances ride on the stack (8-byte entries in a
 //     shared-memory column per thread) and are re-checked against the shrunk
 //     maxt when popped -- exactly the box test the reference evaluates at pop
@@ -81,8 +84,25 @@ __device__ __forceinline__ bool rootTest(float4 n0, float4 n1, float3 o, float3 
         nz ? n0.z : n1.y, o, inv, mint, maxt, &t);
 }
 
+// bits 0..2: dirIsNeg[axis]; bit 3: some component is +-0 (the ordered slab test must decide, wide_node.h)
 __device__ __forceinline__ unsigned int signBits(float3 d) {
-    return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u) |
+           ((d.x == 0.0f) | (d.y == 0.0f) | (d.z == 0.0f) ? NEG_ZERO_COMPONENT : 0u);
+}
+
+// A box stored as the reference's node words (n0 = bmin.xyz, bmax.x; n1 = bmax.yz, ..) against a ray: the ordered
+// form when the ray has a zero direction component, the min / max form otherwise.  `ordered` is warp-divergent only
+// in the presence of such rays.
+__device__ __forceinline__ bool boxTest(float4 n0, float4 n1, float3 o, float3 inv, unsigned int neg, float mint, float maxt,
+    float* tEntry) {
+#if GB_SLAB_MINMAX
+    if (!(neg & NEG_ZERO_COMPONENT)) {
+        return slabMinMax(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o.x, o.y, o.z, inv.x, inv.y, inv.z, mint, maxt, tEntry);
+    }
+#endif
+    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+    return slabOrdered(nx ? n0.w : n0.x, ny ? n1.x : n0.y, nz ? n1.y : n0.z, nx ? n0.x : n0.w, ny ? n0.y : n1.x,
+        nz ? n0.z : n1.y, o.x, o.y, o.z, inv.x, inv.y, inv.z, mint, maxt, tEntry);
 }
 
 // Policy interface (all members __device__):
@@ -305,6 +325,8 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                         const float4* p = pairs + 8 * (size_t)cur;
                         const Sector sa = ldgSector(p), sb = ldgSector(p + 2), sc4 = ldgSector(p + 4), sd = ldgSector(p + 6);
                         const float4 a0 = sa.lo, a1 = sa.hi, b0 = sb.lo, b1 = sb.hi, c0 = sc4.lo, c1 = sc4.hi, d0 = sd.lo, d1 = sd.hi;
+                        // the ordered form for all four (measured: the min / max form with its zero-component fallback
+                        // doubles the code of this stage and is 15 % slower here; the pair walk below gains 3 - 6 % from it)
                         const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
                         float t0, t1, t2, t3;
 #define GB_WIDE_BOX(n0, n1, tt)                                                                                   \
@@ -330,12 +352,11 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     const Sector s01 = ldgSector(p), s23 = ldgSector(p + 2);
                     const float4 q0 = s01.lo, q1 = s01.hi, q2 = s23.lo;
                     const uint4 q3 = make_uint4(__float_as_uint(s23.hi.x), __float_as_uint(s23.hi.y), __float_as_uint(s23.hi.z), __float_as_uint(s23.hi.w));
-                    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
                     float tL, tR;
-                    const bool hitL = slabNoBranch(nx ? q0.w : q0.x, ny ? q1.x : q0.y, nz ? q1.y : q0.z,
-                        nx ? q0.x : q0.w, ny ? q0.y : q1.x, nz ? q0.z : q1.y, o, inv, mint, maxt, &tL);
-                    const bool hitR = slabNoBranch(nx ? q2.y : q1.z, ny ? q2.z : q1.w, nz ? q2.w : q2.x,
-                        nx ? q1.z : q2.y, ny ? q1.w : q2.z, nz ? q2.x : q2.w, o, inv, mint, maxt, &tR);
+                    // pair record: left box = (q0.xyz | q0.w q1.xy), right box = (q1.zw q2.x | q2.yzw)
+                    const bool hitL = boxTest(q0, q1, o, inv, neg, mint, maxt, &tL);
+                    const bool hitR = boxTest(make_float4(q1.z, q1.w, q2.x, q2.y), make_float4(q2.z, q2.w, 0.0f, 0.0f), o, inv, neg,
+                        mint, maxt, &tR);
                     const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
                     const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
                     const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;

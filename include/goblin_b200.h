@@ -455,15 +455,16 @@ int gb_set_wave_paths(gb_context* ctx, size_t max_paths);
  * resident CTAs per SM (0 = as many as fit).  Results never depend on them. */
 int gb_set_tuning(gb_context* ctx, const int* values, int n);
 /* How the traversal kernels walk the reference's tree (BVH::intersect / occluded,
- * src/GoblinBVH.cpp:189-280).  GB_TRACE_WIDE (default): 4-wide nodes collapsed from the same
- * tree on the device, children visited in the reference's order -- same hit ids and distances
- * (the one exception: a ray with a zero direction component whose origin lies exactly on a plane
- * of an INTERMEDIATE node's box, where the reference's NaN comparison prunes a subtree the wide
- * walk still enters).  GB_TRACE_EXACT: the pair-node walk that evaluates every box test the
- * reference evaluates, including that case; it is also what runs while the counters are on.
- * A scene whose trees are too deep for the wide walk's shared-memory stack is always walked
- * pair-wise; gb_get_trace_mode reports what the kernels run for the uploaded scene. */
-enum { GB_TRACE_WIDE = 0, GB_TRACE_EXACT = 1 };
+ * src/GoblinBVH.cpp:189-280).  GB_TRACE_PAIR (default): pair nodes -- both children of an interior
+ * node in one 64-byte record -- with every box test the reference evaluates, in its order; it is also
+ * what runs while the counters are on.  GB_TRACE_WIDE: 4-wide nodes collapsed from the same tree on
+ * the device, children still visited in the reference's order: same hit ids and distances (the one
+ * exception: a ray with a zero direction component whose origin lies exactly on a plane of an
+ * INTERMEDIATE node's box, where the reference's NaN comparison prunes a subtree the wide walk still
+ * enters).  Measured 8 - 18 % slower than the pair walk on B200; kept as an option.  A scene whose
+ * trees are too deep for the wide walk's shared-memory stack is always walked pair-wise;
+ * gb_get_trace_mode reports what the kernels run for the uploaded scene. */
+enum { GB_TRACE_WIDE = 0, GB_TRACE_PAIR = 1, GB_TRACE_EXACT = 1 /* older name */ };
 int gb_set_trace_mode(gb_context* ctx, int mode);
 int gb_get_trace_mode(gb_context* ctx, int* mode);
 

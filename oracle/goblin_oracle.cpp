@@ -32,6 +32,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <thread>
@@ -1546,6 +1547,54 @@ void block(uint64_t seed, uint64_t sampleId, uint32_t blk, float out[4]) {
     for (int k = 0; k < 4; ++k) out[k] = Philox::u01(r[k]);
 }
 
+// The product's counter-form restatement of Sampler::requestSamples' per-pixel stratification + shuffle
+// (src/GoblinSampler.cpp:108-197; goblin_b200/csrc/shade.cuh): sample s of a pixel takes stratum pi(s) of every
+// dimension, pi = Kensler's hash permutation keyed by (seed, pixel, dimension), the Philox value is the jitter.
+uint32_t permuteIndex(uint32_t i, uint32_t l, uint32_t p) {
+    uint32_t w = l - 1u;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8; i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1; i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11; i *= 0x74dcb303u;
+        i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+uint32_t strataKey(uint64_t seed, uint64_t pixel, uint32_t dim) {
+    uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u) ^ ((uint32_t)pixel * 0x85EBCA6Bu) ^
+                 ((uint32_t)(pixel >> 32) * 0xC2B2AE35u) ^ (dim * 0x27D4EB2Fu);
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+struct Strata {
+    uint64_t seed, pixel;
+    uint32_t s, spp, root;
+    // GO_NO_STRATA=1: plain Philox values (what round 1 drew), for the variance comparison in the tests
+    bool on() const { static const bool off = std::getenv("GO_NO_STRATA") != nullptr; return spp > 1u && !off; }
+    float one(float u, uint32_t dim) const {
+        uint32_t k = permuteIndex(s, spp, strataKey(seed, pixel, dim));
+        return std::min(((float)k + u) * (1.0f / (float)spp), 0.99999994f);
+    }
+    void two(float* u0, float* u1, uint32_t dim) const {
+        uint32_t k = permuteIndex(s, spp, strataKey(seed, pixel, dim));
+        uint32_t cy = k / root, cx = k - cy * root;
+        float inv = 1.0f / (float)root;
+        *u0 = std::min(((float)cx + *u0) * inv, 0.99999994f);
+        *u1 = std::min(((float)cy + *u1) * inv, 0.99999994f);
+    }
+};
+enum { DIM_LIGHT_COMP = 0, DIM_LIGHT_UV = 1, DIM_BSDF_COMP = 2, DIM_BSDF_UV = 3, DIM_PICK = 4, DIM_PER_BOUNCE = 5,
+       DIM_LENS = 0x10000, DIM_AO = 0x20000 };
+
 unsigned threadCount(int threads) {
     if (threads > 0) return (unsigned)threads;
     return std::max(1u, std::thread::hardware_concurrency());
@@ -1596,6 +1645,12 @@ void addStats(gb_counters* out, const std::vector<Stats>& per, uint64_t samples,
 extern "C" {
 
 int go_hardware_threads(void) { return (int)threadCount(0); }
+
+// the stratum sample s of `pixel` takes in dimension `dim`, for s = 0 .. spp - 1 (tests: it must be a permutation)
+int go_strata(uint64_t seed, uint64_t pixel, uint32_t dim, uint32_t spp, uint32_t* out) {
+    for (uint32_t s = 0; s < spp; ++s) out[s] = permuteIndex(s, spp, strataKey(seed, pixel, dim));
+    return 0;
+}
 
 // Scene::intersect on a ray batch; hits as gb_hit (inst = scene instance index, prim = face index)
 int go_trace_closest(const gb_scene_desc* d, const gb_ray* rays, size_t n, gb_hit* hits, int threads,
@@ -1743,6 +1798,8 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                 uint64_t id = (uint64_t)pix * (uint64_t)sppTotal + (uint64_t)s;
                 float u0[4];
                 block(p->seed, id, 0, u0);
+                const Strata strata{p->seed, (uint64_t)pix, (uint32_t)s, (uint32_t)sppTotal, (uint32_t)root};
+                if (strata.on() && d->camera.lens_radius > 0.0f) strata.two(&u0[2], &u0[3], DIM_LENS);
                 // Sampler::requestSamples' image stratification (src/GoblinSampler.cpp:142,192-195, 290-307)
                 float sub = 1.0f / (float)root;
                 float imageX = (float)px + ((float)(s % root) + u0[0]) * sub;
@@ -1754,6 +1811,7 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                         float r4[4];
                         block(p->seed, id, 1u + ((uint32_t)a >> 1), r4);
                         float ux = (a & 1) ? r4[2] : r4[0], uy = (a & 1) ? r4[3] : r4[1];
+                        if (strata.on()) strata.two(&ux, &uy, DIM_AO + (uint32_t)a);
                         float asub = 1.0f / (float)aoRoot; // stratifiedUniform2D over the pixel's AO rays
                         uv[0] = ((float)(a % aoRoot) + ux) * asub;
                         uv[1] = ((float)(a / aoRoot) + uy) * asub;
@@ -1765,6 +1823,14 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                         block(p->seed, id, 2u + 2u * (uint32_t)bn, b4);
                         ub[0] = a4[0]; ub[1] = a4[1]; ub[2] = a4[2]; ub[3] = a4[3];
                         ub[4] = b4[0]; ub[5] = b4[1]; ub[6] = b4[2];
+                        if (strata.on()) {
+                            const uint32_t d0 = DIM_PER_BOUNCE * (uint32_t)bn;
+                            ub[0] = strata.one(ub[0], d0 + DIM_LIGHT_COMP);
+                            strata.two(&ub[1], &ub[2], d0 + DIM_LIGHT_UV);
+                            ub[3] = strata.one(ub[3], d0 + DIM_BSDF_COMP);
+                            strata.two(&ub[4], &ub[5], d0 + DIM_BSDF_UV);
+                            ub[6] = strata.one(ub[6], d0 + DIM_PICK);
+                        }
                     };
                     L = hasMask ? o.liPathMask(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, ubs, st)
                                 : o.liPath(ray, o.cameraRayDiff(imageX, imageY, u0[2], u0[3]), depth, ubs, st);

@@ -102,7 +102,19 @@ inline bool nodeTest(const gb_bvh_node& n, float3 o, float3 inv, uint32_t neg, f
         nx ? n.bmin[0] : n.bmax[0], ny ? n.bmin[1] : n.bmax[1], nz ? n.bmin[2] : n.bmax[2], o.x, o.y, o.z, inv.x, inv.y,
         inv.z, mint, maxt, &t);
 }
-inline uint32_t signs(float3 d) { return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u); }
+inline uint32_t signs(float3 d) {
+    return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u) |
+           ((d.x == 0.0f) | (d.y == 0.0f) | (d.z == 0.0f) ? NEG_ZERO_COMPONENT : 0u);
+}
+// boxTest of traverse.cuh: min / max form unless the ray has a zero direction component
+inline bool boxTest(const float lo[3], const float hi[3], float3 o, float3 inv, uint32_t neg, float mint, float maxt, float* t) {
+#if GB_SLAB_MINMAX
+    if (!(neg & NEG_ZERO_COMPONENT)) return slabMinMax(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], o.x, o.y, o.z, inv.x, inv.y, inv.z, mint, maxt, t);
+#endif
+    const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
+    return slabOrdered(nx ? hi[0] : lo[0], ny ? hi[1] : lo[1], nz ? hi[2] : lo[2], nx ? lo[0] : hi[0], ny ? lo[1] : hi[1],
+        nz ? lo[2] : hi[2], o.x, o.y, o.z, inv.x, inv.y, inv.z, mint, maxt, t);
+}
 
 struct Entry { uint32_t ref; float t; };
 
@@ -207,14 +219,10 @@ bool walk(const Tables& T, const gb_ray& ray, bool any, HitRec* hit, int* maxSp)
             }
         } else if (!(cur & REF_LEAF)) { // ---- interior stage: four box tests
             const WideNode& w = wide[cur];
-            const bool nx = neg & 1u, ny = neg & 2u, nz = neg & 4u;
             uint32_t r[4]; float t[4];
             for (int k = 0; k < 4; ++k) {
                 const WideChild& c = w.c[k];
-                const bool h = slabOrdered(nx ? c.hi[0] : c.lo[0], ny ? c.hi[1] : c.lo[1], nz ? c.hi[2] : c.lo[2],
-                    nx ? c.lo[0] : c.hi[0], ny ? c.lo[1] : c.hi[1], nz ? c.lo[2] : c.hi[2], o.x, o.y, o.z, inv.x, inv.y, inv.z,
-                    mint, maxt, &t[k]);
-                r[k] = h ? c.ref : REF_POP;
+                r[k] = boxTest(c.lo, c.hi, o, inv, neg, mint, maxt, &t[k]) ? c.ref : REF_POP;
             }
             wideVisitOrder(neg, w.c[0].meta, r[0], r[1], r[2], r[3], t[0], t[1], t[2], t[3]);
             uint32_t next = r[3]; float tn = t[3];

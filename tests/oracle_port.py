@@ -30,12 +30,20 @@ def lib():
         l.go_camera_rays.argtypes = [P, P, C.c_size_t, P]
         l.go_li.argtypes = [P, P, C.c_size_t, C.c_size_t, P, P, C.c_int, P]
         l.go_render.argtypes = [P, P, P, C.c_int, C.c_int, P, P]
+        l.go_strata.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, P]
         _lib = l
     return _lib
 
 
 def hardware_threads():
     return lib().go_hardware_threads()
+
+
+def strata(seed, pixel, dim, spp):
+    """Stratum index of every sample of a pixel in one dimension (the product's sampler, restated)."""
+    out = np.zeros(spp, dtype=np.uint32)
+    assert lib().go_strata(seed, pixel, dim, spp, out.ctypes.data) == 0
+    return out
 
 
 def _counters(c):

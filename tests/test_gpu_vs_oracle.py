@@ -33,9 +33,9 @@ def _random_rays(scene, n, seed, finite_frac=0.3):
     return np.concatenate([o, d.astype(np.float32), mint, maxt], 1).astype(np.float32)
 
 
-def _check_traces(ctx, scene, rays, modes=("wide", "exact")):
-    """Both walks of the traversal kernels (include/goblin_b200.h GB_TRACE_*): the default 4-wide one and the
-    pair-node one, bit for bit against the oracle's walk of the reference tree."""
+def _check_traces(ctx, scene, rays, modes=("pair", "wide")):
+    """Both walks of the traversal kernels (include/goblin_b200.h GB_TRACE_*): the default pair-node one and the
+    4-wide one, bit for bit against the oracle's walk of the reference tree."""
     want = op.trace_closest(scene, rays)
     want_any = op.trace_any(scene, rays)
     for mode in modes:
@@ -46,7 +46,7 @@ def _check_traces(ctx, scene, rays, modes=("wide", "exact")):
         assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), mode
         assert np.array_equal(got["eps"].view(np.uint32), want["eps"].view(np.uint32)), mode
         assert np.array_equal(ctx.trace_any(rays), want_any), mode
-    ctx.set_trace_mode("wide")
+    ctx.set_trace_mode("pair")
     return (want["inst"] >= 0).mean()
 
 
@@ -176,10 +176,13 @@ def test_bvh_depth_and_stack_limits(built):
         ctx, scene = _ctx(os.path.join(d, "grid_pt.json"))
     finally:
         del os.environ["GB_MAX_WIDE_SMEM"]
-    assert ctx.trace_mode() == "exact"
+    ctx.set_trace_mode("wide")
+    assert ctx.trace_mode() == "pair"  # asked for, but this scene's wide stack does not fit: walked pair-wise
     _check_traces(ctx, scene, _random_rays(scene, 50_000, 12, finite_frac=0.5), modes=("wide",))
     ctx.close()
     ctx, scene = _ctx(os.path.join(d, "grid_pt.json"))
+    assert ctx.trace_mode() == "pair"
+    ctx.set_trace_mode("wide")
     assert ctx.trace_mode() == "wide"
     rays = _random_rays(scene, 50_000, 13, finite_frac=0.5)
     _check_traces(ctx, scene, rays)
@@ -231,7 +234,7 @@ def test_axis_aligned_rays_nan_in_the_slab_test(built):
     assert gc["nodes_visited"] == wc["nodes_visited"] and gc["prims_tested"] == wc["prims_tested"]
     ctx.enable_counters(False)
     want_any = op.trace_any(scene, rays)
-    for mode in ("exact", "wide"):
+    for mode in ("pair", "wide"):
         # the wide walk skips the intermediate nodes' own box tests (where a NaN would make the reference prune);
         # on this batch the CPU emulation of the wide walk (tests/test_wide_walk.py) agrees with the reference
         # on every ray, so the kernel must as well

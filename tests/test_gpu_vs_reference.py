@@ -123,7 +123,7 @@ def test_reference_exported_rays_and_li(built, tmp_path, name, kind, json_name, 
         # ---- the exported batches, both walks
         want_hits = _ref_hits(want)
         seg = {"primary": slice(0, n), "bounce": slice(n, n + len(bounce)), "shadow": slice(n + len(bounce), len(batch))}
-        for mode in ("wide", "exact"):
+        for mode in ("pair", "wide"):
             ctx.set_trace_mode(mode)
             got = ctx.trace_closest(batch)
             occ = ctx.trace_any(batch)
@@ -133,7 +133,7 @@ def test_reference_exported_rays_and_li(built, tmp_path, name, kind, json_name, 
                 entry[f"{mode}.any.{what}"] = {"rays": int(agree.size), "agreement": float(agree.mean()),
                                                "occluded_fraction": float(occ[sl].mean())}
                 assert agree.mean() >= 0.99999, f"{mode}.any.{what}"
-        ctx.set_trace_mode("wide")
+        ctx.set_trace_mode("pair")
         # ---- per-sample radiance
         got_L = ctx.li(rows)
         close = np.isclose(got_L, want_L, rtol=2e-3, atol=2e-4).all(axis=1)

@@ -76,18 +76,21 @@ def test_li_ao(ao):
 
 
 def test_render_matches_reference_film(pt):
-    """go_render (Philox sampler) against the reference's own renders: 16 x 121 spp batches, the
-    per-pixel two-sample statistic must look standard normal; reference-equivalent call counts
-    per camera sample agree with what the reference's render made (linker --wrap counters)."""
+    """go_render (Philox sampler) against the reference's own renders: 16 x 256 spp batches (the batch size of the
+    reference renders behind the golden file: with smaller batches the per-pixel distributions are skewed enough --
+    a firefly raises a pixel's mean and its variance estimate together -- to pull the mean of the statistic to about
+    -0.15 .. -0.2 for ANY unbiased sampler, measured with and without the strata), the per-pixel two-sample statistic
+    must look standard normal; reference-equivalent call counts per camera sample agree with what the reference's
+    render made (linker --wrap counters)."""
     g = util.golden("tiny_film_pt.npz")
     imgs, total, calls, samples = [], None, [0, 0], 0
     for b in range(16):
-        film, counters, ref_calls = op.render(pt, seed=400 + b, spp_total=121)
+        film, counters, ref_calls = op.render(pt, seed=400 + b, spp_total=256)
         imgs.append(util.film_image(film))
         total = film.astype(np.float64) if total is None else total + film
         calls = [calls[0] + ref_calls[0], calls[1] + ref_calls[1]]
         samples += counters["camera_samples"]
-    assert samples == 16 * pt.camera_samples(121)
+    assert samples == 16 * pt.camera_samples(256)
     assert util.rel_mse(util.film_image(total), g["mean"]) < 5e-3
     t = util.film_ttest(np.stack(imgs), g)
     assert abs(t.mean()) < 0.15 and 0.8 < t.std() < 1.2, (t.mean(), t.std())
