@@ -837,8 +837,6 @@ struct gb_context {
     int device = 0;
     int numSMs = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;  // the shadow kernel of bounce b runs here, beside the extend of bounce b + 1
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool overlapTails = true;
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool haveScene = false;
@@ -868,11 +866,21 @@ struct gb_context {
     float4* film = nullptr;
     size_t filmPixels = 0;
     gb_film_desc filmDesc{};
-    // wavefront buffers
-    size_t capacity = 0;
-    PathState ps{};
-    std::vector<void*> waveAllocs;
-    unsigned int* ctr = nullptr; // (kMaxDepthCtr) x kCtrStride
+    // Wavefront buffers.  A render is cut into waves of camera samples; two "lanes" of waves run side by side on
+    // their own streams with their own path state, so that the tail of one lane's kernel (the last CTAs of a
+    // persistent grid on a mostly idle machine, a launch of a few thousand paths late in a path) is filled by the
+    // other lane's kernels.  Lane 0 runs on the context's stream.
+    struct WaveLane {
+        cudaStream_t stream = nullptr;   // lane 0: the context's stream
+        cudaStream_t stream2 = nullptr;  // the shadow kernel of bounce b runs here, beside the extend of bounce b + 1
+        cudaEvent_t evFork = nullptr, evJoin = nullptr, evDone = nullptr;
+        size_t capacity = 0;
+        PathState ps{};
+        std::vector<void*> allocs;
+        unsigned int* ctr = nullptr; // (kMaxDepthCtr) x kCtrStride
+    } lanes[2];
+    int waveLanes = 2;           // lanes a render uses (gb_set_tuning values[5]; 1 = one wave at a time)
+    cudaEvent_t evLaneStart = nullptr;
     unsigned long long* traceHead = nullptr;
     unsigned long long* stats = nullptr;
     bool statsOn = false;
@@ -926,10 +934,10 @@ void freeScene(gb_context* ctx) {
     ctx->haveScene = false;
 }
 
-void freeWave(gb_context* ctx) {
-    for (void* p : ctx->waveAllocs) cudaFree(p);
-    ctx->waveAllocs.clear();
-    ctx->capacity = 0;
+void freeWave(gb_context::WaveLane& lane) {
+    for (void* p : lane.allocs) cudaFree(p);
+    lane.allocs.clear();
+    lane.capacity = 0;
 }
 
 // Kernel-class timing: an event pair around each launch, resolved at collect time.
@@ -970,27 +978,28 @@ void collectTimes(gb_context* ctx) { // the stream must be idle
 }
 
 template <typename T>
-int waveAlloc(gb_context* ctx, T** out, size_t n) {
+int waveAlloc(gb_context::WaveLane& lane, T** out, size_t n) {
     void* p = nullptr;
     GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    ctx->waveAllocs.push_back(p);
+    lane.allocs.push_back(p);
     *out = static_cast<T*>(p);
     return GB_OK;
 }
 
-int ensureWave(gb_context* ctx, size_t paths) {
-    if (paths <= ctx->capacity) return GB_OK;
-    freeWave(ctx);
-    PathState& ps = ctx->ps;
+int ensureWave(gb_context::WaveLane& lane, size_t paths) {
+    if (paths <= lane.capacity) return GB_OK;
+    GB_CUDA(cudaStreamSynchronize(lane.stream)); // kernels of an earlier render may still use the old buffers
+    freeWave(lane);
+    PathState& ps = lane.ps;
     int rc;
-#define WA(field, type) if ((rc = waveAlloc<type>(ctx, &ps.field, paths)) != GB_OK) return rc
+#define WA(field, type) if ((rc = waveAlloc<type>(lane, &ps.field, paths)) != GB_OK) return rc
     WA(rayO, float4); WA(rayD, float4); WA(hit, float4); WA(hitId, int2); WA(thr, float4); WA(L, float4);
     WA(pend, float4); WA(shO, float4); WA(shD, float4); WA(shC, float4);
     WA(qExtend[0], unsigned int); WA(qExtend[1], unsigned int);
     WA(qMat[0], unsigned int); WA(qMat[1], unsigned int); WA(qMat[2], unsigned int); WA(qMat[3], unsigned int);
     WA(aoCount, unsigned int);
 #undef WA
-    ctx->capacity = paths;
+    lane.capacity = paths;
     return GB_OK;
 }
 
@@ -1057,13 +1066,21 @@ int gb_create(int device, gb_context** out) {
     GB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->numSMs = prop.multiProcessorCount;
     GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    GB_CUDA(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
-    GB_CUDA(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+    GB_CUDA(cudaEventCreateWithFlags(&ctx->evLaneStart, cudaEventDisableTiming));
+    for (int l = 0; l < 2; ++l) {
+        gb_context::WaveLane& lane = ctx->lanes[l];
+        if (l == 0) lane.stream = ctx->stream;
+        else GB_CUDA(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+        GB_CUDA(cudaStreamCreateWithFlags(&lane.stream2, cudaStreamNonBlocking));
+        GB_CUDA(cudaEventCreateWithFlags(&lane.evFork, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&lane.evJoin, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&lane.evDone, cudaEventDisableTiming));
+        GB_CUDA(cudaMalloc((void**)&lane.ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
+    }
+    if (const char* e = std::getenv("GB_WAVE_LANES")) ctx->waveLanes = std::atoi(e) == 1 ? 1 : 2;
     ctx->overlapTails = std::getenv("GB_NO_OVERLAP") == nullptr;
     GB_CUDA(cudaEventCreate(&ctx->evStart));
     GB_CUDA(cudaEventCreate(&ctx->evStop));
-    GB_CUDA(cudaMalloc((void**)&ctx->ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
     GB_CUDA(cudaMalloc((void**)&ctx->traceHead, 64));
     GB_CUDA(cudaMalloc((void**)&ctx->stats, S_COUNT * sizeof(unsigned long long)));
     GB_CUDA(cudaMemset(ctx->stats, 0, S_COUNT * sizeof(unsigned long long)));
@@ -1088,8 +1105,12 @@ int gb_destroy(gb_context* ctx) {
     gb_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->copyStream);
     freeScene(ctx);
-    freeWave(ctx);
-    cudaFree(ctx->ctr);
+    for (gb_context::WaveLane& lane : ctx->lanes) {
+        if (lane.stream) cudaStreamSynchronize(lane.stream);
+        if (lane.stream2) cudaStreamSynchronize(lane.stream2);
+        freeWave(lane);
+        cudaFree(lane.ctr);
+    }
     cudaFree(ctx->traceHead);
     cudaFree(ctx->stats);
     cudaStreamSynchronize(ctx->copyStream);
@@ -1104,9 +1125,15 @@ int gb_destroy(gb_context* ctx) {
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream2);
-    cudaEventDestroy(ctx->evFork);
-    cudaEventDestroy(ctx->evJoin);
+    for (int l = 0; l < 2; ++l) {
+        gb_context::WaveLane& lane = ctx->lanes[l];
+        if (lane.stream2) cudaStreamDestroy(lane.stream2);
+        if (lane.evFork) cudaEventDestroy(lane.evFork);
+        if (lane.evJoin) cudaEventDestroy(lane.evJoin);
+        if (lane.evDone) cudaEventDestroy(lane.evDone);
+        if (l > 0 && lane.stream) cudaStreamDestroy(lane.stream);
+    }
+    cudaEventDestroy(ctx->evLaneStart);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return GB_OK;
@@ -1968,27 +1995,28 @@ int gb_camera_rays(gb_context* ctx, const float* samples, size_t n, gb_ray* rays
 // One wave of the wavefront integrator: nPaths camera samples start to finish.
 // table != nullptr: explicit sample values (gb_li); the wave is then a flat
 // list of samples and the film is not touched.
-static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& src, int method, bool toFilm) {
-    PathState& ps = ctx->ps;
-    cudaStream_t st = ctx->stream;
+static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams& wp, const SampleSource& src, int method,
+    bool toFilm) {
+    PathState& ps = lane.ps;
+    cudaStream_t st = lane.stream;
     const int mode = walkMode(ctx);
     const size_t smem = traceSmem(ctx, mode);
     const int stackEntries = stackEntriesOf(ctx, mode);
     const unsigned int n = wp.nPaths;
     int rc, grid = 0;
-    GB_CUDA(cudaMemsetAsync(ctx->ctr, 0, kMaxDepthCtr * kCtrStride * sizeof(unsigned int), st));
+    GB_CUDA(cudaMemsetAsync(lane.ctr, 0, kMaxDepthCtr * kCtrStride * sizeof(unsigned int), st));
     PathState psRay = ps;
     if (method != GB_METHOD_AO) psRay.aoCount = nullptr;
     {
-        KernelTick tick(ctx, GB_K_RAYGEN);
-        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(ctx->sc, psRay, wp, src, ctx->ctr, ctx->stats);
+        KernelTick tick(ctx, GB_K_RAYGEN, st);
+        k_raygen<<<(n + 255) / 256, 256, 0, st>>>(ctx->sc, psRay, wp, src, lane.ctr, ctx->stats);
     }
     ctx->launches++;
     const int shadeGrid = ctx->numSMs * 8;
     auto extend = [&](int b, int singleBin) -> int {
-        unsigned int* c = ctx->ctr + b * kCtrStride;
+        unsigned int* c = lane.ctr + b * kCtrStride;
         const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
-        KernelTick tick(ctx, GB_K_EXTEND);
+        KernelTick tick(ctx, GB_K_EXTEND, st);
 #define GB_EXTEND(MODEV)                                                                                            \
     do {                                                                                                            \
         if ((rc = setupTraceKernel(ctx, k_extend<MODEV>, MODEV, &grid)) != GB_OK) return rc;                         \
@@ -2002,23 +2030,23 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
     if (method == GB_METHOD_AO) {
         if ((rc = extend(0, 1)) != GB_OK) return rc;
         {
-            KernelTick tick(ctx, GB_K_OTHER);
-            if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
-            else k_ao_frames<false><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, ctx->ctr);
+            KernelTick tick(ctx, GB_K_OTHER, st);
+            if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, lane.ctr);
+            else k_ao_frames<false><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, lane.ctr);
             ctx->launches++;
         }
         {
-            KernelTick tick(ctx, GB_K_AO);
+            KernelTick tick(ctx, GB_K_AO, st);
 #define GB_AO(MODEV)                                                                                                  \
     do {                                                                                                              \
         if ((rc = setupTraceKernel(ctx, k_ao<MODEV>, MODEV, &grid)) != GB_OK) return rc;                               \
-        k_ao<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, ctx->ctr, ctx->stats, stackEntries);         \
+        k_ao<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, wp, src, lane.ctr, ctx->stats, stackEntries);         \
     } while (0)
             if (mode == WALK_WIDE) GB_AO(WALK_WIDE); else if (mode == WALK_PAIR) GB_AO(WALK_PAIR); else GB_AO(WALK_STATS);
 #undef GB_AO
         }
         {
-            KernelTick tick(ctx, GB_K_OTHER);
+            KernelTick tick(ctx, GB_K_OTHER, st);
             k_ao_finish<<<(n + 255) / 256, 256, 0, st>>>(ps, wp);
         }
         ctx->launches += 2;
@@ -2035,7 +2063,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         cudaError_t joinStatus = cudaSuccess;
         auto join = [&]() {
             if (pendingJoin) {
-                const cudaError_t e = cudaStreamWaitEvent(st, ctx->evJoin, 0);
+                const cudaError_t e = cudaStreamWaitEvent(st, lane.evJoin, 0);
                 if (e != cudaSuccess) joinStatus = e;
             }
             pendingJoin = false;
@@ -2052,17 +2080,17 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             if (last && b > 0 && !ctx->sc.hasAreaLight && !ctx->sc.hasEnvLight) break;
             if ((rc = extend(b, 0)) != GB_OK) return rc;
             if (ctx->sc.hasEnvLight) { // rays that left the scene pick up the environment map
-                KernelTick tick(ctx, GB_K_SHADE);
-                k_miss<<<shadeGrid, 256, 0, st>>>(ctx->sc, ps, b == 0 ? nullptr : ps.qExtend[b & 1], ctx->ctr + b * kCtrStride, b);
+                KernelTick tick(ctx, GB_K_SHADE, st);
+                k_miss<<<shadeGrid, 256, 0, st>>>(ctx->sc, ps, b == 0 ? nullptr : ps.qExtend[b & 1], lane.ctr + b * kCtrStride, b);
                 ctx->launches++;
             }
-            unsigned int* c = ctx->ctr + b * kCtrStride;
-            unsigned int* cn = ctx->ctr + (b + 1) * kCtrStride;
+            unsigned int* c = lane.ctr + b * kCtrStride;
+            unsigned int* cn = lane.ctr + (b + 1) * kCtrStride;
             unsigned int* qn = ps.qExtend[(b + 1) & 1];
             int eo = last ? 1 : 0;
             join(); // the previous bounce's shadow kernel is done with the shadow queue and L
             {
-                KernelTick tick(ctx, GB_K_SHADE);
+                KernelTick tick(ctx, GB_K_SHADE, st);
 #define GB_SHADE(MATV, MLV) k_shade<MATV, MLV, false><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
 #define GB_SHADE_TEX(MATV) k_shade<MATV, true, true><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
                 if (ctx->sc.matTex) { // a textured material slot: the variants with the texture evaluator
@@ -2080,15 +2108,15 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
             }
             ctx->launches += ctx->hasBlinn ? 4 : 3;
             if (!last && ctx->sc.matMask) { // masks: filtered shadow / MIS traces with attenuation (mask.cuh)
-                KernelTick tick(ctx, GB_K_SHADOW);
+                KernelTick tick(ctx, GB_K_SHADOW, st);
                 k_shadow_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, c, ctx->stats);
                 if (ctx->sc.hasAreaLight | ctx->sc.hasEnvLight) k_mis_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, qn, cn, ctx->stats);
                 ctx->launches += 2;
             } else if (!last) {
-                cudaStream_t ss = overlap ? ctx->stream2 : st;
+                cudaStream_t ss = overlap ? lane.stream2 : st;
                 if (overlap) {
-                    GB_CUDA(cudaEventRecord(ctx->evFork, st));
-                    GB_CUDA(cudaStreamWaitEvent(ss, ctx->evFork, 0));
+                    GB_CUDA(cudaEventRecord(lane.evFork, st));
+                    GB_CUDA(cudaStreamWaitEvent(ss, lane.evFork, 0));
                 }
                 {
                     KernelTick tick(ctx, GB_K_SHADOW, ss);
@@ -2101,7 +2129,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
 #undef GB_SHADOW
                 }
                 if (overlap) {
-                    GB_CUDA(cudaEventRecord(ctx->evJoin, ss));
+                    GB_CUDA(cudaEventRecord(lane.evJoin, ss));
                     pendingJoin = true;
                 }
                 ctx->launches++;
@@ -2119,7 +2147,7 @@ static int runWave(gb_context* ctx, const WaveParams& wp, const SampleSource& sr
         const unsigned int warpsPerBlock = kFilmBlock / 32;
         unsigned int blocks = std::min<unsigned int>((nPix + warpsPerBlock - 1) / warpsPerBlock, (unsigned int)ctx->numSMs * 16u);
         {
-            KernelTick tick(ctx, GB_K_FILM);
+            KernelTick tick(ctx, GB_K_FILM, st);
             k_film<<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY, invExact);
         }
         ctx->launches++;
@@ -2167,11 +2195,21 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
     if ((size_t)sppChunk * width > ctx->maxWavePaths) sppChunk = std::max<int>(1, (int)(ctx->maxWavePaths / width));
     int rowsPerWave = std::max<int>(1, (int)(ctx->maxWavePaths / ((size_t)sppChunk * width)));
     rowsPerWave = std::min(rowsPerWave, height);
-    int rc = ensureWave(ctx, (size_t)rowsPerWave * width * sppChunk);
-    if (rc != GB_OK) return rc;
-    for (int s0 = p->spp_begin; s0 < p->spp_end; s0 += sppChunk) {
+    // Two lanes of waves side by side (gb_context::WaveLane): with a single wave the rows are cut in two.
+    const int nLanes = (method == GB_METHOD_PATH_TRACING || method == GB_METHOD_AO) && ctx->waveLanes > 1 && !ctx->statsOn && height > 1 ? 2 : 1;
+    if (nLanes == 2 && rowsPerWave >= height && p->spp_end - p->spp_begin <= sppChunk) rowsPerWave = (height + 1) / 2;
+    int rc = GB_OK;
+    for (int l = 0; l < nLanes; ++l) {
+        if ((rc = ensureWave(ctx->lanes[l], (size_t)rowsPerWave * width * sppChunk)) != GB_OK) return rc;
+    }
+    if (nLanes == 2) { // lane 1 starts where the context's stream is now (behind a film clear, an upload ...)
+        GB_CUDA(cudaEventRecord(ctx->evLaneStart, ctx->stream));
+        GB_CUDA(cudaStreamWaitEvent(ctx->lanes[1].stream, ctx->evLaneStart, 0));
+    }
+    int wave = 0;
+    for (int s0 = p->spp_begin; s0 < p->spp_end && rc == GB_OK; s0 += sppChunk) {
         int ns = std::min(sppChunk, p->spp_end - s0);
-        for (int y = 0; y < height; y += rowsPerWave) {
+        for (int y = 0; y < height && rc == GB_OK; y += rowsPerWave) {
             WaveParams wp;
             wp.rows = std::min(rowsPerWave, height - y);
             wp.y0 = sc.sy0 + y;
@@ -2184,9 +2222,15 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
             wp.aoSamples = ao;
             wp.aoRoot = std::max(1, (int)sqrtf((float)ao));
             wp.nPaths = (unsigned int)((size_t)wp.rows * width * ns);
-            if ((rc = runWave(ctx, wp, src, method, true)) != GB_OK) return rc;
+            rc = runWave(ctx, ctx->lanes[wave % nLanes], wp, src, method, true);
+            ++wave;
         }
     }
+    if (nLanes == 2) { // the context's stream continues when lane 1 is through, errors included
+        cudaEventRecord(ctx->lanes[1].evDone, ctx->lanes[1].stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->lanes[1].evDone, 0);
+    }
+    if (rc != GB_OK) return rc;
     GB_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
     return GB_OK;
 }
@@ -2211,7 +2255,7 @@ int gb_li(gb_context* ctx, const float* samples, size_t n, size_t row_floats, fl
     int rc = GB_OK;
     e = cudaMemcpyAsync(d_s, samples, n * row_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
     size_t chunk = std::min<size_t>(n, ctx->maxWavePaths);
-    if (e == cudaSuccess) rc = ensureWave(ctx, chunk);
+    if (e == cudaSuccess) rc = ensureWave(ctx->lanes[0], chunk);
     for (size_t off = 0; e == cudaSuccess && rc == GB_OK && off < n; off += chunk) {
         size_t cnt = std::min(chunk, n - off);
         WaveParams wp{};
@@ -2225,9 +2269,9 @@ int gb_li(gb_context* ctx, const float* samples, size_t n, size_t row_floats, fl
         src.key = make_uint2(0, 0);
         src.spp = src.root = 0u;
         src.invSpp = src.invRoot = 0.0f;
-        rc = runWave(ctx, wp, src, method, false);
+        rc = runWave(ctx, ctx->lanes[0], wp, src, method, false);
         if (rc == GB_OK) {
-            k_copy_L<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->ps, (unsigned int)cnt, d_out + 3 * off);
+            k_copy_L<<<(unsigned int)((cnt + 255) / 256), 256, 0, ctx->stream>>>(ctx->lanes[0].ps, (unsigned int)cnt, d_out + 3 * off);
             ctx->launches++;
             e = cudaGetLastError();
         }
@@ -2415,11 +2459,14 @@ int gb_reset_kernel_times(gb_context* ctx) {
 int gb_set_tuning(gb_context* ctx, const int* values, int n) {
     if (!ctx || (n && !values)) return gb::failWith(GB_ERR_INVALID, "null argument");
     unsigned int* t[4] = {&ctx->tune.refillBelow, &ctx->tune.leafBatch, &ctx->tune.levelBatch, &ctx->tune.moveFloor};
-    for (int k = 0; k < n && k < 4; ++k) {
+    for (int k = 0; k < n && k < 7; ++k) {
         if (values[k] < 0 || values[k] > 33) return gb::failWith(GB_ERR_INVALID, "tuning value out of range");
+        if (k >= 4) continue;
         *t[k] = (unsigned int)values[k];
     }
     if (n > 4) ctx->blocksPerSM = values[4];
+    if (n > 5) ctx->waveLanes = values[5] == 1 ? 1 : 2;
+    if (n > 6) ctx->overlapTails = values[6] != 0;
     ctx->sc.tune = ctx->tune;
     ctx->gridCache.clear();
     return GB_OK;

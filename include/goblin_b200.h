@@ -450,9 +450,12 @@ int gb_reset_kernel_times(gb_context* ctx);
 /* Upper bound on the camera samples in flight per wave of the wavefront
  * integrator (path-state memory ~ 200 B per path). */
 int gb_set_wave_paths(gb_context* ctx, size_t max_paths);
-/* Warp-scheduling knobs of the traversal kernels, for experiments: values[0..3] =
- * refill-below, leaf batch, level batch, move floor (lanes, 0..33); values[4] =
- * resident CTAs per SM (0 = as many as fit).  Results never depend on them. */
+/* Execution knobs, for experiments: values[0..3] = warp scheduling of the traversal kernels
+ * (refill-below, leaf batch, level batch, move floor; lanes, 0..33); values[4] = resident CTAs
+ * per SM (0 = as many as fit); values[5] = wave lanes of a render (2 = two waves side by side
+ * on their own streams, the default; 1 = one wave at a time); values[6] = run the shadow kernel
+ * of a bounce beside the next extend kernel (1, default) or in line (0).  Results never depend
+ * on them beyond the order of float additions into the film. */
 int gb_set_tuning(gb_context* ctx, const int* values, int n);
 /* How the traversal kernels walk the reference's tree (BVH::intersect / occluded,
  * src/GoblinBVH.cpp:189-280).  GB_TRACE_PAIR (default): pair nodes -- both children of an interior
