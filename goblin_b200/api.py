@@ -150,7 +150,7 @@ EXPORTS = [
     "gb_reset_kernel_times", "gb_set_wave_paths", "gb_set_tuning", "gb_upload_bytes",
     "gb_set_trace_mode", "gb_get_trace_mode", "gb_upload_scene_async",
     "gb_comm_init_all", "gb_comm_unique_id", "gb_comm_init_rank", "gb_comm_attach", "gb_comm_destroy", "gb_comm_size",
-    "gb_film_allreduce", "gb_film_allreduce_all", "gb_nccl_version",
+    "gb_film_allreduce", "gb_film_allreduce_all", "gb_nccl_version", "gb_debug_stack_violation",
 ]
 COMM_ID_BYTES = 128
 
@@ -230,6 +230,7 @@ def lib():
         l.gb_film_allreduce.argtypes = [C.c_void_p]
         l.gb_film_allreduce_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         l.gb_nccl_version.argtypes = [C.POINTER(C.c_int)]
+        l.gb_debug_stack_violation.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         l.gb_set_trace_mode.argtypes = [C.c_void_p, C.c_int]
         l.gb_get_trace_mode.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _lib = l
@@ -515,6 +516,11 @@ class Context:
     def film_allreduce(self):
         """Sum the device film over all ranks, in place, asynchronously on the context's stream."""
         check(lib().gb_film_allreduce(self._h))
+
+    def debug_stack_violation(self):
+        out = (C.c_int * 4)()
+        check(lib().gb_debug_stack_violation(self._h, out))
+        return list(out)
 
     def set_trace_mode(self, mode):
         """"pair" (default: pair nodes, every box test of the reference; "exact" is its older name) or

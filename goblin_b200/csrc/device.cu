@@ -200,7 +200,7 @@ k_trace(DeviceScene sc, const gb_ray* __restrict__ rays, unsigned long long n, g
     TracePolicy<ANY> pol{rays, hits, occluded, &sc};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
-    persistentTrace<ANY, STATS, WIDE>(sc, pol, n, head, s_stack, s_ray, ts, &done);
+    persistentTrace<ANY, STATS, WIDE>(sc, pol, n, head, s_stack, s_ray, ts, &done, stackEntries);
     flushStats<ANY, STATS>(stats, done, ts);
 }
 
@@ -286,7 +286,7 @@ k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, u
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
     persistentTrace<false, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_EXTEND],
-        reinterpret_cast<unsigned long long*>(ctr + C_EXTEND_HEAD), s_stack, s_ray, ts, &done);
+        reinterpret_cast<unsigned long long*>(ctr + C_EXTEND_HEAD), s_stack, s_ray, ts, &done, stackEntries);
     flushStats<false, STATS>(stats, done, ts);
 }
 
@@ -322,7 +322,7 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
     persistentTrace<true, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_SHADOW],
-        reinterpret_cast<unsigned long long*>(ctr + C_SHADOW_HEAD), s_stack, s_ray, ts, &done);
+        reinterpret_cast<unsigned long long*>(ctr + C_SHADOW_HEAD), s_stack, s_ray, ts, &done, stackEntries);
     flushStats<true, STATS>(stats, done, ts);
 }
 
@@ -377,8 +377,18 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 int px, py, s;
                 unsigned long long pixel;
                 unsigned long long id = sampleIdOf(sc, wp, i, &px, &py, &s, &pixel);
+                // which of the bounce's dimensions this material and the scene's lights can read at all: light position only
+                // with area / image lights and a BSDF that is not a delta, its component only with mesh emitters, the BSDF
+                // component for glass (and masks), its direction for Lambert / Blinn, the light pick with several lights
+                unsigned int need = sc.nLights > 1u ? 1u << DIM_PICK : 0u;
+                if (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) {
+                    need |= 1u << DIM_BSDF_UV;
+                    if (sc.hasAreaLight | sc.hasEnvLight) need |= 1u << DIM_LIGHT_UV;
+                    if (ML) need |= 1u << DIM_LIGHT_COMP;
+                }
+                if (MAT == GB_MAT_TRANSPARENT || TEX) need |= 1u << DIM_BSDF_COMP;
                 float4 uA, uB;
-                src.bounceBlocks(id, i, pixel, (unsigned int)s, (unsigned int)bounce, &uA, &uB);
+                src.bounceBlocks(id, i, pixel, (unsigned int)s, (unsigned int)bounce, need, &uA, &uB);
                 float pickPdf;
                 int li = pickLight(sc, uB.z, &pickPdf);
                 float4 tv = ps.thr[i];
@@ -668,7 +678,7 @@ k_ao(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, unsigned int
     unsigned int done = 0;
     const unsigned long long n = (unsigned long long)ctr[C_MAT0] * (unsigned long long)wp.aoSamples;
     persistentTrace<true, STATS, WIDE>(sc, pol, n, reinterpret_cast<unsigned long long*>(ctr + C_AO_HEAD), s_stack, s_ray,
-        ts, &done);
+        ts, &done, stackEntries);
     flushStats<true, STATS>(stats, done, ts);
 }
 
@@ -2484,6 +2494,19 @@ int gb_get_trace_mode(gb_context* ctx, int* mode) {
     // what the kernels actually run: a scene too deep for the wide walk's shared-memory stack is walked pair-wise
     *mode = ctx->traceMode == GB_TRACE_WIDE && (!ctx->haveScene || ctx->wideFits) ? GB_TRACE_WIDE : GB_TRACE_PAIR;
     return GB_OK;
+}
+
+int gb_debug_stack_violation(gb_context* ctx, int* out4) {
+    if (!ctx || !out4) return gb::failWith(GB_ERR_INVALID, "null argument");
+#if GB_DEBUG_STACK
+    GB_CUDA(cudaSetDevice(ctx->device));
+    GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaMemcpyFromSymbol(out4, gb::g_stackViolation, 4 * sizeof(int)));
+    return GB_OK;
+#else
+    out4[0] = out4[1] = out4[2] = out4[3] = -1; // not a debug build
+    return GB_OK;
+#endif
 }
 
 int gb_upload_bytes(gb_context* ctx, size_t* bytes) {

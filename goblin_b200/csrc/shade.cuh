@@ -116,18 +116,20 @@ struct SampleSource {
         if (lens && stratified()) strat2(&u.z, &u.w, pixel, s, DIM_LENS);
         return u;
     }
-    // the seven numbers of bounce b: (light component, light u0, u1, BSDF component) and (BSDF u0, u1, light pick)
+    // the seven numbers of bounce b: (light component, light u0, u1, BSDF component) and (BSDF u0, u1, light pick).
+    // `need`: the dimensions the caller's material / lights can read (bit = DIM_*); a dimension nothing reads is left
+    // as the plain Philox value -- unobservable, and each permutation costs ~50 integer instructions per path.
     __device__ __forceinline__ void bounceBlocks(unsigned long long sampleId, unsigned int path, unsigned long long pixel,
-        unsigned int s, unsigned int bounce, float4* uA, float4* uB) const {
+        unsigned int s, unsigned int bounce, unsigned int need, float4* uA, float4* uB) const {
         *uA = block(sampleId, path, 1u + 2u * bounce);
         *uB = block(sampleId, path, 2u + 2u * bounce);
         if (!stratified()) return;
         const unsigned int d0 = DIM_PER_BOUNCE * bounce;
-        uA->x = strat1(uA->x, pixel, s, d0 + DIM_LIGHT_COMP);
-        strat2(&uA->y, &uA->z, pixel, s, d0 + DIM_LIGHT_UV);
-        uA->w = strat1(uA->w, pixel, s, d0 + DIM_BSDF_COMP);
-        strat2(&uB->x, &uB->y, pixel, s, d0 + DIM_BSDF_UV);
-        uB->z = strat1(uB->z, pixel, s, d0 + DIM_PICK);
+        if (need & (1u << DIM_LIGHT_COMP)) uA->x = strat1(uA->x, pixel, s, d0 + DIM_LIGHT_COMP);
+        if (need & (1u << DIM_LIGHT_UV)) strat2(&uA->y, &uA->z, pixel, s, d0 + DIM_LIGHT_UV);
+        if (need & (1u << DIM_BSDF_COMP)) uA->w = strat1(uA->w, pixel, s, d0 + DIM_BSDF_COMP);
+        if (need & (1u << DIM_BSDF_UV)) strat2(&uB->x, &uB->y, pixel, s, d0 + DIM_BSDF_UV);
+        if (need & (1u << DIM_PICK)) uB->z = strat1(uB->z, pixel, s, d0 + DIM_PICK);
     }
     // ambient occlusion: ray a of a camera sample; the caller places the pair in cell a of the pixel's aoRoot x aoRoot
     // grid of directions, this sub-stratifies the cell over the samples of the pixel as the reference does

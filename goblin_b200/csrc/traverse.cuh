@@ -60,13 +60,40 @@ __device__ __forceinline__ Sector ldgSector(const float4* p) {
 
 // Per-thread columns in shared memory: entry k of thread t lives at [k * blockDim.x + t],
 // so a warp's pushes / pops are contiguous.
+// GB_DEBUG_STACK=1 (debug builds, tools/build_variants.sh): every stack access is bounds-checked against the
+// column height the host sized from the trees; the first violation is recorded in g_stackViolation (kind, index,
+// limit, block) and the access is dropped.  gb_debug_stack_violation reads it back.
+#ifndef GB_DEBUG_STACK
+#define GB_DEBUG_STACK 0
+#endif
+#if GB_DEBUG_STACK
+__device__ int g_stackViolation[4] = {0, 0, 0, 0};
+#endif
 struct TravStack {
     uint2* base;
     unsigned int stride;
+#if GB_DEBUG_STACK
+    int limit;
+    __device__ __forceinline__ bool bad(int kind, int k) const {
+        if (k >= 0 && k < limit) return false;
+        if (atomicCAS(&g_stackViolation[0], 0, kind) == 0) {
+            g_stackViolation[1] = k; g_stackViolation[2] = limit; g_stackViolation[3] = (int)blockIdx.x;
+        }
+        return true;
+    }
+#endif
     __device__ __forceinline__ void put(int k, unsigned int ref, float tmin) {
+#if GB_DEBUG_STACK
+        if (bad(1, k)) return;
+#endif
         base[k * stride] = make_uint2(ref, __float_as_uint(tmin));
     }
-    __device__ __forceinline__ uint2 get(int k) const { return base[k * stride]; }
+    __device__ __forceinline__ uint2 get(int k) const {
+#if GB_DEBUG_STACK
+        if (bad(2, k)) return make_uint2(REF_NONE, 0u);
+#endif
+        return base[k * stride];
+    }
 };
 
 // The reference's ordered slab test on sign-selected bounds, without early returns (wide_node.h).
@@ -115,10 +142,15 @@ __device__ __forceinline__ bool boxTest(float4 n0, float4 n1, float3 o, float3 i
 // while a lane is inside an instance).
 template <bool ANY, bool STATS, bool WIDE, typename Policy>
 __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& pol, unsigned long long n,
-    unsigned long long* head, uint2* s_stack, float* s_ray, TraceStats& ts, unsigned int* raysDone) {
+    unsigned long long* head, uint2* s_stack, float* s_ray, TraceStats& ts, unsigned int* raysDone, int stackEntries) {
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31;
+#if GB_DEBUG_STACK
+    TravStack st{s_stack + threadIdx.x, blockDim.x, stackEntries};
+#else
     TravStack st{s_stack + threadIdx.x, blockDim.x};
+    (void)stackEntries;
+#endif
     float* wr = s_ray + threadIdx.x;
     const unsigned int ws = blockDim.x;
 
@@ -371,7 +403,23 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                         cur = hitN ? nearRef : (hitF ? farRef : REF_POP);
                     }
                 }
-                // ---- pop stage: one entry per trip for every lane that needs one
+                // ---- pop stage
+#if defined(GB_POP_LANE_LOOP) && GB_POP_LANE_LOOP
+                // every lane that needs an entry pops until it holds a node or its level is exhausted (a divergent loop)
+                if (have && !fin) {
+                    while (cur == REF_POP) {
+                        if (sp > spFloor) {
+                            const uint2 e = st.get(--sp);
+                            if (STATS) ts.nodes++;
+                            if (__uint_as_float(e.y) < maxt) cur = e.x;
+                        } else {
+                            cur = REF_NONE;
+                            if (level == 1 && spFloor == 0 && instNext >= instEnd) fin = true;
+                        }
+                    }
+                }
+#else
+                // one entry per trip for every lane that needs one
                 while (__any_sync(FULL, have && !fin && cur == REF_POP)) {
                     if (have && !fin && cur == REF_POP) {
                         if (sp > spFloor) {
@@ -384,9 +432,15 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             // its top-level leaf and on the top-level stack: the ray ends here, no
                             // level change needed
                             if (level == 1 && spFloor == 0 && instNext >= instEnd) fin = true;
+#if defined(GB_POP_END_WORLD) && GB_POP_END_WORLD
+                            // round 1's dropped variant: also end world-space rays here.  Kept behind a
+                            // macro for the fault hunt of tools/fault_hunt.sh; never part of a shipped build.
+                            if (level == 0) fin = true;
+#endif
                         }
                     }
                 }
+#endif
             }
             const unsigned int busy = __ballot_sync(FULL, have && !fin);
             if (busy == 0) break;

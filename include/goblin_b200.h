@@ -471,6 +471,10 @@ enum { GB_TRACE_WIDE = 0, GB_TRACE_PAIR = 1, GB_TRACE_EXACT = 1 /* older name */
 int gb_set_trace_mode(gb_context* ctx, int mode);
 int gb_get_trace_mode(gb_context* ctx, int* mode);
 
+/* Debug builds (GB_DEBUG_STACK=1): the first out-of-range access of a traversal stack column, as
+ * (kind 1 = push / 2 = pop, index, column height, block); all zero = none.  Other builds: all -1. */
+int gb_debug_stack_violation(gb_context* ctx, int* out4);
+
 const char* gb_last_error(void);
 const char* gb_version(void);
 
