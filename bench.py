@@ -507,8 +507,9 @@ def main():
     # ---- end to end through the C ABI with host buffers: scene upload (H2D) + render + film download (D2H)
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 20))
     host_film = np.zeros(1, np.float32)
-    for i in range(2 if e2e_steps else 0):
-        ctx.upload_scene(scene)
+    for i in range(2 if e2e_steps else 0):  # warm both scene slots of the asynchronous path (their arenas are allocated on first use)
+        ctx.upload_scene_async(scene)
+        ctx.synchronize()
     host_buf = np.zeros((scene.desc.film.yres, scene.desc.film.xres, 4), np.float32)
     barrier()
     torch.cuda.synchronize()
@@ -639,6 +640,9 @@ def main():
                     "frac": achieved / peak, "peak_source": peak_src,
                     "frac_of_nominal_8000": achieved / 8000.0,  # north_star quotes the 8 TB/s nominal figure as well
                     "traffic": traffic,
+                    # DRAM bytes actually moved per launch / launch time / peak: what fraction of HBM bandwidth the kernel uses.
+                    # `frac` above counts ALGORITHMIC bytes, most of which L1 / L2 serve on scenes that fit there.
+                    "dram_frac": (traffic / (avg_launch_ms * 1e-3) * 1e-9 / peak) if (traffic and avg_launch_ms > 0) else None,
                     "algorithmic_bytes_per_ray": kbytes / max(krays, 1),
                     "algorithmic_bytes_per_launch": kbytes / max(launches_per_step, 1),
                     "avg_launch_ms": avg_launch_ms, "launches_per_step": launches_per_step,

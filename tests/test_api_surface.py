@@ -135,3 +135,44 @@ def test_async_upload_pipeline_equals_synchronous_uploads(built):
         ctx.upload_scene_async(bunny)
         assert np.allclose(ctx.film_download(), ref, rtol=1e-4, atol=1e-5)
     ctx.close()
+
+
+@pytest.mark.parametrize("kind,args,json_name", [("bunny", (), "bunny_pt_small.json"),   # 163,839 nodes: the sequential scan
+                                                  ("grid", (512,), "grid_pt.json")])      # 1,048,575 nodes: the parallel scan
+def test_malformed_bvh_arrays_are_refused(built, kind, args, json_name):
+    """gb_upload_scene validates the tree it is handed before a kernel can walk it: a child index outside its
+    subtree, a node reached twice, an unreachable node, a bad axis, a leaf range beyond the primitives -- each is
+    GB_ERR_INVALID, the arrays are never read out of bounds, and the intact scene uploads again afterwards."""
+    import os
+    scene = api.Scene(os.path.join(util.gen_scene(kind, *args), json_name))
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    nodes = scene.model_nodes()
+    mesh = max((m for m in scene.models() if m.kind == 0), key=lambda m: m.node_count)
+    base, n = mesh.node_offset, mesh.node_count
+    interior = [i for i in range(base, base + min(n, 4000)) if nodes["nprims"][i] == 0]
+    deep = [i for i in range(base + n // 2, base + n // 2 + 4000) if nodes["nprims"][i] == 0]
+    leaf = next(i for i in range(base + n - 1, base, -1) if nodes["nprims"][i] > 0)
+
+    def corrupt(i, field, value):
+        old = nodes[field][i].copy()
+        nodes[field][i] = value
+        try:
+            with pytest.raises(api.GoblinError) as e:
+                ctx.upload_scene(scene)
+            assert e.value.code == 1, (i, field, value)
+        finally:
+            nodes[field][i] = old
+
+    corrupt(interior[0], "offset", n + 5)                       # root's second child beyond the array
+    corrupt(interior[3], "offset", int(nodes["offset"][interior[3]]) + 1)  # lands inside the left subtree's sibling: reached twice / unreachable
+    corrupt(interior[5], "offset", interior[5] - base)          # points back at itself (model-local index)
+    corrupt(interior[7], "axis", 3)
+    corrupt(deep[0], "offset", 1)                               # a deep node pointing at the top of the tree
+    corrupt(deep[1], "offset", n - 1 if int(nodes["offset"][deep[1]]) != n - 1 else n - 2)  # outside its own subtree
+    corrupt(leaf, "offset", mesh.tri_count)                     # leaf range beyond the triangles
+    corrupt(interior[9], "nprims", 1)                           # an interior node turned into a leaf: its subtree is unreachable
+    ctx.upload_scene(scene)                                     # intact again
+    rays = _rays(scene, 10_000, 2)
+    assert (ctx.trace_closest(rays)["inst"] >= 0).any()
+    ctx.close()
