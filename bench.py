@@ -190,8 +190,8 @@ def bench_reference(args, rank):
     last = None
     full_spp = None
     if os.path.exists(REF_TOOL) and not args.ref_budget:
-        probe = run_ref_tool(scene_json, 1)
-        if config["camera_samples_per_gpu_step"] / max(probe["camera_samples"] / max(probe["seconds"], 1e-3), 1.0) <= 8.0:
+        probe = run_ref_tool(scene_json, 4)  # 4 spp: enough work that the thread pool's start-up does not dominate the rate
+        if config["camera_samples_per_gpu_step"] / max(probe["camera_samples"] / max(probe["seconds"], 1e-3), 1.0) <= 10.0:
             full_spp = config["spp"]
     for step in range(args.warmup + args.steps):
         if full_spp:

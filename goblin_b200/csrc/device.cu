@@ -189,7 +189,15 @@ enum { WALK_WIDE = 0,   // 4-wide nodes (GB_TRACE_WIDE)
        WALK_PAIR = 1,   // pair nodes, box tests exactly where the reference evaluates them: the default
        WALK_STATS = 2 };// the pair walk with the traversal counters on
 #define GB_WALK_FLAGS(MODE) constexpr bool STATS = (MODE) == WALK_STATS, WIDE = (MODE) == WALK_WIDE
-constexpr int traceMinBlocks(int mode) { return mode == WALK_WIDE ? GB_WIDE_MIN_BLOCKS : kTraceMinBlocks; }
+// the counting walk is not timed: one CTA per SM less buys it the registers to compile without spills (k_extend<STATS>
+// spilled a predicate pair at 72 registers; see the fault hunt in DESIGN.md 4 for why no spill is left in these kernels)
+constexpr int traceMinBlocks(int mode) {
+#if defined(GB_STATS_SAME_BOUNDS) && GB_STATS_SAME_BOUNDS // the fault hunt's control: the counting walk at 7 CTAs / SM again, spill included
+    return mode == WALK_WIDE ? GB_WIDE_MIN_BLOCKS : kTraceMinBlocks;
+#else
+    return mode == WALK_WIDE ? GB_WIDE_MIN_BLOCKS : (mode == WALK_STATS ? kTraceMinBlocks - 1 : kTraceMinBlocks);
+#endif
+}
 
 template <bool ANY, int MODE>
 __global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
@@ -702,11 +710,17 @@ __global__ void k_ao_finish(PathState ps, WaveParams wp) {
 // The inclusion test is the reference's: x0 = ceil(dx - w) <= x <= floor(dx + w)
 // clamped to the crop window; for integer x that is dx - w <= x <= dx + w.
 constexpr int kFilmBlock = 256;
+#ifndef GB_FILM_LDS
+#define GB_FILM_LDS 1
+#endif
 
 __global__ void __launch_bounds__(kFilmBlock)
 k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int radX, int radY,
     int invExact) {
     __shared__ float s_table[256];
+#if GB_FILM_LDS
+    __shared__ float4 s_stage[(kFilmBlock / 32) * 64];
+#endif
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_table[k] = __ldg(sc.filterTable + k);
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31;
@@ -747,13 +761,28 @@ k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* fi
                 }
                 const unsigned int okMask = __ballot_sync(0xffffffffu, ok);
                 const int cnt = min(32, wp.nSpp - k0);
+#if GB_FILM_LDS
+                // the 32 samples of this pass go through shared memory: two 128-bit broadcast reads per sample instead of
+                // five shuffles (the loop is bound by the shuffle / shared-memory pipe, one warp instruction per clock per SM)
+                float4* stage = s_stage + (threadIdx.x >> 5) * 64;
+                __syncwarp();
+                stage[2 * lane] = make_float4(dImageX, dImageY, 0.0f, 0.0f);
+                stage[2 * lane + 1] = make_float4(L.x, L.y, L.z, 0.0f);
+                __syncwarp();
+#endif
                 for (int j = 0; j < cnt; ++j) {
+#if GB_FILM_LDS
+                    if (!((okMask >> j) & 1u)) continue;
+                    const float4 sp = stage[2 * j], sl = stage[2 * j + 1];
+                    const float sx = sp.x, sy = sp.y, lr = sl.x, lg = sl.y, lb = sl.z;
+#else
                     const float sx = __shfl_sync(0xffffffffu, dImageX, j);
                     const float sy = __shfl_sync(0xffffffffu, dImageY, j);
                     const float lr = __shfl_sync(0xffffffffu, L.x, j);
                     const float lg = __shfl_sync(0xffffffffu, L.y, j);
                     const float lb = __shfl_sync(0xffffffffu, L.z, j);
                     if (!((okMask >> j) & 1u)) continue;
+#endif
                     if (mine && fx >= sx - wX && fx <= sx + wX && fy >= sy - wY && fy <= sy + wY) {
                         // FilterTable::evaluate: nearest lower entry of the 16 x 16 table
                         const float tx = invExact ? fabsf((fx - sx) * sX) : fabsf(16 * (fx - sx) / wX);
@@ -910,6 +939,7 @@ struct gb_context {
     bool hasMeshLight = false; // the scene has a mesh emitter: shade kernels with the GeometrySet loop
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;
+    bool syncLaunches = false; // GB_SYNC_LAUNCHES=1
     std::vector<cudaEvent_t> evPool;
     size_t evUsed = 0;
     std::vector<int> evClass; // class of event pair k (events 2k, 2k + 1)
@@ -954,8 +984,9 @@ void freeWave(gb_context::WaveLane& lane) {
 struct KernelTick {
     gb_context* ctx;
     cudaStream_t on;
+    int cls;
     bool live = false;
-    KernelTick(gb_context* c, int cls, cudaStream_t s = nullptr) : ctx(c), on(s ? s : c->stream) {
+    KernelTick(gb_context* c, int cls_, cudaStream_t s = nullptr) : ctx(c), on(s ? s : c->stream), cls(cls_) {
         if (!ctx->timingOn) return;
         if (ctx->evUsed + 2 > ctx->evPool.size()) {
             for (int k = 0; k < 2; ++k) {
@@ -969,6 +1000,10 @@ struct KernelTick {
         live = true;
     }
     ~KernelTick() {
+        if (ctx->syncLaunches) { // GB_SYNC_LAUNCHES=1 (fault hunting): wait for the launch and name the class that failed
+            const cudaError_t e = cudaStreamSynchronize(on);
+            if (e != cudaSuccess) std::fprintf(stderr, "[goblin_b200] kernel class %d failed: %s\n", cls, cudaGetErrorString(e));
+        }
         if (!live) return;
         cudaEventRecord(ctx->evPool[ctx->evUsed + 1], on);
         ctx->evUsed += 2;
@@ -1088,6 +1123,7 @@ int gb_create(int device, gb_context** out) {
         GB_CUDA(cudaMalloc((void**)&lane.ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
     }
     if (const char* e = std::getenv("GB_WAVE_LANES")) ctx->waveLanes = std::atoi(e) == 1 ? 1 : 2;
+    ctx->syncLaunches = std::getenv("GB_SYNC_LAUNCHES") != nullptr;
     ctx->overlapTails = std::getenv("GB_NO_OVERLAP") == nullptr;
     GB_CUDA(cudaEventCreate(&ctx->evStart));
     GB_CUDA(cudaEventCreate(&ctx->evStop));

@@ -176,3 +176,16 @@ def test_malformed_bvh_arrays_are_refused(built, kind, args, json_name):
     rays = _rays(scene, 10_000, 2)
     assert (ctx.trace_closest(rays)["inst"] >= 0).any()
     ctx.close()
+
+
+def test_counting_kernels_survive_the_fault_hunt(built):
+    """Regression for round 1's heisenbug ("the fault hunt"): counters-on renders and ray batches of S3 --
+    1,029 sphere / disk instances, the scene on which a dropped traversal variant faulted with `misaligned address`
+    in 11 of 12 fresh processes -- in fresh processes of the shipped library: no CUDA fault, closest- and any-hit agree."""
+    import os
+    import subprocess
+    import sys
+    tool = os.path.join(util.ROOT, "tools", "fault_hunt.py")
+    for _ in range(4):
+        out = subprocess.run([sys.executable, tool, "spheres", "1"], capture_output=True, text=True, timeout=300)
+        assert "faults 0" in out.stdout, out.stdout[-600:] + out.stderr[-600:]

@@ -4,9 +4,10 @@
 out=gpurun_out; mkdir -p $out
 for spec in bunny:k_extend:7 spheres:k_extend:14 grid:k_extend:16 field:k_extend:16 bunny_ao:k_ao:1; do
   scene=${spec%%:*}; rest=${spec#*:}; kern=${rest%%:*}; cnt=${rest#*:}
+  KSEL="regex:$kern"; [ "$kern" = "k_ao" ] && KSEL="k_ao"   # exact base name: the regex would also match k_ao_frames
   B="python bench.py --scene $scene --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-stats --no-fast-tree --tune 20,6,4,10,0,1,0"
   # skip the warm-up steps' launches (3 warm-up + 2 exclusive-pass warm-ups come before; take launches from the timed step on)
-  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:$kern -s $((cnt*3)) -c $cnt --csv --log-file $out/traffic_$scene.csv $B > $out/traffic_$scene.log 2>&1
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k $KSEL -s $((cnt*3)) -c $cnt --csv --log-file $out/traffic_$scene.csv $B > $out/traffic_$scene.log 2>&1
 done
 python - <<'PY'
 import csv, json, collections
