@@ -917,8 +917,8 @@ struct gb_context {
         PathState ps{};
         std::vector<void*> allocs;
         unsigned int* ctr = nullptr; // (kMaxDepthCtr) x kCtrStride
-    } lanes[2];
-    int waveLanes = 2;           // lanes a render uses (gb_set_tuning values[5]; 1 = one wave at a time)
+    } lanes[4];
+    int waveLanes = 2;           // lanes a render uses (gb_set_tuning values[5], 1 .. 4; 1 = one wave at a time)
     cudaEvent_t evLaneStart = nullptr;
     unsigned long long* traceHead = nullptr;
     unsigned long long* stats = nullptr;
@@ -1112,7 +1112,7 @@ int gb_create(int device, gb_context** out) {
     ctx->numSMs = prop.multiProcessorCount;
     GB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     GB_CUDA(cudaEventCreateWithFlags(&ctx->evLaneStart, cudaEventDisableTiming));
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < 4; ++l) {
         gb_context::WaveLane& lane = ctx->lanes[l];
         if (l == 0) lane.stream = ctx->stream;
         else GB_CUDA(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
@@ -1122,7 +1122,7 @@ int gb_create(int device, gb_context** out) {
         GB_CUDA(cudaEventCreateWithFlags(&lane.evDone, cudaEventDisableTiming));
         GB_CUDA(cudaMalloc((void**)&lane.ctr, kMaxDepthCtr * kCtrStride * sizeof(unsigned int)));
     }
-    if (const char* e = std::getenv("GB_WAVE_LANES")) ctx->waveLanes = std::atoi(e) == 1 ? 1 : 2;
+    if (const char* e = std::getenv("GB_WAVE_LANES")) ctx->waveLanes = std::min(4, std::max(1, std::atoi(e)));
     ctx->syncLaunches = std::getenv("GB_SYNC_LAUNCHES") != nullptr;
     ctx->overlapTails = std::getenv("GB_NO_OVERLAP") == nullptr;
     GB_CUDA(cudaEventCreate(&ctx->evStart));
@@ -1171,7 +1171,7 @@ int gb_destroy(gb_context* ctx) {
     cudaEventDestroy(ctx->evStart);
     cudaEventDestroy(ctx->evStop);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < 4; ++l) {
         gb_context::WaveLane& lane = ctx->lanes[l];
         if (lane.stream2) cudaStreamDestroy(lane.stream2);
         if (lane.evFork) cudaEventDestroy(lane.evFork);
@@ -2320,15 +2320,16 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
     int rowsPerWave = std::max<int>(1, (int)(ctx->maxWavePaths / ((size_t)sppChunk * width)));
     rowsPerWave = std::min(rowsPerWave, height);
     // Two lanes of waves side by side (gb_context::WaveLane): with a single wave the rows are cut in two.
-    const int nLanes = (method == GB_METHOD_PATH_TRACING || method == GB_METHOD_AO) && ctx->waveLanes > 1 && !ctx->statsOn && height > 1 ? 2 : 1;
-    if (nLanes == 2 && rowsPerWave >= height && p->spp_end - p->spp_begin <= sppChunk) rowsPerWave = (height + 1) / 2;
+    const int nLanes = (method == GB_METHOD_PATH_TRACING || method == GB_METHOD_AO) && !ctx->statsOn
+        ? std::max(1, std::min(std::min(ctx->waveLanes, 4), height)) : 1;
+    if (nLanes > 1 && p->spp_end - p->spp_begin <= sppChunk) rowsPerWave = std::min(rowsPerWave, (height + nLanes - 1) / nLanes);
     int rc = GB_OK;
     for (int l = 0; l < nLanes; ++l) {
         if ((rc = ensureWave(ctx->lanes[l], (size_t)rowsPerWave * width * sppChunk)) != GB_OK) return rc;
     }
-    if (nLanes == 2) { // lane 1 starts where the context's stream is now (behind a film clear, an upload ...)
+    if (nLanes > 1) { // the other lanes start where the context's stream is now (behind a film clear, an upload ...)
         GB_CUDA(cudaEventRecord(ctx->evLaneStart, ctx->stream));
-        GB_CUDA(cudaStreamWaitEvent(ctx->lanes[1].stream, ctx->evLaneStart, 0));
+        for (int l = 1; l < nLanes; ++l) GB_CUDA(cudaStreamWaitEvent(ctx->lanes[l].stream, ctx->evLaneStart, 0));
     }
     int wave = 0;
     for (int s0 = p->spp_begin; s0 < p->spp_end && rc == GB_OK; s0 += sppChunk) {
@@ -2350,9 +2351,9 @@ int gb_render(gb_context* ctx, const gb_render_params* p) {
             ++wave;
         }
     }
-    if (nLanes == 2) { // the context's stream continues when lane 1 is through, errors included
-        cudaEventRecord(ctx->lanes[1].evDone, ctx->lanes[1].stream);
-        cudaStreamWaitEvent(ctx->stream, ctx->lanes[1].evDone, 0);
+    for (int l = 1; l < nLanes; ++l) { // the context's stream continues when every lane is through, errors included
+        cudaEventRecord(ctx->lanes[l].evDone, ctx->lanes[l].stream);
+        cudaStreamWaitEvent(ctx->stream, ctx->lanes[l].evDone, 0);
     }
     if (rc != GB_OK) return rc;
     GB_CUDA(cudaEventRecord(ctx->evStop, ctx->stream));
@@ -2589,7 +2590,7 @@ int gb_set_tuning(gb_context* ctx, const int* values, int n) {
         *t[k] = (unsigned int)values[k];
     }
     if (n > 4) ctx->blocksPerSM = values[4];
-    if (n > 5) ctx->waveLanes = values[5] == 1 ? 1 : 2;
+    if (n > 5) ctx->waveLanes = std::min(4, std::max(1, values[5]));
     if (n > 6) ctx->overlapTails = values[6] != 0;
     ctx->sc.tune = ctx->tune;
     ctx->gridCache.clear();
