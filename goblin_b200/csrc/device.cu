@@ -616,7 +616,7 @@ __global__ void k_mis_mask(DeviceScene sc, PathState ps, const unsigned int* __r
 // The hit frame of every AO path, once (instead of once per occlusion ray): position + epsilon,
 // tangent, bitangent, normal go to path-state arrays the AO integrator does not otherwise use.
 template <bool TEX> // TEX: the scene has textured materials, i.e. possibly bump / normal maps
-__global__ void k_ao_frames(DeviceScene sc, PathState ps, const unsigned int* ctr) {
+__global__ void k_ao_frames(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, const unsigned int* ctr) {
     const unsigned int n = ctr[C_MAT0];
     for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         unsigned int i = __ldg(ps.qMat[0] + q);
@@ -633,7 +633,11 @@ __global__ void k_ao_frames(DeviceScene sc, PathState ps, const unsigned int* ct
         }
         ShadeFrame sf = makeFrame(fr);
         ps.shO[i] = make_float4(fr.p.x, fr.p.y, fr.p.z, 1e-3f * h.t); // Ray(fragment.getPosition(), dir, epsilon)
-        ps.thr[i] = make_float4(sf.t.x, sf.t.y, sf.t.z, 0.0f);
+        int px, py, s;
+        unsigned long long pixel;
+        sampleIdOf(sc, wp, i, &px, &py, &s, &pixel);
+        // .w: the sub-cell this camera sample takes in every AO direction's stratum (SampleSource::aoCell)
+        ps.thr[i] = make_float4(sf.t.x, sf.t.y, sf.t.z, __uint_as_float(src.aoCell(pixel, (unsigned int)s)));
         ps.pend[i] = make_float4(sf.b.x, sf.b.y, sf.b.z, 0.0f);
         ps.shD[i] = make_float4(sf.n.x, sf.n.y, sf.n.z, 0.0f);
     }
@@ -654,7 +658,7 @@ struct AOPolicy {
         int px, py, s;
         unsigned long long pixel;
         unsigned long long id = sampleIdOf(*sc, wp, i, &px, &py, &s, &pixel);
-        float2 u = src.aoPair(id, i, pixel, (unsigned int)s, a);
+        float2 u = src.aoPair(id, i, pixel, __float_as_uint(ft.w), a);
         if (!src.table) { // the reference stratifies the AO directions on a root x root grid
             float sub = 1.0f / (float)wp.aoRoot;
             u.x = ((float)(a % (unsigned int)wp.aoRoot) + u.x) * sub;
@@ -2155,8 +2159,8 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
         if ((rc = extend(0, 1)) != GB_OK) return rc;
         {
             KernelTick tick(ctx, GB_K_OTHER, st);
-            if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, lane.ctr);
-            else k_ao_frames<false><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, lane.ctr);
+            if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, wp, src, lane.ctr);
+            else k_ao_frames<false><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, wp, src, lane.ctr);
             ctx->launches++;
         }
         {

@@ -133,16 +133,32 @@ struct SampleSource {
     }
     // ambient occlusion: ray a of a camera sample; the caller places the pair in cell a of the pixel's aoRoot x aoRoot
     // grid of directions, this sub-stratifies the cell over the samples of the pixel as the reference does
-    // (stratifiedUniform2D(buffer, n): n strata x sample_per_pixel sub-strata)
+    // (stratifiedUniform2D(buffer, n): n strata x sample_per_pixel sub-strata).  One permutation per camera sample
+    // (aoCell, computed once per hit by k_ao_frames) gives the sample its sub-cell; ray a shifts it by its own hashed
+    // offset, cyclically per axis -- for every a still a bijection between the pixel's samples and the sub-cells, at a
+    // hash instead of a permutation per ray (25 rays per sample: the per-ray permutation cost 8 % of k_ao).
+    __device__ __forceinline__ unsigned int aoCell(unsigned long long pixel, unsigned int s) const {
+        if (!stratified()) return 0u;
+        const unsigned int k = permuteIndex(s, spp, strataKey(key.x, key.y, pixel, DIM_AO));
+        const unsigned int cy = k / root;
+        return (cy << 16) | (k - cy * root);
+    }
     __device__ __forceinline__ float2 aoPair(unsigned long long sampleId, unsigned int path, unsigned long long pixel,
-        unsigned int s, unsigned int a) const {
+        unsigned int cell, unsigned int a) const {
         if (table) {
             const float* row = table + (size_t)path * rowFloats;
             return make_float2(row[4 + 2 * a], row[4 + 2 * a + 1]);
         }
         uint4 r = Philox::gen(key, make_uint4((unsigned int)sampleId, (unsigned int)(sampleId >> 32), 1u + (a >> 1), 0u));
         float2 u = (a & 1) ? make_float2(Philox::u01(r.z), Philox::u01(r.w)) : make_float2(Philox::u01(r.x), Philox::u01(r.y));
-        if (stratified()) strat2(&u.x, &u.y, pixel, s, DIM_AO + a);
+        if (stratified()) {
+            const unsigned int h = strataKey(key.x, key.y, pixel, DIM_AO + 1u + a);
+            unsigned int cx = (cell & 0xffffu) + __umulhi(h, root), cy = (cell >> 16) + __umulhi(h * 0x9E3779B1u, root);
+            cx = cx >= root ? cx - root : cx;
+            cy = cy >= root ? cy - root : cy;
+            u.x = fminf(((float)cx + u.x) * invRoot, GB_ONE_MINUS_EPS);
+            u.y = fminf(((float)cy + u.y) * invRoot, GB_ONE_MINUS_EPS);
+        }
         return u;
     }
 };

@@ -1811,7 +1811,18 @@ int go_render(const gb_scene_desc* d, const gb_render_params* p, float* film, in
                         float r4[4];
                         block(p->seed, id, 1u + ((uint32_t)a >> 1), r4);
                         float ux = (a & 1) ? r4[2] : r4[0], uy = (a & 1) ? r4[3] : r4[1];
-                        if (strata.on()) strata.two(&ux, &uy, DIM_AO + (uint32_t)a);
+                        if (strata.on()) { // one permutation per camera sample, a hashed cyclic shift per AO ray (shade.cuh aoCell / aoPair)
+                            const uint32_t k = permuteIndex((uint32_t)s, (uint32_t)sppTotal, strataKey(p->seed, (uint64_t)pix, DIM_AO));
+                            const uint32_t h = strataKey(p->seed, (uint64_t)pix, DIM_AO + 1u + (uint32_t)a);
+                            uint32_t cy = k / (uint32_t)root, cx = k - cy * (uint32_t)root;
+                            cx += (uint32_t)(((uint64_t)h * (uint32_t)root) >> 32);
+                            cy += (uint32_t)(((uint64_t)(uint32_t)(h * 0x9E3779B1u) * (uint32_t)root) >> 32);
+                            if (cx >= (uint32_t)root) cx -= (uint32_t)root;
+                            if (cy >= (uint32_t)root) cy -= (uint32_t)root;
+                            const float inv = 1.0f / (float)root;
+                            ux = std::min(((float)cx + ux) * inv, 0.99999994f);
+                            uy = std::min(((float)cy + uy) * inv, 0.99999994f);
+                        }
                         float asub = 1.0f / (float)aoRoot; // stratifiedUniform2D over the pixel's AO rays
                         uv[0] = ((float)(a % aoRoot) + ux) * asub;
                         uv[1] = ((float)(a / aoRoot) + uy) * asub;

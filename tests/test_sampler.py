@@ -53,6 +53,43 @@ def test_variance_per_sample_matches_the_reference_cpu(built):
     assert abs(t.mean()) < 0.1 and 0.85 < t.std() < 1.15  # and still unbiased
 
 
+def _ao_variance_ratio(render_batch):
+    gold = util.golden("tiny_film_ao.npz")
+    nb, spp = int(gold["batches"]), int(gold["spp_per_batch"])
+    imgs = np.stack([util.film_image(render_batch(b, spp)) for b in range(24)])
+    var, ref_var = imgs.var(0, ddof=1), gold["var_of_mean"].astype(np.float64) * nb
+    lit = gold["mean"].sum(2) > 0
+    noisy = ref_var[lit].sum(1) > 1e-8  # unoccluded pixels are exactly 1 on both sides
+    return var[lit].mean() / ref_var[lit].mean(), float(np.median(var[lit].sum(1)[noisy] / ref_var[lit].sum(1)[noisy]))
+
+
+def test_ao_variance_per_sample_matches_the_reference_cpu(built):
+    """The AO integrator's 25 direction strata, sub-stratified over the samples of a pixel (stratifiedUniform2D(buffer, n),
+    src/GoblinSampler.cpp:276-307): one permutation per camera sample + a hashed cyclic shift per AO ray.  16 x 64 spp
+    reference renders behind tiny_film_ao.npz; without the sub-strata (GO_NO_STRATA) the ratio is 2.1."""
+    scene = api.Scene(util.TINY_AO)
+    mean_ratio, median_ratio = _ao_variance_ratio(lambda b, spp: op.render(scene, seed=300 + b, spp_total=spp)[0])
+    print(f"AO variance per image, product sampler / reference sampler: mean {mean_ratio:.3f}, median pixel {median_ratio:.3f}")
+    assert median_ratio <= 1.08 and mean_ratio <= 1.08
+
+
+@pytest.mark.gpu
+def test_ao_variance_per_sample_matches_the_reference_gpu(built):
+    scene = api.Scene(util.TINY_AO)
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+
+    def batch(b, spp):
+        ctx.film_clear()
+        ctx.render(seed=300 + b, spp_total=spp)
+        return ctx.film_download().copy()
+
+    mean_ratio, median_ratio = _ao_variance_ratio(batch)
+    print(f"GPU AO variance per image / reference: mean {mean_ratio:.3f}, median pixel {median_ratio:.3f}")
+    assert median_ratio <= 1.08 and mean_ratio <= 1.08
+    ctx.close()
+
+
 @pytest.mark.gpu
 def test_variance_per_sample_matches_the_reference_gpu(built):
     gold = util.golden("tiny_film_pt.npz")
