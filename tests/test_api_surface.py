@@ -189,3 +189,55 @@ def test_counting_kernels_survive_the_fault_hunt(built):
     for _ in range(4):
         out = subprocess.run([sys.executable, tool, "spheres", "1"], capture_output=True, text=True, timeout=300)
         assert "faults 0" in out.stdout, out.stdout[-600:] + out.stderr[-600:]
+
+
+def test_wave_lanes_and_shadow_overlap_do_not_change_the_film(built):
+    """gb_set_tuning values[5] / [6]: 1 .. 4 wave lanes, shadow kernel beside the next extend or in line: execution
+    detail only (the film sums the same samples in another order)."""
+    scene = api.Scene(util.gen_scene("bunny") + "/bunny_pt_small.json")
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    films = []
+    for lanes, overlap in ((1, 0), (1, 1), (2, 1), (3, 1), (4, 0)):
+        ctx.set_tuning([20, 6, 4, 10, 0, lanes, overlap])
+        ctx.film_clear()
+        ctx.render(seed=11, spp_total=16)
+        films.append(ctx.film_download().copy())
+    for f in films[1:]:
+        assert np.allclose(f, films[0], rtol=2e-4, atol=1e-5)
+    c = ctx.counters()
+    assert c["camera_samples"] == 5 * scene.camera_samples(16)
+    ctx.close()
+
+
+def test_async_upload_reports_a_bad_index_at_the_next_synchronising_call(built):
+    """A vertex index beyond the mesh is only seen by the device-side derivation: gb_upload_scene reports it at once,
+    gb_upload_scene_async at the next gb_synchronize (include/goblin_b200.h), and the context says it has no scene."""
+    scene = api.Scene(util.gen_scene("bunny") + "/bunny_pt_small.json")
+    tri = scene.tri_index()
+    mesh = max((m for m in scene.models() if m.kind == 0), key=lambda m: m.tri_count)
+    row = mesh.tri_offset + 5
+    old = tri[row, 1].copy()
+    ctx = api.Context(0)
+    ctx.upload_scene(scene)
+    tri[row, 1] = mesh.vert_count + 7
+    try:
+        with pytest.raises(api.GoblinError) as e:
+            ctx.upload_scene(scene)
+        assert e.value.code == 1 and "vertex index" in str(e.value)
+        tri[row, 1] = old
+        ctx.upload_scene(scene)
+        tri[row, 1] = mesh.vert_count + 7
+        ctx.upload_scene_async(scene)          # returns: the host-side checks cannot see it
+        with pytest.raises(api.GoblinError) as e:
+            ctx.synchronize()
+        assert e.value.code == 1 and "asynchronous upload" in str(e.value)
+        with pytest.raises(api.GoblinError) as e:   # no scene any more
+            ctx.render(seed=1, spp_total=4)
+        assert e.value.code == 4
+    finally:
+        tri[row, 1] = old
+    ctx.upload_scene(scene)
+    ctx.render(seed=1, spp_total=4)
+    assert np.isfinite(ctx.film_download()).all()
+    ctx.close()
