@@ -303,13 +303,7 @@ k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, u
 // their (already weighted) contribution to the owning path.
 struct ShadowPolicy {
     PathState ps;
-#if GB_DEBUG_FINISH
-    unsigned int n; // queue length; ps.aoCount (unused by the path tracer, zeroed before the launch) holds one "finished" flag per item
-#endif
     __device__ __forceinline__ bool fetch(unsigned long long j, float3* o, float3* d, float* mint, float* maxt) {
-#if GB_DEBUG_FINISH
-        if (j >= n) { recordViolation(3, (int)j, (int)n); *o = make3(0, 0, 0); *d = make3(0, 0, 1); *mint = 0.0f; *maxt = 0.0f; return true; }
-#endif
         float4 a = ps.shO[j], b = ps.shD[j];
         *o = make3(a.x, a.y, a.z);
         *d = make3(b.x, b.y, b.z);
@@ -318,12 +312,6 @@ struct ShadowPolicy {
         return true;
     }
     __device__ __forceinline__ void finish(bool done, unsigned long long j, bool found, const HitRec&) {
-#if GB_DEBUG_FINISH
-        if (done) {
-            if (j >= n) { recordViolation(4, (int)j, (int)n); return; }
-            if (atomicExch(ps.aoCount + j, 1u) != 0u) { recordViolation(5, (int)j, (int)n); return; }
-        }
-#endif
         if (!done || found) return;
         float4 c = ps.shC[j];
         unsigned int i = (unsigned int)__float_as_int(c.w);
@@ -338,11 +326,7 @@ __global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
 k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* stats, int stackEntries) {
     GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
-#if GB_DEBUG_FINISH
-    ShadowPolicy pol{ps, ctr[C_SHADOW]};
-#else
     ShadowPolicy pol{ps};
-#endif
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
     persistentTrace<true, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_SHADOW],
@@ -2262,9 +2246,6 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
                     GB_CUDA(cudaEventRecord(lane.evFork, st));
                     GB_CUDA(cudaStreamWaitEvent(ss, lane.evFork, 0));
                 }
-#if GB_DEBUG_FINISH
-                GB_CUDA(cudaMemsetAsync(ps.aoCount, 0, (size_t)lane.capacity * sizeof(unsigned int), ss));
-#endif
                 {
                     KernelTick tick(ctx, GB_K_SHADOW, ss);
 #define GB_SHADOW(MODEV)                                                                                      \
@@ -2636,7 +2617,7 @@ int gb_get_trace_mode(gb_context* ctx, int* mode) {
 
 int gb_debug_stack_violation(gb_context* ctx, int* out4) {
     if (!ctx || !out4) return gb::failWith(GB_ERR_INVALID, "null argument");
-#if GB_DEBUG_STACK || GB_DEBUG_FINISH
+#if GB_DEBUG_STACK
     GB_CUDA(cudaSetDevice(ctx->device));
     GB_CUDA(cudaDeviceSynchronize());
     GB_CUDA(cudaMemcpyFromSymbol(out4, gb::g_stackViolation, 4 * sizeof(int)));

@@ -66,16 +66,8 @@ __device__ __forceinline__ Sector ldgSector(const float4* p) {
 #ifndef GB_DEBUG_STACK
 #define GB_DEBUG_STACK 0
 #endif
-#ifndef GB_DEBUG_FINISH
-#define GB_DEBUG_FINISH 0 // debug builds: k_shadow checks that every queue item finishes exactly once and lies inside the queue
-#endif
-#if GB_DEBUG_STACK || GB_DEBUG_FINISH
+#if GB_DEBUG_STACK
 __device__ int g_stackViolation[4] = {0, 0, 0, 0};
-__device__ __forceinline__ void recordViolation(int kind, int a, int b) {
-    if (atomicCAS(&g_stackViolation[0], 0, kind) == 0) {
-        g_stackViolation[1] = a; g_stackViolation[2] = b; g_stackViolation[3] = (int)blockIdx.x;
-    }
-}
 #endif
 struct TravStack {
     uint2* base;
@@ -428,9 +420,6 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 }
 #else
                 // one entry per trip for every lane that needs one
-#if defined(GB_POP_END_WORLD) && GB_POP_END_WORLD == 2
-                bool endWorld = false; // fault hunt: the same variant with the ray ended just AFTER the loop instead of inside it
-#endif
                 while (__any_sync(FULL, have && !fin && cur == REF_POP)) {
                     if (have && !fin && cur == REF_POP) {
                         if (sp > spFloor) {
@@ -443,19 +432,14 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                             // its top-level leaf and on the top-level stack: the ray ends here, no
                             // level change needed
                             if (level == 1 && spFloor == 0 && instNext >= instEnd) fin = true;
-#if defined(GB_POP_END_WORLD) && GB_POP_END_WORLD == 1
+#if defined(GB_POP_END_WORLD) && GB_POP_END_WORLD
                             // round 1's dropped variant: also end world-space rays here.  Kept behind a
                             // macro for the fault hunt of tools/fault_hunt.sh; never part of a shipped build.
                             if (level == 0) fin = true;
-#elif defined(GB_POP_END_WORLD) && GB_POP_END_WORLD == 2
-                            if (level == 0) endWorld = true;
 #endif
                         }
                     }
                 }
-#if defined(GB_POP_END_WORLD) && GB_POP_END_WORLD == 2
-                if (endWorld) fin = true;
-#endif
 #endif
             }
             const unsigned int busy = __ballot_sync(FULL, have && !fin);
