@@ -654,6 +654,10 @@ def main():
                                       "with one wave lane and the shadow kernel in line (event pairs per launch); "
                                       "kernel_ms_per_step_overlapped: the same event pairs inside the timed region, where two wave "
                                       "lanes and the shadow kernels share the machine, so the classes add up to more than the step"}
+        if roofline.get("dram_frac") is not None:
+            roofline["reading"] = (f"the kernel's algorithmic bytes are served by L1 / L2 on this scene: DRAM moves {roofline['dram_frac']:.1%} of the peak, "
+                                   f"so `frac` is a throughput in HBM units (it can exceed 1), not distance to the HBM wall; the kernel is bound by "
+                                   f"SM issue slots at ~18 of 32 active lanes and by the L1 gather pipe (profiles/README.md, DESIGN.md 4)")
         if stats_failed:
             roofline.update({"achieved": None, "frac": None, "frac_of_nominal_8000": None,
                              "note": "no algorithmic bytes: the counters pass was skipped (--no-stats)" if args.no_stats
