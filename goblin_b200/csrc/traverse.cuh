@@ -44,13 +44,43 @@ constexpr int kStepsPerCheckPair = GB_STEPS_PAIR, kStepsPerCheckWide = GB_STEPS_
 // this many lanes wait for it; moveFloor = ... or when fewer lanes than this can still move
 
 // One 32-byte sector as two float4: a single 256-bit read-only load where the build allows it.
+// L1 policy (GB_NODE_HINT / GB_TRI_HINT, A/B builds): the true L1 hit rate of the node fetches is ~15 % (ncu r02i: the
+// 55 % of the 128-bit layout was the second half of a sector hitting behind the first); a ray's first ~8 pair nodes are
+// shared by most rays, its triangle records and path state are touched once.  evict_last asks L1 to keep nodes,
+// no_allocate keeps the one-touch records out of it.
+#ifndef GB_NODE_HINT
+#define GB_NODE_HINT 0 // 1: .L1::evict_last on interior records
+#endif
+#ifndef GB_TRI_HINT
+#define GB_TRI_HINT 0  // 1: .L1::no_allocate on triangle records
+#endif
 struct Sector { float4 lo, hi; };
-__device__ __forceinline__ Sector ldgSector(const float4* p) {
+#define GB_LD256_ASM(QUAL)                                                                                              \
+    asm volatile("ld.global.nc" QUAL ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                         \
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) \
+                 : "l"(p))
+__device__ __forceinline__ Sector ldgSector(const float4* p) { // interior records
     Sector r;
 #if GB_LD256
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
-                 : "l"(p));
+#if GB_NODE_HINT == 1
+    GB_LD256_ASM(".L1::evict_last");
+#else
+    GB_LD256_ASM("");
+#endif
+#else
+    r.lo = __ldg(p);
+    r.hi = __ldg(p + 1);
+#endif
+    return r;
+}
+__device__ __forceinline__ Sector ldgSectorOnce(const float4* p) { // records a ray touches once (triangles)
+    Sector r;
+#if GB_LD256
+#if GB_TRI_HINT == 1
+    GB_LD256_ASM(".L1::no_allocate");
+#else
+    GB_LD256_ASM("");
+#endif
 #else
     r.lo = __ldg(p);
     r.hi = __ldg(p + 1);
@@ -237,7 +267,7 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                 for (unsigned int k = 0; k < count; ++k) {
                     const float4* tr = sc.triRec + kTriRecVec4 * ((size_t)triBase + first + k);
 #if GB_LD256
-                    const Sector ab = ldgSector(tr);
+                    const Sector ab = ldgSectorOnce(tr);
                     const float4 a = ab.lo, b = ab.hi, c = __ldg(tr + 2);
 #else
                     const float4 a = __ldg(tr), b = __ldg(tr + 1), c = __ldg(tr + 2);
