@@ -55,7 +55,9 @@ constexpr int kMaxStack = 64;      // entries per thread; the reference's todo[6
 constexpr size_t kMaxTraceSmem = 200 * 1024;
 constexpr size_t kMaxWideSmem = 56 * 1024; // beyond this the 4-wide walk would run fewer than 4 CTAs per SM: walk pair-wise
 constexpr int kCtrStride = 16;     // counters per bounce
-// per-bounce counters; the *_HEAD cursors are 64-bit (two slots, 8-byte aligned)
+// per-bounce counters; the *_HEAD cursors are 64-bit (two slots, 8-byte aligned).  Row b holds what bounce b's kernels
+// consume, except C_SHADOW / C_SHADOW_HEAD: the shadow segments of bounce b are counted in row b + 1, next to the
+// C_EXTEND its shade kernels fill at the same time (k_shade reserves both with one 64-bit atomic)
 enum { C_EXTEND = 0, C_SHADOW = 1, C_MAT0 = 2 /* .. 5: one per GB_MAT_* */, C_EXTEND_HEAD = 6, C_SHADOW_HEAD = 8, C_AO_HEAD = 10 };
 // traversal statistics are kept apart for closest-hit and any-hit walks (S_ANY_BASE + ...)
 enum { S_RAYS_CLOSEST = 0, S_RAYS_ANY = 1, S_NODES = 2, S_PRIMS = 3, S_INSTS = 4, S_SAMPLES = 5, S_ANY_BASE = 8, S_COUNT = 16 };
@@ -335,25 +337,42 @@ k_shadow(DeviceScene sc, PathState ps, unsigned int* ctr, unsigned long long* st
 }
 
 // -------------------------------------------------------------------- shade
+// resident CTAs the Lambert / Blinn variants are compiled for: 80 registers and a 72-byte spill frame.  Measured round 2
+// (profiles/r02/call17_stdout.txt): 5 CTAs (95 registers, no spills) the same within 2 %, 7 CTAs (72 registers) 3 - 10 % slower.
+constexpr int kShadeHeavyBlocks = 6;
+
 // One bounce of PathTracer::Li (GoblinPathtracer.cpp:76-172) for the paths whose
 // hit carries material MAT.  `bounce` is the reference's loop variable; with
 // emissionOnly the kernel only resolves the pending BSDF-sampled emission
 // (the reference's trace #4 of the last iteration).
 template <int MAT, bool ML, bool TEX>
-__global__ void __launch_bounds__(kShadeBlock, (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) ? 6 : 8)
+__global__ void __launch_bounds__(kShadeBlock, (MAT == GB_MAT_LAMBERT || MAT == GB_MAT_BLINN) ? kShadeHeavyBlocks : 8)
 k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounce, int emissionOnly,
     unsigned int* ctr, unsigned int* ctrNext, unsigned int* qNext) {
     const unsigned int n = ctr[C_MAT0 + MAT];
     const unsigned int lane = threadIdx.x & 31;
-    for (unsigned int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; j0 < n; j0 += gridDim.x * blockDim.x) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    // The kernel is a chain of dependent fetches (queue entry -> path state -> instance -> triangle -> material) at 24
+    // warps per SM, and ncu puts a fifth of its stall samples on the first two links (profiles/r02/r02j_*).  The queue
+    // entries are therefore read two trips ahead: when a warp starts a trip its entry is already in a register.  Asking
+    // the next trip's path state into L2 as well (prefetch.global.L2, five lines per path) made the kernel 13 - 20 %
+    // slower on every scene (profiles/r02/call17_stdout.txt) and is not done.
+    const unsigned int jFirst = ((blockIdx.x * blockDim.x + threadIdx.x) & ~31u) + lane;
+    unsigned int iCur = jFirst < n ? __ldg(ps.qMat[MAT] + jFirst) : 0u;
+    unsigned int iNext = jFirst + stride < n ? __ldg(ps.qMat[MAT] + jFirst + stride) : 0u;
+    for (unsigned int j0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; j0 < n; j0 += stride) {
         unsigned int j = j0 + lane;
         bool alive = false;   // continues to the next extend
         bool shadow = false;  // emits a shadow segment
-        unsigned int i = 0;
+        const unsigned int i = iCur;
+        {
+            const unsigned int j2 = j + 2u * stride; // n <= 2^25 paths: no wrap-around
+            iCur = iNext;
+            iNext = j2 < n ? __ldg(ps.qMat[MAT] + j2) : 0u;
+        }
         float3 shO = make3(0, 0, 0), shD = make3(0, 0, 0), shC = make3(0, 0, 0);
         float shMint = 0.0f, shMaxt = 0.0f;
         if (j < n) {
-            i = __ldg(ps.qMat[MAT] + j);
             float4 ro = ps.rayO[i], rd = ps.rayD[i], hv = ps.hit[i];
             int2 hid = ps.hitId[i];
             HitRec h;
@@ -493,21 +512,21 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
                 }
             }
         }
-        // warp-aggregated appends: next extend queue, shadow queue
-        unsigned int mask = __ballot_sync(0xffffffffu, alive);
-        if (mask) {
-            unsigned int leader = __ffs(mask) - 1, start = 0;
-            if (lane == leader) start = atomicAdd(ctrNext + C_EXTEND, __popc(mask));
-            start = __shfl_sync(0xffffffffu, start, leader);
-            if (alive) qNext[start + __popc(mask & ((1u << lane) - 1))] = i;
-        }
-        mask = __ballot_sync(0xffffffffu, shadow);
-        if (mask) {
-            unsigned int leader = __ffs(mask) - 1, start = 0;
-            if (lane == leader) start = atomicAdd(ctr + C_SHADOW, __popc(mask));
-            start = __shfl_sync(0xffffffffu, start, leader);
+        // warp-aggregated appends to the next extend queue and to the shadow queue.  Their two counters sit side by side
+        // in the next bounce's row (C_EXTEND, C_SHADOW: one aligned 64-bit word), so one atomic reserves both ranges and the
+        // warp waits for one round trip to L2 instead of two.  Neither half can carry into the other (< 2^25 paths a wave).
+        const unsigned int aliveMask = __ballot_sync(0xffffffffu, alive);
+        const unsigned int shadowMask = __ballot_sync(0xffffffffu, shadow);
+        if (aliveMask | shadowMask) {
+            unsigned long long start = 0;
+            if (lane == 0) {
+                start = atomicAdd(reinterpret_cast<unsigned long long*>(ctrNext + C_EXTEND),
+                    (unsigned long long)__popc(aliveMask) | ((unsigned long long)__popc(shadowMask) << 32));
+            }
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if (alive) qNext[(unsigned int)start + __popc(aliveMask & ((1u << lane) - 1))] = i;
             if (shadow) {
-                unsigned int k = start + __popc(mask & ((1u << lane) - 1));
+                unsigned int k = (unsigned int)(start >> 32) + __popc(shadowMask & ((1u << lane) - 1));
                 ps.shO[k] = make_float4(shO.x, shO.y, shO.z, shMint);
                 ps.shD[k] = make_float4(shD.x, shD.y, shD.z, shMaxt);
                 ps.shC[k] = make_float4(shC.x, shC.y, shC.z, __int_as_float((int)i));
@@ -717,6 +736,9 @@ constexpr int kFilmBlock = 256;
 #ifndef GB_FILM_LDS
 #define GB_FILM_LDS 1
 #endif
+#ifndef GB_FILM_WARP
+#define GB_FILM_WARP 1 // k_film_warp for candidate windows of at most 32 pixels
+#endif
 
 __global__ void __launch_bounds__(kFilmBlock)
 k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int radX, int radY,
@@ -800,6 +822,96 @@ k_film(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* fi
             if (mine && (aW != 0.0f || aR != 0.0f || aG != 0.0f || aB != 0.0f)) {
                 atomicAdd(film + (size_t)cy * sc.xres + cx, make_float4(aR, aG, aB, aW));
             }
+        }
+    }
+}
+
+// The same gather for filters whose candidate window fits one warp ((2 ceil(wx) + 1) (2 ceil(wy) + 1) <= 32: every
+// width up to 2, the reference's defaults included).  k_film spends ~50 warp instructions per sample, most of them on
+// the inclusion test and its bookkeeping, repeated by all 32 lanes for every sample (ncu: 83 % of the SM's issue
+// slots, profiles/r02).  Here the lane that loads a sample also computes the reference's pixel range
+// [ceil(dx - w), floor(dx + w)] x [ceil(dy - w), floor(dy + w)] (GoblinFilm.cpp:66-69) once and publishes it as a 32-bit
+// mask over the warp's candidate pixels (0 for a NaN sample), so a consumer lane tests one bit.  The weights, the order
+// of the additions and therefore the film are those of k_film, bit for bit.
+template <bool INV_EXACT>
+__global__ void __launch_bounds__(kFilmBlock)
+k_film_warp(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, float4* film, int radX, int radY) {
+    __shared__ float s_table[256];
+    __shared__ float4 s_stage[(kFilmBlock / 32) * 64];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_table[k] = __ldg(sc.filterTable + k);
+    __syncthreads();
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warpsPerBlock = blockDim.x >> 5;
+    const unsigned int nPix = (unsigned int)wp.width * (unsigned int)wp.rows;
+    const int dX = 2 * radX + 1, dY = 2 * radY + 1;
+    const int rx = (int)lane % dX, ry = (int)lane / dX; // this lane's pixel inside the candidate window
+    const int cropX1 = sc.xstart + sc.xcount - 1, cropY1 = sc.ystart + sc.ycount - 1;
+    const float wX = sc.filterWidthX, wY = sc.filterWidthY;
+    const float sX = 16.0f / wX, sY = 16.0f / wY; // exact when the width is a power of two
+    float4* stage = s_stage + (threadIdx.x >> 5) * 64;
+    // the table's shared-memory address, made opaque so that it lives in a register (the compiler otherwise rebuilds
+    // it from the CTA's shared window, three instructions, at every lookup)
+    unsigned int tableAt = (unsigned int)__cvta_generic_to_shared(s_table);
+    asm volatile("" : "+r"(tableAt));
+    for (unsigned int pix = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); pix < nPix;
+         pix += gridDim.x * warpsPerBlock) {
+        const unsigned int row = pix / (unsigned int)wp.width, col = pix - row * (unsigned int)wp.width;
+        const int px = sc.sx0 + (int)col, py = wp.y0 + (int)row;
+        const int wx0 = px - radX, wy0 = py - radY; // corner of the candidate window
+        const unsigned int base = pix * (unsigned int)wp.nSpp;
+        const int cx = wx0 + rx, cy = wy0 + ry;
+        const bool mine = ry < dY && cx >= sc.xstart && cx <= cropX1 && cy >= sc.ystart && cy <= cropY1;
+        const float fx = (float)cx, fy = (float)cy;
+        float aR = 0.0f, aG = 0.0f, aB = 0.0f, aW = 0.0f;
+        for (int k0 = 0; k0 < wp.nSpp; k0 += 32) {
+            const int k = k0 + (int)lane;
+            float dImageX = 0.0f, dImageY = 0.0f;
+            float4 L = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            unsigned int inside = 0u; // candidate pixels this sample reaches
+            if (k < wp.nSpp) {
+                const unsigned int i = base + (unsigned int)k;
+                L = ps.L[i];
+                // sampleIdOf(i) without its divisions: the warp knows the pixel, the lane the sample
+                const int s = wp.sppBegin + k;
+                const unsigned long long id = ((unsigned long long)(py - sc.sy0) * (unsigned long long)wp.width + col) *
+                        (unsigned long long)wp.sppTotal + (unsigned long long)s;
+                float4 u = src.block(id, i, 0);
+                float imageX, imageY;
+                imagePosition(wp, px, py, s, u, src.table != nullptr, &imageX, &imageY);
+                dImageX = imageX - 0.5f;
+                dImageY = imageY - 0.5f;
+                if (!(L.x != L.x || L.y != L.y || L.z != L.z)) { // NaN samples are discarded, weight included
+                    // relative to the window, clipped to it (k_film's candidates are the window's pixels too)
+                    const int x0 = max((int)ceilf(dImageX - wX) - wx0, 0), x1 = min((int)floorf(dImageX + wX) - wx0, dX - 1);
+                    const int y0 = max((int)ceilf(dImageY - wY) - wy0, 0), y1 = min((int)floorf(dImageY + wY) - wy0, dY - 1);
+                    if (x0 <= x1) {
+                        const unsigned int span = ((2u << (x1 - x0)) - 1u) << x0;
+                        for (int y = y0; y <= y1; ++y) inside |= span << (y * dX);
+                    }
+                }
+            }
+            const int cnt = min(32, wp.nSpp - k0);
+            __syncwarp();
+            stage[2 * lane] = make_float4(dImageX, dImageY, __uint_as_float(inside), 0.0f);
+            stage[2 * lane + 1] = make_float4(L.x, L.y, L.z, 0.0f);
+            __syncwarp();
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const float4 sp = stage[2 * j];
+                if ((__float_as_uint(sp.z) >> lane) & 1u) {
+                    const float4 sl = stage[2 * j + 1];
+                    // FilterTable::evaluate: nearest lower entry of the 16 x 16 table
+                    const float tx = INV_EXACT ? fabsf((fx - sp.x) * sX) : fabsf(16 * (fx - sp.x) / wX);
+                    const float ty = INV_EXACT ? fabsf((fy - sp.y) * sY) : fabsf(16 * (fy - sp.y) / wY);
+                    const int ix = min((int)floorf(tx), 15), iy = min((int)floorf(ty), 15);
+                    float w;
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(tableAt + 4u * (unsigned int)(iy * 16 + ix)));
+                    aR += w * sl.x; aG += w * sl.y; aB += w * sl.z; aW += w;
+                }
+            }
+        }
+        if (mine && (aW != 0.0f || aR != 0.0f || aG != 0.0f || aB != 0.0f)) {
+            atomicAdd(film + (size_t)cy * sc.xres + cx, make_float4(aR, aG, aB, aW));
         }
     }
 }
@@ -939,7 +1051,8 @@ struct gb_context {
     size_t maxWavePaths = 32u << 20;
     TraceTuning tune{20u, 6u, 4u, 10u};
     int blocksPerSM = 0; // 0 = as many as fit
-    bool hasBlinn = false; // the scene uses a Blinn material: launch its shade kernel
+    bool generalFilm = false;    // gb_set_tuning values[7]: k_film also where k_film_warp applies (tests)
+    unsigned int matBins = 0;    // bit m: some material of the scene has type m, so shade bin m can be non-empty
     bool hasMeshLight = false; // the scene has a mesh emitter: shade kernels with the GeometrySet loop
     // optional per-kernel-class timing (CUDA event pairs on the context's stream)
     bool timingOn = false;
@@ -1754,9 +1867,10 @@ static int uploadScene(gb_context* ctx, const gb_scene_desc* d, bool async) {
         if (md.area_light >= 0) hasArea = true;
     }
     DeviceMaterial* mats = reinterpret_cast<DeviceMaterial*>(H + oMaterials);
-    bool hasBlinn = false;
+    unsigned int matBins = 0;
     for (uint32_t m = 0; m < d->n_materials; ++m) {
         const gb_material& mm = d->materials[m];
+        matBins |= 1u << mm.type;
         float tb;
         std::memcpy(&tb, &mm.type, 4);
         mats[m].kdType = make_float4(mm.kd[0], mm.kd[1], mm.kd[2], tb);
@@ -1765,7 +1879,6 @@ static int uploadScene(gb_context* ctx, const gb_scene_desc* d, bool async) {
             float fb;
             std::memcpy(&fb, &mm.fresnel, 4);
             mats[m].ktEta = make_float4(mm.k, mm.exponent, fb, mm.eta);
-            hasBlinn = true;
         } else if (mm.type == GB_MAT_MIRROR) mats[m].ktEta = make_float4(mm.k, 0.0f, 0.0f, mm.eta);
         else mats[m].ktEta = make_float4(mm.kt[0], mm.kt[1], mm.kt[2], mm.eta);
     }
@@ -1996,7 +2109,7 @@ static int uploadScene(gb_context* ctx, const gb_scene_desc* d, bool async) {
     ctx->slot = k;
     ctx->sc = sc;
     ctx->setting = d->setting;
-    ctx->hasBlinn = hasBlinn;
+    ctx->matBins = matBins;
     ctx->hasMeshLight = hasMeshLight;
     ctx->wideFits = wideFits;
     ctx->stackEntries = stackEntries;
@@ -2219,25 +2332,37 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
             join(); // the previous bounce's shadow kernel is done with the shadow queue and L
             {
                 KernelTick tick(ctx, GB_K_SHADE, st);
-#define GB_SHADE(MATV, MLV) k_shade<MATV, MLV, false><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
-#define GB_SHADE_TEX(MATV) k_shade<MATV, true, true><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn)
+#define GB_SHADE(MATV, MLV)                                                                                           \
+    do {                                                                                                              \
+        if (ctx->matBins & (1u << MATV)) {                                                                            \
+            k_shade<MATV, MLV, false><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);     \
+            ctx->launches++;                                                                                          \
+        }                                                                                                             \
+    } while (0)
+#define GB_SHADE_TEX(MATV)                                                                                            \
+    do {                                                                                                              \
+        if (ctx->matBins & (1u << MATV)) {                                                                            \
+            k_shade<MATV, true, true><<<shadeGrid, kShadeBlock, 0, st>>>(ctx->sc, ps, wp, src, b, eo, c, cn, qn);     \
+            ctx->launches++;                                                                                          \
+        }                                                                                                             \
+    } while (0)
+                // one launch per material type the scene holds (a bin nobody can land in needs no kernel)
                 if (ctx->sc.matTex) { // a textured material slot: the variants with the texture evaluator
                     GB_SHADE_TEX(GB_MAT_LAMBERT); GB_SHADE_TEX(GB_MAT_MIRROR); GB_SHADE_TEX(GB_MAT_TRANSPARENT);
-                    if (ctx->hasBlinn) GB_SHADE_TEX(GB_MAT_BLINN);
+                    GB_SHADE_TEX(GB_MAT_BLINN);
                 } else if (ctx->hasMeshLight) {
                     GB_SHADE(GB_MAT_LAMBERT, true); GB_SHADE(GB_MAT_MIRROR, true); GB_SHADE(GB_MAT_TRANSPARENT, true);
-                    if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, true);
+                    GB_SHADE(GB_MAT_BLINN, true);
                 } else {
                     GB_SHADE(GB_MAT_LAMBERT, false); GB_SHADE(GB_MAT_MIRROR, false); GB_SHADE(GB_MAT_TRANSPARENT, false);
-                    if (ctx->hasBlinn) GB_SHADE(GB_MAT_BLINN, false);
+                    GB_SHADE(GB_MAT_BLINN, false);
                 }
 #undef GB_SHADE
 #undef GB_SHADE_TEX
             }
-            ctx->launches += ctx->hasBlinn ? 4 : 3;
             if (!last && ctx->sc.matMask) { // masks: filtered shadow / MIS traces with attenuation (mask.cuh)
                 KernelTick tick(ctx, GB_K_SHADOW, st);
-                k_shadow_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, c, ctx->stats);
+                k_shadow_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, cn, ctx->stats); // row b + 1: see C_SHADOW
                 if (ctx->sc.hasAreaLight | ctx->sc.hasEnvLight) k_mis_mask<<<shadeGrid, 128, 0, st>>>(ctx->sc, ps, qn, cn, ctx->stats);
                 ctx->launches += 2;
             } else if (!last) {
@@ -2251,7 +2376,7 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
 #define GB_SHADOW(MODEV)                                                                                      \
     do {                                                                                                      \
         if ((rc = setupTraceKernel(ctx, k_shadow<MODEV>, MODEV, &grid)) != GB_OK) return rc;                   \
-        k_shadow<MODEV><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, c, ctx->stats, stackEntries);             \
+        k_shadow<MODEV><<<grid, kTraceBlock, smem, ss>>>(ctx->sc, ps, cn, ctx->stats, stackEntries); /* row b + 1 */ \
     } while (0)
                     if (mode == WALK_WIDE) GB_SHADOW(WALK_WIDE); else if (mode == WALK_PAIR) GB_SHADOW(WALK_PAIR); else GB_SHADOW(WALK_STATS);
 #undef GB_SHADOW
@@ -2276,7 +2401,12 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
         unsigned int blocks = std::min<unsigned int>((nPix + warpsPerBlock - 1) / warpsPerBlock, (unsigned int)ctx->numSMs * 16u);
         {
             KernelTick tick(ctx, GB_K_FILM, st);
-            k_film<<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY, invExact);
+            if (GB_FILM_WARP && !ctx->generalFilm && (2 * radX + 1) * (2 * radY + 1) <= 32) { // the candidate window fits one warp
+                if (invExact) k_film_warp<true><<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY);
+                else k_film_warp<false><<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY);
+            } else {
+                k_film<<<blocks, kFilmBlock, 0, st>>>(ctx->sc, ps, wp, src, ctx->film, radX, radY, invExact);
+            }
         }
         ctx->launches++;
     }
@@ -2588,7 +2718,7 @@ int gb_reset_kernel_times(gb_context* ctx) {
 int gb_set_tuning(gb_context* ctx, const int* values, int n) {
     if (!ctx || (n && !values)) return gb::failWith(GB_ERR_INVALID, "null argument");
     unsigned int* t[4] = {&ctx->tune.refillBelow, &ctx->tune.leafBatch, &ctx->tune.levelBatch, &ctx->tune.moveFloor};
-    for (int k = 0; k < n && k < 7; ++k) {
+    for (int k = 0; k < n && k < 8; ++k) {
         if (values[k] < 0 || values[k] > 33) return gb::failWith(GB_ERR_INVALID, "tuning value out of range");
         if (k >= 4) continue;
         *t[k] = (unsigned int)values[k];
@@ -2596,6 +2726,7 @@ int gb_set_tuning(gb_context* ctx, const int* values, int n) {
     if (n > 4) ctx->blocksPerSM = values[4];
     if (n > 5) ctx->waveLanes = std::min(4, std::max(1, values[5]));
     if (n > 6) ctx->overlapTails = values[6] != 0;
+    if (n > 7) ctx->generalFilm = values[7] != 0;
     ctx->sc.tune = ctx->tune;
     ctx->gridCache.clear();
     return GB_OK;

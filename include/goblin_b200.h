@@ -454,8 +454,10 @@ int gb_set_wave_paths(gb_context* ctx, size_t max_paths);
  * (refill-below, leaf batch, level batch, move floor; lanes, 0..33); values[4] = resident CTAs
  * per SM (0 = as many as fit); values[5] = wave lanes of a render (2 = two waves side by side
  * on their own streams, the default; 1 = one wave at a time); values[6] = run the shadow kernel
- * of a bounce beside the next extend kernel (1, default) or in line (0).  Results never depend
- * on them beyond the order of float additions into the film. */
+ * of a bounce beside the next extend kernel (1, default) or in line (0); values[7] = 1 keeps the
+ * general film kernel also for filter windows of at most 32 pixels, where a one-warp form exists
+ * (0, default: use it).  Results never depend on them beyond the order of float additions into
+ * the film. */
 int gb_set_tuning(gb_context* ctx, const int* values, int n);
 /* How the traversal kernels walk the reference's tree (BVH::intersect / occluded,
  * src/GoblinBVH.cpp:189-280).  GB_TRACE_PAIR (default): pair nodes -- both children of an interior

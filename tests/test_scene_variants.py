@@ -338,6 +338,15 @@ def test_gpu_matches_oracle(variant_files, v):
         assert (g[~mask] == 0).all() and (g[mask][:, 3] > 0).all()
     if v == "nolights":
         assert (g[..., :3] == 0).all() and (g[..., 3] > 0).any()
+    # the one-warp film kernel (candidate windows of at most 32 pixels: every variant but wide_gaussian) against the
+    # general one, gb_set_tuning values[7]: same weights, same order of additions per sample pixel
+    g = g.copy()
+    ctx.set_tuning([20, 6, 4, 10, 0, 2, 1, 1])
+    ctx.film_clear()
+    ctx.render(seed=12, spp_total=spp)
+    general = ctx.film_download()
+    assert np.allclose(general, g, rtol=2e-5, atol=1e-6), v
+    assert np.array_equal(general == 0, g == 0), v
     ctx.close()
 
 
