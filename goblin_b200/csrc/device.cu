@@ -246,7 +246,7 @@ struct ExtendPolicy {
     PathState ps;
     const unsigned int* queue;
     unsigned int* ctr;
-    int singleBin;
+    int fixedBin; // >= 0: every hit goes to this bin (AO; scenes with one material type), no lookup
     unsigned int path; // per lane: the path the lane's ray belongs to
     __device__ __forceinline__ bool fetch(unsigned long long j, float3* o, float3* d, float* mint, float* maxt) {
         path = queue ? __ldg(queue + j) : (unsigned int)j;
@@ -264,7 +264,7 @@ struct ExtendPolicy {
             ps.hit[path] = make_float4(h.t, h.b1, h.b2, 0.0f);
             ps.hitId[path] = make_int2(h.inst, h.prim);
             if (found) {
-                if (singleBin) bin = 0;
+                if (fixedBin >= 0) bin = fixedBin;
                 else {
                     int mat = __ldg(sc->instShade + h.inst).z;
                     bin = __float_as_int(__ldg(&sc->materials[mat].kdType).w);
@@ -288,11 +288,11 @@ struct ExtendPolicy {
 
 template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock, traceMinBlocks(MODE))
-k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int singleBin,
+k_extend(DeviceScene sc, PathState ps, const unsigned int* __restrict__ queue, unsigned int* ctr, int fixedBin,
     unsigned long long* stats, int stackEntries) {
     GB_WALK_FLAGS(MODE);
     GB_TRACE_SMEM(stackEntries);
-    ExtendPolicy pol{&sc, ps, queue, ctr, singleBin, 0u};
+    ExtendPolicy pol{&sc, ps, queue, ctr, fixedBin, 0u};
     TraceStats ts{0, 0, 0};
     unsigned int done = 0;
     persistentTrace<false, STATS, WIDE>(sc, pol, (unsigned long long)ctr[C_EXTEND],
@@ -2254,14 +2254,16 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
     }
     ctx->launches++;
     const int shadeGrid = ctx->numSMs * 8;
-    auto extend = [&](int b, int singleBin) -> int {
+    // the one bin every hit of this scene lands in, if its materials are all of one type (else -1: look it up per hit)
+    const int onlyBin = (ctx->matBins & (ctx->matBins - 1u)) == 0u && ctx->matBins ? __builtin_ctz(ctx->matBins) : -1;
+    auto extend = [&](int b, int fixedBin) -> int {
         unsigned int* c = lane.ctr + b * kCtrStride;
         const unsigned int* q = b == 0 ? nullptr : ps.qExtend[b & 1];
         KernelTick tick(ctx, GB_K_EXTEND, st);
 #define GB_EXTEND(MODEV)                                                                                            \
     do {                                                                                                            \
         if ((rc = setupTraceKernel(ctx, k_extend<MODEV>, MODEV, &grid)) != GB_OK) return rc;                         \
-        k_extend<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, singleBin, ctx->stats, stackEntries);    \
+        k_extend<MODEV><<<grid, kTraceBlock, smem, st>>>(ctx->sc, ps, q, c, fixedBin, ctx->stats, stackEntries);     \
     } while (0)
         if (mode == WALK_WIDE) GB_EXTEND(WALK_WIDE); else if (mode == WALK_PAIR) GB_EXTEND(WALK_PAIR); else GB_EXTEND(WALK_STATS);
 #undef GB_EXTEND
@@ -2269,7 +2271,7 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
         return GB_OK;
     };
     if (method == GB_METHOD_AO) {
-        if ((rc = extend(0, 1)) != GB_OK) return rc;
+        if ((rc = extend(0, 0)) != GB_OK) return rc; // AO reads the hits in path order: one bin
         {
             KernelTick tick(ctx, GB_K_OTHER, st);
             if (ctx->sc.matTex) k_ao_frames<true><<<ctx->numSMs * 8, 256, 0, st>>>(ctx->sc, ps, wp, src, lane.ctr);
@@ -2319,7 +2321,7 @@ static int runWave(gb_context* ctx, gb_context::WaveLane& lane, const WaveParams
             // the last extend only feeds the BSDF-sampled emission term; skip it when no area light exists
             const bool last = b == depth - 1;
             if (last && b > 0 && !ctx->sc.hasAreaLight && !ctx->sc.hasEnvLight) break;
-            if ((rc = extend(b, 0)) != GB_OK) return rc;
+            if ((rc = extend(b, onlyBin)) != GB_OK) return rc;
             if (ctx->sc.hasEnvLight) { // rays that left the scene pick up the environment map
                 KernelTick tick(ctx, GB_K_SHADE, st);
                 k_miss<<<shadeGrid, 256, 0, st>>>(ctx->sc, ps, b == 0 ? nullptr : ps.qExtend[b & 1], lane.ctr + b * kCtrStride, b);
