@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """GPU box, one GPU: what one rank of an N-way strong split does, for N = 1, 2, 4, 8 -- the slice [0, spp / N) of the
 sample indices of one frame, timed with CUDA events, per kernel class.  Shows where a strong split loses efficiency
-before any collective is involved.  usage: tools/strong_probe.py [scene] [frames]"""
+before any collective is involved.  usage: tools/strong_probe.py [scene] [frames] [lanes]
+(lanes: gb_set_tuning values[5], the wave lanes a render uses; default: the library's choice)"""
 import json
 import os
 import sys
@@ -14,9 +15,12 @@ from goblin_b200 import api  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "bunny"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+lanes = int(sys.argv[3]) if len(sys.argv) > 3 else None
 scene = api.Scene(bench.scene_path(name))
 ctx = api.Context(0)
 ctx.upload_scene(scene)
+if lanes is not None:
+    ctx.set_tuning([20, 6, 4, 10, 0, lanes, 1])
 spp = scene.spp_squared()
 stream = torch.cuda.ExternalStream(ctx.stream())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -45,7 +49,7 @@ for n in (1, 2, 4, 8):
     kt = ctx.kernel_times()
     ms /= frames
     base = base or ms
-    print(json.dumps({"scene": name, "split": n, "spp_slice": end, "ms_per_frame": round(ms, 3),
+    print(json.dumps({"scene": name, "lanes": lanes, "split": n, "spp_slice": end, "ms_per_frame": round(ms, 3),
                       "efficiency_vs_split1": round(base / (n * ms), 3),
                       "kernel_ms": {k: round(v[0] / frames, 3) for k, v in kt.items() if v[1]},
                       "launches_per_frame": {k: v[1] // frames for k, v in kt.items() if v[1]}}))
