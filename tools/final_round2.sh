@@ -29,5 +29,5 @@ print()
 print("reference arm:", round(ref["value"], 3), "Msamples/s,", ref["reference_step"], "; same config:", ref["config"] == json.loads(open(f"gpurun_out/bench_{tag}.json").read().strip().splitlines()[-1])["config"])
 PY
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-stats --no-fast-tree"
-$B > $out/plain_$tag.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 60 --csv --log-file $out/launches_$tag.csv $B > $out/ncu_l_$tag.log 2>&1
+$B > $out/plain_$tag.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 187 -c 61 --csv --log-file $out/launches_$tag.csv $B > $out/ncu_l_$tag.log 2>&1
 tail -n 1 $out/ncu_l_$tag.log | cut -c1-200
