@@ -24,7 +24,10 @@
 //     and pop stage; triangle tests and level changes are batched across the
 //     warp (lanes park until enough of them need the same stage);
 //   * lanes that finish a ray pull the next one from a global cursor with a
-//     warp-aggregated atomic instead of idling until the whole warp is done.
+//     warp-aggregated atomic instead of idling until the whole warp is done;
+//   * any-hit walks (occluded(): shadow and AO rays) keep the reference's box and
+//     triangle tests but not its visiting order, which cannot change their answer:
+//     left child first for every lane (GB_ANY_FIXED_ORDER).
 #pragma once
 #include "rt_core.cuh"
 #include "wide_node.h"
@@ -36,6 +39,9 @@ namespace gb {
 #endif
 #ifndef GB_STEPS_WIDE
 #define GB_STEPS_WIDE 2
+#endif
+#ifndef GB_ANY_FIXED_ORDER
+#define GB_ANY_FIXED_ORDER 1 // any-hit walks visit the left child first (0: the reference's near child first, for A/B runs)
 #endif
 // interior + pop stages between two scheduling checks
 constexpr int kStepsPerCheckPair = GB_STEPS_PAIR, kStepsPerCheckWide = GB_STEPS_WIDE;
@@ -419,6 +425,17 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                     const bool hitL = boxTest(q0, q1, o, inv, neg, mint, maxt, &tL);
                     const bool hitR = boxTest(make_float4(q1.z, q1.w, q2.x, q2.y), make_float4(q2.z, q2.w, 0.0f, 0.0f), o, inv, neg,
                         mint, maxt, &tR);
+#if GB_ANY_FIXED_ORDER
+                    // Any-hit walks (shadow, AO): "is some triangle of some reachable leaf hit inside [mint, maxt]" does not
+                    // depend on the order of the visits, and maxt never shrinks, so they always go left first.  The lanes
+                    // of a warp then agree on the order whatever their directions, which is worth more than the near
+                    // child's better odds: k_ao - 17 %, k_shadow - 6.5 % (profiles/r02/call21_stdout.txt).  The counting
+                    // instantiation keeps the reference's order, so gb_get_counters still reports the reference's tests.
+                    if (ANY && !STATS) {
+                        if (hitL & hitR) st.put(sp++, q3.y, -INFINITY);
+                        cur = hitL ? q3.x : (hitR ? q3.y : REF_POP);
+                    } else {
+#endif
                     const bool rightFirst = (neg >> (q3.z & 3u)) & 1u; // dirIsNeg[axis]
                     const unsigned int nearRef = rightFirst ? q3.y : q3.x, farRef = rightFirst ? q3.x : q3.y;
                     const bool hitN = rightFirst ? hitR : hitL, hitF = rightFirst ? hitL : hitR;
@@ -432,6 +449,9 @@ __device__ __forceinline__ void persistentTrace(const DeviceScene& sc, Policy& p
                         if (hitN & hitF) st.put(sp++, farRef, tF);
                         cur = hitN ? nearRef : (hitF ? farRef : REF_POP);
                     }
+#if GB_ANY_FIXED_ORDER
+                    }
+#endif
                 }
                 // ---- pop stage
 #if defined(GB_POP_LANE_LOOP) && GB_POP_LANE_LOOP
