@@ -366,7 +366,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
         bool shadow = false;  // emits a shadow segment
         const unsigned int i = iCur;
         {
-            const unsigned int j2 = j + 2u * stride; // n <= 2^25 paths: no wrap-around
+            const unsigned int j2 = j + 2u * stride; // a wave holds at most 2^28 paths (gb_set_wave_paths): no wrap-around
             iCur = iNext;
             iNext = j2 < n ? __ldg(ps.qMat[MAT] + j2) : 0u;
         }
@@ -514,7 +514,7 @@ k_shade(DeviceScene sc, PathState ps, WaveParams wp, SampleSource src, int bounc
         }
         // warp-aggregated appends to the next extend queue and to the shadow queue.  Their two counters sit side by side
         // in the next bounce's row (C_EXTEND, C_SHADOW: one aligned 64-bit word), so one atomic reserves both ranges and the
-        // warp waits for one round trip to L2 instead of two.  Neither half can carry into the other (< 2^25 paths a wave).
+        // warp waits for one round trip to L2 instead of two.  Neither half can carry into the other (at most 2^28 paths a wave).
         const unsigned int aliveMask = __ballot_sync(0xffffffffu, alive);
         const unsigned int shadowMask = __ballot_sync(0xffffffffu, shadow);
         if (aliveMask | shadowMask) {
